@@ -1,0 +1,107 @@
+"""Pins oracle/kg_oracle.py against the UNMODIFIED reference run in the authoring container.
+
+Skipped where /root/reference is absent (the GPU box); there the committed golden vectors
+(tests/golden/, produced from the reference by oracle/gen_golden.py) take over.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kg_oracle as O
+
+pytestmark = pytest.mark.reference
+
+
+def _ref_decode_scale(pp, kp, short, mid):
+    t = lambda a: torch.from_numpy(a[None])
+    return pp.get_skeletons_and_masks(t(kp), t(short), t(mid))
+
+
+@pytest.mark.parametrize("seed,size,cells", [(1, 128, 6), (2, 192, 14)])
+def test_decode_stages_bit_exact(reference, seed, size, cells):
+    _, pp, nms = reference
+    heads, _ = O.planted_scene(seed, size, size, cells, side=(24, 60))
+    all_ref, all_ora = [], []
+    for kp, short, mid in heads:
+        kph = np.ascontiguousarray(kp.transpose(1, 2, 0)); shh = np.ascontiguousarray(short.transpose(1, 2, 0))
+        ref_heat = pp.compute_heatmaps(kph, shh)
+        ora_heat = O.vote_heatmaps(kph, shh)
+        assert np.array_equal(ref_heat, ora_heat)
+        from scipy.ndimage import gaussian_filter
+        ref_blur = np.stack([gaussian_filter(ref_heat[:, :, i], sigma=2) for i in range(5)], -1)
+        ora_blur = O.gaussian_blur(ora_heat)
+        assert np.array_equal(ref_blur, ora_blur)
+        ref_kps = pp.get_keypoints(ref_blur, 0.004)
+        pk = O.find_peaks(ora_blur)
+        assert [k["id"] for k in ref_kps] == pk["id"].tolist()
+        assert [tuple(k["xy"]) for k in ref_kps] == list(zip(pk["x"].tolist(), pk["y"].tolist()))
+        assert [k["conf"] for k in ref_kps] == pk["conf"].tolist()
+        ref_sk = _ref_decode_scale(pp, kp, short, mid)
+        ora_sk, _, _ = O.decode_scale(kp, short, mid)
+        assert len(ref_sk) == len(ora_sk)
+        for a, b in zip(ref_sk, ora_sk):
+            assert np.array_equal(a, b)
+        all_ref.append(pp.refine_skeleton(ref_sk)); all_ora.append(O.refine_skeleton(ora_sk))
+    ref_boxes = pp.gather_skeleton(*copy.deepcopy(all_ref))
+    ora_boxes = O.gather_skeleton(*all_ora)
+    assert ref_boxes.shape == ora_boxes.shape and np.array_equal(ref_boxes, ora_boxes)
+    assert len(ora_boxes) > 0
+    r = nms.non_maximum_suppression_numpy(ref_boxes, 0.5); o = O.nms(ora_boxes, 0.5)
+    assert np.array_equal(r, o)
+
+
+def test_empty_and_edge_cases(reference):
+    _, pp, nms = reference
+    assert nms.non_maximum_suppression_numpy(np.zeros((0,)), 0.5) is None and O.nms(np.zeros((0,)), 0.5) is None
+    z = [np.zeros((c, 32, 32), np.float32) for c in (5, 10, 40)]
+    assert _ref_decode_scale(pp, *z) == [] and O.decode_scale(*z)[0] == []
+    # single keypoint near the origin + a keypoint with x == 0 ("absent" by the x>0 rule)
+    kp = np.zeros((5, 32, 32), np.float32); kp[0, 4, 0] = 1.0; kp[3, 20, 20] = 0.9; kp[1, 3, 3] = 0.8
+    ref = _ref_decode_scale(pp, kp, z[1], z[2]); ora = O.decode_scale(kp, z[1], z[2])[0]
+    assert len(ref) == len(ora) and all(np.array_equal(a, b) for a, b in zip(ref, ora))
+    assert len(pp.refine_skeleton(ref)) == len(O.refine_skeleton(ora))
+
+
+def test_box_case_table(reference):
+    _, pp, _ = reference
+    rs = np.random.RandomState(0)
+    sks = []
+    for mask in range(32):
+        sk = np.zeros((5, 3))
+        for k in range(5):
+            if mask >> k & 1:
+                sk[k] = (rs.randint(1, 60), rs.randint(0, 60), rs.uniform(0.01, 1))
+        sks.append(sk)
+    ref_keep = pp.refine_skeleton(copy.deepcopy(sks)); ora_keep = O.refine_skeleton(sks)
+    assert len(ref_keep) == len(ora_keep)
+    for sc in (1, 2, 4, 8):
+        r = pp.skeleton_to_box(copy.deepcopy(ref_keep), sc); o = O.skeleton_to_box(ora_keep, sc)
+        assert np.array_equal(np.asarray(r, np.float64), np.asarray(o, np.float64))
+
+
+def test_forward_dec_and_seg_match_reference_module(reference):
+    KGnet, _, _ = reference
+    sd = O.make_state_dict(seed=0)
+    model = KGnet.resnet50(pretrained=False).eval()
+    missing = model.load_state_dict(sd, strict=True)
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 64, 64) - 0.5
+    with torch.no_grad():
+        ref = model.forward_dec(x)
+    ora = O.forward_dec(sd, x)
+    for s in range(4):
+        for a, b in zip(ref[s], ora[s]):
+            assert torch.equal(a, b)
+    for a, b in zip(ref[4], ora[4]):
+        assert torch.equal(a, b)
+    boxes = [np.array([[4., 6., 40., 50., 0.9], [10., 10., 20., 22., 0.5], [0., 0., 2., 2., 0.1], [30., 30., 31., 31., 0.05]])]
+    with torch.no_grad():
+        rseg = model.forward_seg(ref[4], boxes)
+    oseg = O.forward_seg(sd, ora[4], boxes)
+    assert len(rseg[0][0]) == len(oseg[0][0]) == 3   # the 1x1 box is dropped (KGnet.py:253)
+    for a, b in zip(rseg[0][0], oseg[0][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(rseg[1][0], oseg[1][0]):
+        assert torch.equal(a, b)
