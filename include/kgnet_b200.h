@@ -1,0 +1,126 @@
+/*
+ * kgnet_b200 — C-ABI of the B200-native KGnet inference hot path.
+ *
+ * The reference (yijingru/KG_Instance_Segmentation) has no FFI layer: its boundary is a Python call
+ * surface.  Every entry point below names the reference function(s) (file:line, relative to the
+ * reference checkout) whose arithmetic it replaces; the Python package
+ * `kg_instance_segmentation_b200` binds them with ctypes and re-exposes the reference names
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C types only; `void* stream` is a cudaStream_t (NULL = legacy default stream);
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers;
+ *   - every function returns 0 on success or a negative kg_status; kg_last_error() returns the
+ *     message of the last failure on the calling thread;
+ *   - device entry points never allocate and never synchronise: the caller passes a workspace of
+ *     kg_*_workspace_bytes() bytes and owns all buffers.  The *_host convenience entry points
+ *     allocate, copy H2D/D2H and synchronise internally.
+ *   - all tensors are dense; activations at this boundary are fp32 NCHW exactly like the reference's
+ *     torch tensors, detections are fp64 rows [y1, x1, y2, x2, conf] like the reference's NumPy arrays.
+ */
+#ifndef KGNET_B200_H_
+#define KGNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KG_ABI_VERSION 1
+#define KG_NUM_KPS 5          /* config.py:3  */
+#define KG_NUM_EDGES 10       /* config.py:2  */
+#define KG_MAX_SCALES 4       /* test.py:105-108: c0..c3 */
+
+typedef enum kg_status {
+  KG_OK = 0,
+  KG_ERR_INVALID = -1,   /* bad argument / unsupported shape                               */
+  KG_ERR_CUDA = -2,      /* CUDA runtime / driver failure                                   */
+  KG_ERR_CAPACITY = -3,  /* a bounded device list (peaks / boxes) overflowed: raise the cap */
+  KG_ERR_STATE = -4,     /* call order violated                                             */
+  KG_ERR_WORKSPACE = -5  /* caller-provided workspace too small                             */
+} kg_status;
+
+const char* kg_last_error(void);
+int kg_abi_version(void);
+/* Compute capability of the current device as major*10+minor (100 on B200); <0 on error. */
+int kg_device_arch(void);
+
+/* Optional per-stage device timing (CUDA events recorded on the launching stream around each kernel
+ * class).  Stage ids: 0 vote, 1 blur+peak, 2 sort+group+boxes, 3 nms, >=8 network stages.
+ * kg_timing_collect synchronises the device and returns the accumulated milliseconds and launch counts
+ * since the last collect.  No reference equivalent (the reference only prints time.time(), test.py:96-98). */
+int kg_timing_enable(int on);
+int kg_timing_collect(float* ms_per_stage, int* launches_per_stage, int n_stages);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode path: Hough vote -> Gaussian blur -> peaks -> conf-sorted greedy keypoint-graph grouping
+ * -> refine -> boxes -> NMS.
+ * Replaces postprocessing.py:8-64 (compute_heatmaps / accumulate_votes / get_keypoints),
+ * :80-147 (group_skeletons / get_skeletons_and_masks), :150-261 (refine_skeleton / skeleton_to_box /
+ * gather_skeleton) and nms.py:4-53, batched over N images (the reference handles batch element 0 only).
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct kg_decode_scale {
+  const float* d_kp;     /* [N, 5, H, W]  keypoint heatmaps (sigmoid applied), KGnet.py:300-314           */
+  const float* d_short;  /* [N,10, H, W]  short offsets, channel 2i = dx, 2i+1 = dy (postprocessing.py:49) */
+  const float* d_mid;    /* [N,40, H, W]  mid offsets, directed edge m -> channels (2m, 2m+1) (:108-112)   */
+  int H, W;
+  int box_scale;         /* 1, 2, 4, 8 (postprocessing.py:256-259)                                         */
+} kg_decode_scale;
+
+typedef struct kg_decode_config {
+  int N;                 /* images in the batch                                      */
+  int n_scales;          /* 1..KG_MAX_SCALES                                         */
+  int max_peaks;         /* cap per (image, scale): power of two, 64..8192           */
+  int max_boxes;         /* cap per image over all scales (pre-NMS): power of two, 64..8192 */
+  double nms_thresh;     /* nms.py:4 (default 0.5)                                   */
+  double peak_thresh;    /* postprocessing.py:145 (0.004)                            */
+} kg_decode_config;
+
+/* Device outputs; any pointer other than d_status may be NULL to skip that export. */
+typedef struct kg_decode_outputs {
+  double* d_dets;        /* [N, max_boxes, 5]  post-NMS rows in keep order (nms.py:51)                      */
+  int* d_det_count;      /* [N]                                                                               */
+  double* d_boxes;       /* [N, max_boxes, 5]  pre-NMS boxes in gather_skeleton order (postprocessing.py:255)  */
+  int* d_box_count;      /* [N]                                                                               */
+  double* d_skeletons;   /* [N, n_scales, max_peaks, 5, 3]  (x, y, conf); ALL skeletons of group_skeletons     */
+  int* d_skel_count;     /* [N, n_scales]                                                                     */
+  uint8_t* d_skel_keep;  /* [N, n_scales, max_peaks]  1 where refine_skeleton keeps the skeleton (:150-159)   */
+  double* d_peak_conf;   /* [N, n_scales, max_peaks]  peaks in group_skeletons' sorted order (:87)            */
+  int* d_peak_key;       /* [N, n_scales, max_peaks]  id*H*W + y*W + x                                        */
+  int* d_peak_count;     /* [N, n_scales]                                                                     */
+  double* d_heat[KG_MAX_SCALES];  /* per scale [N,5,H,W]: Hough heat AFTER the Gaussian blur (:143-144)       */
+  double* d_vote[KG_MAX_SCALES];  /* per scale [N,5,H,W]: Hough heat BEFORE the blur (compute_heatmaps)        */
+  int* d_status;         /* [1] bit0: a peak list overflowed, bit1: a box list overflowed                     */
+} kg_decode_outputs;
+
+size_t kg_decode_workspace_bytes(const kg_decode_config* cfg, const kg_decode_scale* scales);
+
+/* Enqueue the whole decode on `stream`.  No sync, no allocation.  Number of kernel launches is
+ * returned through *n_launches when non-NULL. */
+int kg_decode(const kg_decode_config* cfg, const kg_decode_scale* scales, const kg_decode_outputs* out,
+              void* d_workspace, size_t workspace_bytes, void* stream, int* n_launches);
+
+/* Host-buffer end-to-end variant of the same path (the reference API's data flow,
+ * postprocessing.py:134-136: head maps in host memory -> detections in host memory).
+ * h_kp/h_short/h_mid[s] are [N,C,H_s,W_s] fp32 host arrays (pinned for full speed).
+ * h_dets [N,max_boxes,5], h_det_count [N].  Copies, runs and synchronises on `stream`. */
+int kg_decode_host(const kg_decode_config* cfg, const float* const* h_kp, const float* const* h_short,
+                   const float* const* h_mid, const int* H, const int* W, const int* box_scale,
+                   double* h_dets, int* h_det_count, void* stream);
+
+/* refine_skeleton + skeleton_to_box for host lists (postprocessing.py:150-242): h_skeletons [n,5,3]
+ * -> h_keep [n] (refine mask) and h_boxes [n,5] rows for the kept skeletons that yield a box, in
+ * order; *n_boxes receives the count.  Does not mutate the input (the reference scales it in place). */
+int kg_skeletons_to_boxes_host(const double* h_skeletons, int n, int box_scale, int apply_refine,
+                               uint8_t* h_keep, double* h_boxes, int* n_boxes);
+
+/* nms.py:4-53 on a host array [n,5]; h_out [n,5] receives the kept rows in keep order. */
+int kg_nms_host(const double* h_boxes, int n, double nms_thresh, double* h_out, int* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGNET_B200_H_ */

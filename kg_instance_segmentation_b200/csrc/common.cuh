@@ -6,18 +6,12 @@
 #include <cstdio>
 #include <cstdarg>
 #include <string>
+#include "../../include/kgnet_b200.h"
 
 namespace kg {
 
 // ---- error reporting (C-ABI: int return codes + kg_last_error()) ------------------------------
-enum : int {
-  KG_OK = 0,
-  KG_ERR_INVALID = -1,     // bad argument / unsupported shape
-  KG_ERR_CUDA = -2,        // CUDA runtime / driver failure
-  KG_ERR_CAPACITY = -3,    // a bounded device buffer (peaks / skeletons / boxes) overflowed
-  KG_ERR_STATE = -4,       // call order violated (e.g. forward before finalize)
-  KG_ERR_WORKSPACE = -5,   // caller-provided workspace too small
-};
+// status codes: kg_status in include/kgnet_b200.h (KG_OK, KG_ERR_*), shared with the C-ABI
 
 void set_error(const char* fmt, ...);
 const char* last_error();
@@ -27,7 +21,7 @@ const char* last_error();
     cudaError_t _e = (expr);                                                                     \
     if (_e != cudaSuccess) {                                                                     \
       kg::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
-      return kg::KG_ERR_CUDA;                                                                    \
+      return KG_ERR_CUDA;                                                                    \
     }                                                                                            \
   } while (0)
 
@@ -35,14 +29,14 @@ const char* last_error();
   do {                                         \
     if (!(cond)) {                             \
       kg::set_error(__VA_ARGS__);              \
-      return kg::KG_ERR_INVALID;               \
+      return KG_ERR_INVALID;               \
     }                                          \
   } while (0)
 
 #define KG_TRY(expr)            \
   do {                          \
     int _r = (expr);            \
-    if (_r != kg::KG_OK) return _r; \
+    if (_r != KG_OK) return _r; \
   } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -59,6 +53,18 @@ struct Arena {
     return r;
   }
   bool ok() const { return off <= size; }
+};
+
+// ---- optional per-stage device timing (kg_timing_enable / kg_timing_collect) ---------------------
+// Stage ids: 0 vote, 1 blur+peak, 2 sort+group+boxes, 3 nms, 8.. network stages (see net.cu).
+constexpr int KG_MAX_STAGES = 64;
+bool timing_enabled();
+void stage_begin(int id, cudaStream_t s);
+void stage_end(int id, cudaStream_t s);
+struct StageScope {
+  int id; cudaStream_t s;
+  StageScope(int id_, cudaStream_t s_) : id(id_), s(s_) { if (timing_enabled()) stage_begin(id, s); }
+  ~StageScope() { if (timing_enabled()) stage_end(id, s); }
 };
 
 // ---- split-bf16 activations: v ~= float(hi) + float(lo) ---------------------------------------

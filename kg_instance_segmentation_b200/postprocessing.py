@@ -1,0 +1,205 @@
+"""Drop-in for the reference's postprocessing.py: same function names, argument meaning and return
+types; every function runs the CUDA decode kernels (csrc/decode.cu) through the C-ABI.
+
+`decode_batched` is the new batched entry point (the reference decodes batch element 0 only,
+postprocessing.py:138-140); `get_skeletons_and_masks` keeps the reference's single-image contract.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import config as cfg
+
+
+def _as_cuda_f32(t):
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    if not torch.cuda.is_available():
+        raise RuntimeError("kg_instance_segmentation_b200 needs a CUDA device (no CPU fallback)")
+    return t.detach().to(device="cuda", dtype=torch.float32).contiguous()
+
+
+@dataclass
+class DecodeResult:
+    """Device-resident outputs of one decode call (torch tensors own the memory)."""
+    dets: torch.Tensor          # [N, max_boxes, 5] f64
+    det_count: torch.Tensor     # [N] i32
+    boxes: Optional[torch.Tensor] = None
+    box_count: Optional[torch.Tensor] = None
+    skeletons: Optional[torch.Tensor] = None     # [N, S, max_peaks, 5, 3] f64
+    skel_count: Optional[torch.Tensor] = None    # [N, S]
+    skel_keep: Optional[torch.Tensor] = None     # [N, S, max_peaks] u8
+    peak_conf: Optional[torch.Tensor] = None
+    peak_key: Optional[torch.Tensor] = None
+    peak_count: Optional[torch.Tensor] = None
+    heat: Optional[list] = None
+    vote: Optional[list] = None
+    status: Optional[torch.Tensor] = None
+    n_launches: int = 0
+
+    def check(self):
+        st = int(self.status.item())
+        if st:
+            raise _cabi.KgError(-3, f"decode list overflow (status={st}: bit0 peaks, bit1 boxes); raise max_peaks/max_boxes")
+
+    def detections(self) -> List[Optional[np.ndarray]]:
+        """Per image: (M,5) float64 array in NMS keep order, or None (nms.py:8-9) when there are no boxes."""
+        self.check()
+        cnt = self.det_count.cpu().numpy()
+        m = int(cnt.max()) if len(cnt) else 0
+        d = self.dets[:, :max(m, 1)].cpu().numpy()
+        return [d[i, :c].copy() if c > 0 else None for i, c in enumerate(cnt)]
+
+
+class Decoder:
+    """Holds the workspace / output buffers for one (N, scale shapes) configuration so that repeated
+    calls launch kernels only (no allocation, no host sync)."""
+
+    def __init__(self, N, shapes: Sequence[tuple], box_scales: Sequence[int] = None, max_peaks=4096, max_boxes=4096,
+                 nms_thresh=0.5, peak_thresh=cfg.PEAK_THRESH, debug=False, device="cuda"):
+        self.L = _cabi.lib()
+        self.N, self.shapes = int(N), [tuple(map(int, s)) for s in shapes]
+        S = len(self.shapes)
+        self.box_scales = list(box_scales) if box_scales is not None else list(cfg.BOX_SCALES[:S])
+        self.cfg = _cabi.DecodeConfig(self.N, S, int(max_peaks), int(max_boxes), float(nms_thresh), float(peak_thresh))
+        self.sc = (_cabi.DecodeScale * S)()
+        for s, (h, w) in enumerate(self.shapes):
+            self.sc[s].H, self.sc[s].W, self.sc[s].box_scale = h, w, int(self.box_scales[s])
+        ws = self.L.kg_decode_workspace_bytes(C.byref(self.cfg), self.sc)
+        if ws == 0:
+            raise _cabi.KgError(-1, self.L.kg_last_error().decode())
+        dev = torch.device(device)
+        self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev)
+        self.debug = debug
+        f64, i32 = torch.float64, torch.int32
+        r = DecodeResult(dets=torch.zeros(self.N, max_boxes, 5, dtype=f64, device=dev),
+                         det_count=torch.zeros(self.N, dtype=i32, device=dev),
+                         status=torch.zeros(1, dtype=i32, device=dev))
+        if debug:
+            r.boxes = torch.zeros(self.N, max_boxes, 5, dtype=f64, device=dev)
+            r.box_count = torch.zeros(self.N, dtype=i32, device=dev)
+            r.peak_conf = torch.zeros(self.N, S, max_peaks, dtype=f64, device=dev)
+            r.peak_key = torch.zeros(self.N, S, max_peaks, dtype=i32, device=dev)
+            r.peak_count = torch.zeros(self.N, S, dtype=i32, device=dev)
+            r.skel_keep = torch.zeros(self.N, S, max_peaks, dtype=torch.uint8, device=dev)
+            r.heat = [torch.zeros(self.N, 5, h, w, dtype=f64, device=dev) for h, w in self.shapes]
+            r.vote = [torch.zeros(self.N, 5, h, w, dtype=f64, device=dev) for h, w in self.shapes]
+        r.skeletons = torch.zeros(self.N, S, max_peaks, 5, 3, dtype=f64, device=dev)
+        r.skel_count = torch.zeros(self.N, S, dtype=i32, device=dev)
+        self.result = r
+        o = _cabi.DecodeOutputs()
+        p = lambda t: t.data_ptr() if t is not None else None
+        o.d_dets, o.d_det_count, o.d_boxes, o.d_box_count = p(r.dets), p(r.det_count), p(r.boxes), p(r.box_count)
+        o.d_skeletons, o.d_skel_count, o.d_skel_keep = p(r.skeletons), p(r.skel_count), p(r.skel_keep)
+        o.d_peak_conf, o.d_peak_key, o.d_peak_count = p(r.peak_conf), p(r.peak_key), p(r.peak_count)
+        for s in range(S):
+            o.d_heat[s] = p(r.heat[s]) if debug else None
+            o.d_vote[s] = p(r.vote[s]) if debug else None
+        o.d_status = p(r.status)
+        self.out = o
+
+    def __call__(self, heads, stream: Optional[torch.cuda.Stream] = None) -> DecodeResult:
+        """heads: per scale (kp [N,5,H,W], short [N,10,H,W], mid [N,40,H,W]) fp32 contiguous CUDA tensors.
+        Enqueues on `stream` (default: torch's current stream); does not synchronise."""
+        keep = []
+        for s, (kp, sh, mid) in enumerate(heads):
+            h, w = self.shapes[s]
+            for t, c in ((kp, 5), (sh, 10), (mid, 40)):
+                if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != (self.N, c, h, w):
+                    raise ValueError(f"scale {s}: expected contiguous cuda float32 [{self.N},{c},{h},{w}], got "
+                                     f"{tuple(t.shape)} {t.dtype} {t.device}")
+            self.sc[s].d_kp, self.sc[s].d_short, self.sc[s].d_mid = kp.data_ptr(), sh.data_ptr(), mid.data_ptr()
+            keep.append((kp, sh, mid))
+        st = stream if stream is not None else torch.cuda.current_stream()
+        nl = C.c_int(0)
+        _cabi.check(self.L.kg_decode(C.byref(self.cfg), self.sc, C.byref(self.out), self.workspace.data_ptr(),
+                                     self.workspace.numel(), st.cuda_stream, C.byref(nl)))
+        self.result.n_launches = nl.value
+        self._keepalive = keep
+        return self.result
+
+
+_decoders = {}
+
+
+def _decoder(N, shapes, box_scales, **kw) -> Decoder:
+    key = (N, tuple(shapes), tuple(box_scales), tuple(sorted(kw.items())))
+    d = _decoders.get(key)
+    if d is None:
+        if len(_decoders) > 8:
+            _decoders.clear()
+        d = _decoders[key] = Decoder(N, shapes, box_scales, **kw)
+    return d
+
+
+def decode_batched(heads, nms_thresh=0.5, max_peaks=4096, max_boxes=4096, debug=False) -> DecodeResult:
+    """test.py:105-116 for a whole batch: heads = [[kp_s, short_s, mid_s] for s in 0..3] (NCHW torch tensors)."""
+    hs = [tuple(_as_cuda_f32(t) for t in h) for h in heads]
+    N = hs[0][0].shape[0]
+    shapes = [tuple(h[0].shape[2:]) for h in hs]
+    d = _decoder(N, shapes, cfg.BOX_SCALES[:len(hs)], nms_thresh=float(nms_thresh), max_peaks=max_peaks,
+                 max_boxes=max_boxes, debug=debug)
+    return d(hs)
+
+
+def _skeleton_list(res: DecodeResult, n, s):
+    cnt = int(res.skel_count[n, s].item())
+    sk = res.skeletons[n, s, :cnt].cpu().numpy()
+    return [sk[i].copy() for i in range(cnt)]
+
+
+def get_skeletons_and_masks(kp_maps, short_offsets, mid_offsets):
+    """postprocessing.py:129-147: batch x {5,10,40} x H x W tensors -> list of (5,3) float64 [x,y,conf]
+    skeletons of batch element 0 (missing keypoints are all-zero rows)."""
+    kp, sh, mid = (_as_cuda_f32(t)[0:1] for t in (kp_maps, short_offsets, mid_offsets))
+    d = _decoder(1, [tuple(kp.shape[2:])], (1,), max_peaks=4096, max_boxes=4096, debug=False)
+    res = d([(kp.contiguous(), sh.contiguous(), mid.contiguous())])
+    res.check()
+    return _skeleton_list(res, 0, 0)
+
+
+def _boxes_host(skeletons, scale, apply_refine):
+    n = len(skeletons)
+    if n == 0:
+        return np.zeros((0,), np.uint8), np.zeros((0, 5), np.float64)
+    sk = np.ascontiguousarray(np.asarray(skeletons, np.float64).reshape(n, 5, 3))
+    keep = np.zeros(n, np.uint8)
+    boxes = np.zeros((n, 5), np.float64)
+    nb = C.c_int(0)
+    _cabi.check(_cabi.lib().kg_skeletons_to_boxes_host(sk.ctypes.data, n, int(scale), int(apply_refine), keep.ctypes.data,
+                                                       boxes.ctypes.data, C.byref(nb)))
+    return keep, boxes[:nb.value]
+
+
+def refine_skeleton(skeletons):
+    """postprocessing.py:150-159."""
+    keep, _ = _boxes_host(skeletons, 1, False)
+    return [s for s, k in zip(skeletons, keep) if k]
+
+
+def skeleton_to_box(skeletons, scale):
+    """postprocessing.py:164-242.  Like the reference this scales the skeletons' xy IN PLACE."""
+    _, boxes = _boxes_host(skeletons, scale, False)
+    for s in skeletons:
+        s[:, :2] *= scale
+    return [list(b) for b in boxes]
+
+
+def gather_skeleton_single(skeleton0, skeleton1, skeleton2, skeleton3):
+    """postprocessing.py:245-252."""
+    return tuple(np.asarray(skeleton_to_box(s, sc)) for s, sc in zip((skeleton0, skeleton1, skeleton2, skeleton3),
+                                                                     cfg.BOX_SCALES))
+
+
+def gather_skeleton(skeleton0, skeleton1, skeleton2, skeleton3):
+    """postprocessing.py:255-261."""
+    b = []
+    for s, sc in zip((skeleton0, skeleton1, skeleton2, skeleton3), cfg.BOX_SCALES):
+        b += skeleton_to_box(s, sc)
+    return np.asarray(b)
