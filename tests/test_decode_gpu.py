@@ -168,7 +168,7 @@ def test_box_case_table_and_nms_edge_cases():
 
 
 def test_overflow_is_reported_not_hidden():
-    heads, _ = O.planted_scene(2, 192, 192, 14, side=(24, 60))
+    heads, _ = O.planted_scene(11, 256, 256, 20, side=(24, 80))        # 70 peaks at scale 0 > cap of 64
     res = _pp().decode_batched(_to_batch([heads]), max_peaks=64, max_boxes=64)
     with pytest.raises(RuntimeError):
         res.check()
