@@ -120,6 +120,61 @@ int kg_skeletons_to_boxes_host(const double* h_skeletons, int n, int box_scale, 
 /* nms.py:4-53 on a host array [n,5]; h_out [n,5] receives the kept rows in keep order. */
 int kg_nms_host(const double* h_boxes, int n, double nms_thresh, double* h_out, int* n_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Network: truncated ResNet backbone + top-down decoder + 12 two-layer 7x7 heads (forward_dec) and the per-box
+ * mask branch (forward_seg).  Replaces KGnet.py:123-350 (ResNet.__init__ / forward_dec / forward_seg /
+ * get_patches / mask_forward / CombinationModule) of the reference.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct kg_net kg_net;
+
+/* blocks = {3,4,6} (resnet50, KGnet.py:377-386), {3,4,23} (resnet101) or {3,8,36} (resnet152); NULL = resnet50. */
+int kg_net_create(kg_net** out, const int* blocks);
+void kg_net_destroy(kg_net* net);
+
+/* Register one nn.Conv2d by its state-dict prefix (e.g. "layer1.0.conv1", "c0_conv.0", "kp_head_c2.2").
+ * h_w: HOST fp32 [Cout,Cin,R,S] (torch layout); h_bias: [Cout] or NULL; h_bn_*: the eval-mode BatchNorm2d that
+ * follows it (weight, bias, running_mean, running_var) or NULL — folded into the conv at load time. */
+int kg_net_set_conv(kg_net* net, const char* name, const float* h_w, int Cout, int Cin, int R, int S, const float* h_bias,
+                    const float* h_bn_weight, const float* h_bn_bias, const float* h_bn_mean, const float* h_bn_var,
+                    double bn_eps);
+/* Checks that every layer of the architecture was set, fuses the first-layer head convs, repacks and uploads. */
+int kg_net_finalize(kg_net* net);
+
+/* precision: 0 = CUDA-core fp32 FFMA everywhere (on-device reference), 1 = "fast" (tcgen05; split-fp16 3-pass in
+ * backbone/decoder, single-pass fp16 in the heads; meets 1e-3 on the keypoint heatmaps), 2 = "exact" (tcgen05,
+ * split-fp16 3-pass everywhere). */
+size_t kg_net_workspace_bytes(kg_net* net, int N, int H, int W, int precision);
+
+/* ResNet.forward_dec (KGnet.py:275-318).  d_x: [N,3,H,W] fp32 NCHW.  d_heads[12]: kp0, short0, mid0, kp1, ... mid3,
+ * each [N,{5,10,40},H/2^s,W/2^s] fp32 NCHW.  d_feats[5] (or NULL): c0..c4 fp32 NCHW.  H, W multiples of 16.
+ * The workspace keeps c0..c4 in the internal layout for a following kg_net_forward_seg. */
+int kg_net_forward_dec(kg_net* net, const float* d_x, int N, int H, int W, float* const* d_heads, float* const* d_feats,
+                       int precision, void* d_workspace, size_t workspace_bytes, void* stream, int* n_launches);
+
+/* Loads caller-provided fp32 NCHW features c0..c4 into the workspace (forward_seg on features that did not come
+ * from kg_net_forward_dec, KGnet.py:321). */
+int kg_net_import_feats(kg_net* net, const float* const* d_feats, int N, int H, int W, int precision, void* d_workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ResNet.forward_seg (KGnet.py:321-350), two calls.  prepare: host boxes ([sum(box_counts),5] fp64 rows
+ * y1,x1,y2,x2,score, image-major) -> crop rectangles (get_patches, :246-256), grouped problem lists, required
+ * scratch bytes and the mask layout: h_mask_index[box] = mask slot or -1 when the box is skipped (:341-342),
+ * h_mask_hw[slot] = (h, w), h_mask_off[slot] = float offset into d_masks.  run: all boxes in grouped launches. */
+int kg_net_seg_prepare(kg_net* net, int N, int H, int W, const int* box_counts, const double* h_boxes,
+                       size_t* seg_workspace_bytes, long long* mask_floats, int* n_masks, int* h_mask_index,
+                       int* h_mask_hw, long long* h_mask_off);
+int kg_net_forward_seg(kg_net* net, void* d_dec_workspace, void* d_seg_workspace, size_t seg_workspace_bytes,
+                       float* d_masks, void* stream, int* n_launches);
+
+/* One nn.Conv2d (+bias, +residual, +ReLU) on fp32 NCHW device tensors: operator-level entry for unit tests.
+ * mode: 0 CUDA cores, 1 / 3 = tcgen05 with 1 / 3 split-fp16 passes.  Allocates and synchronises internally. */
+int kg_conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R,
+                   int S, int stride, int pad, int relu, const float* d_res, int mode, float* d_y, void* stream);
+
+/* 1 when the tcgen05/TMA path initialised on the current device; kg_tc_status() says why not otherwise. */
+int kg_tc_available(void);
+const char* kg_tc_status(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,344 @@
+"""Drop-in for the reference's KGnet.py (`resnet50()`, `ResNet.forward_dec / forward_seg / forward`).
+
+The module is a torch `nn.Module` only as a PARAMETER CONTAINER: it registers the reference's 346 state-dict
+tensors under the reference's names so that `load_state_dict(torch.load('end_model.pth'))`, `.to(device)` and
+`.eval()` work unchanged (test.py:53,61,196-197).  All arithmetic of `forward_dec` / `forward_seg` runs in the
+sm_100a kernels of libkgnet_b200.so (csrc/net.cu, net_kernels.cu, tc_conv.cu) through the C-ABI; there is no
+torch-op or CPU fallback, and training-mode BatchNorm is not part of this path (eval-mode statistics are folded
+into the convolutions when the weights are uploaded).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+PRECISIONS = {"reference": 0, "ffma": 0, "fast": 1, "exact": 2}
+_FEAT_C = (64, 64, 256, 512, 1024)
+_HEADS = (("kp_head", 5), ("short_offset_head", 10), ("mid_offset_head", 40))
+
+
+class _Conv(nn.Module):
+    """weight [Cout,Cin,k,k] (+ bias): Kaiming-normal fan_out like KGnet.py:212-214, default Conv2d bias init."""
+
+    def __init__(self, cin, cout, k, bias):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
+        nn.init.kaiming_normal_(self.weight, mode="fan_out", nonlinearity="relu")
+        if bias:
+            bound = 1.0 / math.sqrt(cin * k * k)
+            self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+        else:
+            self.register_parameter("bias", None)
+
+
+class _BN(nn.Module):
+    """BatchNorm2d state (KGnet.py:215-217: weight 1, bias 0); used in eval mode only."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self.eps = 1e-5
+
+
+def _seq(**children):
+    """Container whose children carry the numeric names of the reference's nn.Sequential slots."""
+    m = nn.Module()
+    for k, v in children.items():
+        m.add_module(k.lstrip("_"), v)
+    return m
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, inplanes, planes, downsample):
+        super().__init__()
+        self.conv1, self.bn1 = _Conv(inplanes, planes, 1, False), _BN(planes)
+        self.conv2, self.bn2 = _Conv(planes, planes, 3, False), _BN(planes)
+        self.conv3, self.bn3 = _Conv(planes, planes * 4, 1, False), _BN(planes * 4)
+        if downsample:
+            self.downsample = _seq(_0=_Conv(inplanes, planes * 4, 1, False), _1=_BN(planes * 4))
+
+
+class _Combination(nn.Module):
+    def __init__(self, in_size, out_size, cat_size):
+        super().__init__()
+        self.up = _seq(_0=_Conv(in_size, out_size, 3, True))
+        self.cat_conv = _seq(_0=_Conv(cat_size, out_size, 1, True))
+
+
+class ResNet(nn.Module):
+    """KGnet (KGnet.py:123-350): ResNet truncated after layer3 + decoder + keypoint heads + mask branch."""
+
+    def __init__(self, layers=(3, 4, 6, 3), precision="fast"):
+        super().__init__()
+        self.blocks = tuple(int(b) for b in layers[:3])       # layer4 is never built (KGnet.py:131-137)
+        self.conv1, self.bn1 = _Conv(3, 64, 7, False), _BN(64)
+        inpl = 64
+        for li, (planes, nb) in enumerate(zip((64, 128, 256), self.blocks)):
+            blocks = []
+            for b in range(nb):
+                blocks.append(_Bottleneck(inpl, planes, downsample=(b == 0)))
+                inpl = planes * 4
+            setattr(self, f"layer{li + 1}", nn.ModuleList(blocks))
+        self.c0_conv = _seq(_0=_Conv(3, 64, 3, True), _2=_Conv(64, 64, 3, True))
+        self.skip_combine = nn.ModuleList([_Combination(64, 64, 128), _Combination(256, 64, 128),
+                                           _Combination(512, 256, 512), _Combination(1024, 512, 1024)])
+        self.seg_head = _seq(_0=_Conv(64, 64, 3, True), _2=_Conv(64, 1, 3, True))
+        self.c4_up_conv = _seq(_0=_Conv(1024, 512, 3, True))
+        self.c3_up_conv = _seq(_0=_Conv(512, 256, 3, True))
+        self.c2_up_conv = _seq(_0=_Conv(256, 64, 3, True))
+        self.c1_up_conv = _seq(_0=_Conv(64, 64, 3, True))
+        self.c3_cat_refine = _seq(_0=_Conv(1024, 512, 1, True))
+        self.c2_cat_refine = _seq(_0=_Conv(512, 256, 1, True))
+        self.c1_cat_refine = _seq(_0=_Conv(128, 64, 1, True))
+        self.c0_cat_refine = _seq(_0=_Conv(128, 64, 1, True))
+        for s, c in ((3, 512), (2, 256), (1, 64), (0, 64)):
+            for name, co in _HEADS:
+                setattr(self, f"{name}_c{s}", _seq(_0=_Conv(c, c, 7, True), _2=_Conv(c, co, 7, True)))
+        self.precision = precision
+        self.export_feats = True
+        self._handle = None
+        self._weights_sig = None
+        self._ws = {}
+        self._seg_ws = None
+        self._last = None
+        self.last_launches = 0
+
+    # ---- weight upload --------------------------------------------------------------------------
+    def _conv_list(self):
+        """(state-dict prefix of the conv, prefix of the BatchNorm that follows it or None)."""
+        out = [("conv1", "bn1"), ("c0_conv.0", None), ("c0_conv.2", None), ("seg_head.0", None), ("seg_head.2", None)]
+        for li, nb in enumerate(self.blocks):
+            for b in range(nb):
+                p = f"layer{li + 1}.{b}"
+                out += [(p + ".conv1", p + ".bn1"), (p + ".conv2", p + ".bn2"), (p + ".conv3", p + ".bn3")]
+                if b == 0:
+                    out.append((p + ".downsample.0", p + ".downsample.1"))
+        for l in range(4):
+            out += [(f"skip_combine.{l}.up.0", None), (f"skip_combine.{l}.cat_conv.0", None)]
+        for n in ("c4_up_conv", "c3_up_conv", "c2_up_conv", "c1_up_conv", "c3_cat_refine", "c2_cat_refine", "c1_cat_refine",
+                  "c0_cat_refine"):
+            out.append((n + ".0", None))
+        for s in range(4):
+            for name, _ in _HEADS:
+                out += [(f"{name}_c{s}.0", None), (f"{name}_c{s}.2", None)]
+        return out
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _sync_weights(self):
+        sig = self._signature()
+        if self._handle is not None and sig == self._weights_sig:
+            return
+        L = _cabi.lib()
+        if self._handle is None:
+            h = C.c_void_p()
+            blocks = (C.c_int * 3)(*self.blocks)
+            _cabi.check(L.kg_net_create(C.byref(h), blocks))
+            self._handle = h
+        sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in self.state_dict().items()
+              if not k.endswith("num_batches_tracked")}
+        fp = lambda t: t.numpy().ctypes.data_as(C.c_void_p) if t is not None else None
+        for conv, bn in self._conv_list():
+            w = sd[conv + ".weight"]
+            b = sd.get(conv + ".bias")
+            bnp = [sd[f"{bn}.{k}"] for k in ("weight", "bias", "running_mean", "running_var")] if bn else [None] * 4
+            co, ci, r, s = w.shape
+            _cabi.check(L.kg_net_set_conv(self._handle, conv.encode(), fp(w), co, ci, r, s, fp(b), *[fp(t) for t in bnp], 1e-5))
+        _cabi.check(L.kg_net_finalize(self._handle))
+        self._weights_sig = sig
+        self._last = None
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _cabi.lib().kg_net_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _precision_code(self):
+        p = self.precision
+        return PRECISIONS[p] if isinstance(p, str) else int(p)
+
+    def _workspace(self, N, H, W, prec, device):
+        key = (N, H, W, prec, str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = _cabi.lib().kg_net_workspace_bytes(self._handle, N, H, W, prec)
+            if nbytes == 0:
+                raise _cabi.KgError(-1, _cabi.lib().kg_last_error().decode())
+            self._ws.clear()
+            ws = self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return ws
+
+    # ---- KGnet.py:275-318 -----------------------------------------------------------------------
+    def forward_dec(self, x):
+        if self.training:
+            raise RuntimeError("kgnet_b200 implements the inference path: call .eval() first (train-mode BatchNorm is out of scope)")
+        if not x.is_cuda:
+            raise RuntimeError("kgnet_b200 needs CUDA tensors (no CPU fallback): move the model and input to cuda")
+        x = x.detach().to(torch.float32).contiguous()
+        N, c, H, W = x.shape
+        assert c == 3, "input must be [N,3,H,W]"
+        with torch.cuda.device(x.device):
+            self._sync_weights()
+            prec = self._precision_code()
+            ws = self._workspace(N, H, W, prec, x.device)
+            outs = []
+            for s in range(4):
+                hs, wsz = H >> s, W >> s
+                outs.append([torch.empty(N, co, hs, wsz, dtype=torch.float32, device=x.device) for _, co in _HEADS])
+            fsz = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8), (H // 16, W // 16)]
+            feats = [torch.empty(N, cc, h, w, dtype=torch.float32, device=x.device) for cc, (h, w) in zip(_FEAT_C, fsz)] \
+                if self.export_feats else None
+            heads_p = (C.c_void_p * 12)(*[t.data_ptr() for o in outs for t in o])
+            feats_p = (C.c_void_p * 5)(*[t.data_ptr() for t in feats]) if feats is not None else None
+            nl = C.c_int(0)
+            _cabi.check(_cabi.lib().kg_net_forward_dec(self._handle, x.data_ptr(), N, H, W, heads_p, feats_p, prec, ws.data_ptr(),
+                                                       ws.numel(), torch.cuda.current_stream().cuda_stream, C.byref(nl)))
+        self.last_launches = nl.value
+        feat_list = _FeatList(feats if feats is not None else [None] * 5)
+        feat_list.owner_key = (id(self), N, H, W, prec)
+        self._last = (feat_list.owner_key, ws, [None if t is None else (t.data_ptr(), t._version) for t in feat_list])
+        return outs[0], outs[1], outs[2], outs[3], feat_list
+
+    # ---- KGnet.py:246-256 -----------------------------------------------------------------------
+    def get_patches(self, box, feat):
+        y1, x1, y2, x2 = box
+        _, h, w = feat.shape
+        y1 = np.maximum(0, np.int32(np.round(y1 * h)))
+        x1 = np.maximum(0, np.int32(np.round(x1 * w)))
+        y2 = np.minimum(np.int32(np.round(y2 * h)), h - 1)
+        x2 = np.minimum(np.int32(np.round(x2 * w)), w - 1)
+        if y2 < y1 or x2 < x1 or y2 - y1 < 2 or x2 - x1 < 2:
+            return None
+        return feat[:, y1:y2, x1:x2].unsqueeze(0)
+
+    # ---- KGnet.py:321-350 -----------------------------------------------------------------------
+    def forward_seg(self, feat_seg, bboxes):
+        """feat_seg: the list returned by forward_dec (any list of 5 fp32 NCHW CUDA tensors works too);
+        bboxes: per image an (M,5) array [y1,x1,y2,x2,score] or an empty list.
+        Returns [mask_patches, mask_dets] with the reference's nesting."""
+        nimg = len(bboxes)
+        L = _cabi.lib()
+        internal = (isinstance(feat_seg, _FeatList) and self._last is not None and feat_seg.owner_key == self._last[0] and
+                    all((t is None and s is None) or (t is not None and s is not None and (t.data_ptr(), t._version) == s)
+                        for t, s in zip(feat_seg, self._last[2])))
+        if internal:
+            _, N, H, W, prec = self._last[0]
+            ws = self._last[1]
+            device = ws.device
+        else:
+            f0 = feat_seg[0]
+            if f0 is None or not f0.is_cuda:
+                raise RuntimeError("forward_seg needs CUDA feature tensors (or the list returned by forward_dec)")
+            N, _, H, W = f0.shape
+            device = f0.device
+            with torch.cuda.device(device):
+                self._sync_weights()
+                prec = self._precision_code()
+                ws = self._workspace(N, H, W, prec, device)
+                fl = [t.detach().to(torch.float32).contiguous() for t in feat_seg]
+                fp = (C.c_void_p * 5)(*[t.data_ptr() for t in fl])
+                _cabi.check(L.kg_net_import_feats(self._handle, fp, N, H, W, prec, ws.data_ptr(), ws.numel(),
+                                                  torch.cuda.current_stream().cuda_stream))
+            self._last = None
+        if nimg > N:
+            raise ValueError(f"{nimg} box lists for a batch of {N} images")
+        counts = np.zeros(N, np.int32)
+        rows = []
+        for i in range(nimg):
+            if len(bboxes[i]) == 0:
+                continue
+            b = np.asarray(bboxes[i], np.float64).reshape(-1, 5)
+            counts[i] = len(b)
+            rows.append(b)
+        total = int(counts.sum())
+        mask_patches = [[] for _ in range(nimg)]
+        mask_dets = [[] for _ in range(nimg)]
+        if total == 0:
+            return [mask_patches, mask_dets]
+        boxes = np.ascontiguousarray(np.concatenate(rows, 0))
+        seg_bytes, mask_floats, n_masks = C.c_size_t(0), C.c_longlong(0), C.c_int(0)
+        mask_index = np.zeros(total, np.int32); mask_hw = np.zeros((total, 2), np.int32); mask_off = np.zeros(total, np.int64)
+        with torch.cuda.device(device):
+            _cabi.check(L.kg_net_seg_prepare(self._handle, N, H, W, counts.ctypes.data, boxes.ctypes.data, C.byref(seg_bytes),
+                                             C.byref(mask_floats), C.byref(n_masks), mask_index.ctypes.data, mask_hw.ctypes.data,
+                                             mask_off.ctypes.data))
+            if self._seg_ws is None or self._seg_ws.numel() < seg_bytes.value or self._seg_ws.device != device:
+                self._seg_ws = torch.empty(int(seg_bytes.value * 1.25) + 1024, dtype=torch.uint8, device=device)
+            masks = torch.empty(max(1, mask_floats.value), dtype=torch.float32, device=device)
+            nl = C.c_int(0)
+            _cabi.check(L.kg_net_forward_seg(self._handle, ws.data_ptr(), self._seg_ws.data_ptr(), self._seg_ws.numel(),
+                                             masks.data_ptr(), torch.cuda.current_stream().cuda_stream, C.byref(nl)))
+        self.last_launches = nl.value
+        k = 0
+        for i in range(nimg):
+            for j in range(counts[i]):
+                slot = mask_index[k]
+                if slot >= 0:
+                    h, w = mask_hw[slot]
+                    o = int(mask_off[slot])
+                    mask_patches[i].append(masks[o:o + int(h) * int(w)].view(int(h), int(w)))
+                    mask_dets[i].append(torch.Tensor(np.append(boxes[k, :4], boxes[k, 4])))
+                k += 1
+        return [mask_patches, mask_dets]
+
+    # ---- KGnet.py:269-272 -----------------------------------------------------------------------
+    def forward(self, x, bboxes):
+        dec0, dec1, dec2, dec3, feat_seg = self.forward_dec(x)
+        seg = self.forward_seg(feat_seg, bboxes)
+        return dec0, dec1, dec2, dec3, seg
+
+
+class _FeatList(list):
+    """[c0..c4] as returned by forward_dec; remembers which forward pass produced it so that forward_seg can
+    read the features from the device workspace in their internal layout instead of re-importing them."""
+    owner_key = None
+
+
+def _no_basic_block(name):
+    raise NotImplementedError(f"{name}: the reference's decoder hard-codes Bottleneck widths (c2/c3/c4 = 256/512/1024, "
+                              "KGnet.py:150-158), so its BasicBlock variants cannot run forward_dec either")
+
+
+def resnet18(pretrained=False, **kwargs):
+    _no_basic_block("resnet18")
+
+
+def resnet34(pretrained=False, **kwargs):
+    _no_basic_block("resnet34")
+
+
+def _make(layers, pretrained, kwargs):
+    model = ResNet(layers, **kwargs)
+    if pretrained:
+        raise RuntimeError("pretrained=True downloads ImageNet weights in the reference (KGnet.py:383-386); there is no "
+                           "network here: construct with pretrained=False and load_state_dict() a checkpoint")
+    return model
+
+
+def resnet50(pretrained=False, **kwargs):
+    """KGnet.py:377-386."""
+    return _make((3, 4, 6, 3), pretrained, kwargs)
+
+
+def resnet101(pretrained=False, **kwargs):
+    """KGnet.py:389-398."""
+    return _make((3, 4, 23, 3), pretrained, kwargs)
+
+
+def resnet152(pretrained=False, **kwargs):
+    """KGnet.py:401-410."""
+    return _make((3, 8, 36, 3), pretrained, kwargs)

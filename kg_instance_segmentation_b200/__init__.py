@@ -8,5 +8,6 @@ All compute runs in hand-written sm_100a CUDA kernels (csrc/) behind a C-ABI sha
 from . import config  # noqa: F401
 from . import _cabi  # noqa: F401
 from . import nms, postprocessing  # noqa: F401
+from . import KGnet  # noqa: F401
 
-__all__ = ["config", "nms", "postprocessing"]
+__all__ = ["config", "nms", "postprocessing", "KGnet"]

@@ -75,8 +75,29 @@ def lib():
 
 def _bind_net(L):
     """Signatures of the network entry points (present once the conv path is built in)."""
-    if not hasattr(L, "kg_net_create"):
-        return
+    vp, ci, cd, cs = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+    L.kg_net_create.restype = ci
+    L.kg_net_create.argtypes = [C.POINTER(vp), C.POINTER(ci)]
+    L.kg_net_destroy.restype = None
+    L.kg_net_destroy.argtypes = [vp]
+    L.kg_net_set_conv.restype = ci
+    L.kg_net_set_conv.argtypes = [vp, C.c_char_p, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd]
+    L.kg_net_finalize.restype = ci
+    L.kg_net_finalize.argtypes = [vp]
+    L.kg_net_workspace_bytes.restype = cs
+    L.kg_net_workspace_bytes.argtypes = [vp, ci, ci, ci, ci]
+    L.kg_net_forward_dec.restype = ci
+    L.kg_net_forward_dec.argtypes = [vp, vp, ci, ci, ci, vp, vp, ci, vp, cs, vp, C.POINTER(ci)]
+    L.kg_net_import_feats.restype = ci
+    L.kg_net_import_feats.argtypes = [vp, vp, ci, ci, ci, ci, vp, cs, vp]
+    L.kg_net_seg_prepare.restype = ci
+    L.kg_net_seg_prepare.argtypes = [vp, ci, ci, ci, vp, vp, C.POINTER(cs), C.POINTER(C.c_longlong), C.POINTER(ci), vp, vp, vp]
+    L.kg_net_forward_seg.restype = ci
+    L.kg_net_forward_seg.argtypes = [vp, vp, vp, cs, vp, vp, C.POINTER(ci)]
+    L.kg_conv2d_nchw.restype = ci
+    L.kg_conv2d_nchw.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp]
+    L.kg_tc_available.restype = ci
+    L.kg_tc_status.restype = C.c_char_p
 
 
 def check(code):
@@ -85,7 +106,9 @@ def check(code):
 
 
 EXPORTS = ["kg_last_error", "kg_abi_version", "kg_device_arch", "kg_decode_workspace_bytes", "kg_decode",
-           "kg_decode_host", "kg_skeletons_to_boxes_host", "kg_nms_host", "kg_timing_enable", "kg_timing_collect"]
+           "kg_decode_host", "kg_skeletons_to_boxes_host", "kg_nms_host", "kg_timing_enable", "kg_timing_collect",
+           "kg_net_create", "kg_net_destroy", "kg_net_set_conv", "kg_net_finalize", "kg_net_workspace_bytes", "kg_net_forward_dec",
+           "kg_net_import_feats", "kg_net_seg_prepare", "kg_net_forward_seg", "kg_conv2d_nchw", "kg_tc_available", "kg_tc_status"]
 
 
 def timing_enable(on=True):

@@ -1,0 +1,808 @@
+// Host-side runtime of the KGnet forward (KGnet.py:123-350 of the reference): weight store (BN folding,
+// repacking), per-shape execution plan, forward_dec and forward_seg.  All arithmetic runs in the kernels of
+// net_kernels.cu (CUDA cores) and tc_conv.cu (tcgen05 tensor cores).
+#include "net.cuh"
+#include "tc_conv.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace kg {
+
+// stage ids for kg_timing_collect
+enum { ST_STEM = 8, ST_BACKBONE = 9, ST_DECODER = 10, ST_HEAD1 = 11, ST_HEAD2 = 12, ST_RESIZE = 13, ST_POOL = 14, ST_EXPORT = 15,
+       ST_SEG = 16 };
+
+struct ConvW {
+  std::string name;
+  int Cout = 0, Cin = 0, R = 0, S = 0;
+  std::vector<float> h_w;   // [tap][cin][cout], BN folded
+  std::vector<float> h_b;   // [cout]
+  float* d_w = nullptr;
+  float* d_b = nullptr;
+  TcWeights tc;             // fp16 hi/lo [tap][cout_pad][cin] (tensor-core path)
+};
+
+struct Tensor {
+  size_t off_hi = 0, off_lo = 0;   // byte offsets into the workspace
+  int H = 0, W = 0, C = 0;
+};
+
+enum OpType { OP_CONV, OP_BILINEAR, OP_MAXPOOL, OP_EXPORT };
+
+struct Op {
+  OpType type = OP_CONV;
+  const ConvW* w = nullptr;
+  int in0 = -1, in1 = -1, out = -1, res = -1;   // tensor ids
+  int in0_coff = 0, C0 = 0, C1 = 0;
+  bool x_input = false, in_single = false, out_single = false;
+  int out32_ext = -1;                            // index into the external fp32 NCHW outputs (heads 0..11, feats 12..16)
+  int stride = 1, pad = 0;
+  bool relu = false, sigmoid = false;
+  size_t prob_off = 0;                           // index into the device problem array
+  int nprob = 0, max_pix = 0;
+  int Hout = 0, Wout = 0;
+  int stage = ST_BACKBONE;
+  int tc_passes = 0;                             // 0: CUDA-core kernel; 1 or 3: tensor-core kernel passes
+  int tc_index = -1;                             // index into Plan::tc_ops
+};
+
+struct Plan {
+  int N = 0, H = 0, W = 0, precision = -1;
+  std::vector<Tensor> tensors;
+  std::vector<Op> ops;
+  std::vector<ConvProb> h_conv_probs;
+  std::vector<ResizeProb> h_resize_probs;
+  ConvProb* d_conv_probs = nullptr;
+  ResizeProb* d_resize_probs = nullptr;
+  std::vector<TcConvOp> tc_ops;
+  const void* tc_workspace = nullptr;            // workspace base the tensor maps were encoded for
+  size_t bytes = 0;
+  int feat_ids[5] = {-1, -1, -1, -1, -1};
+  int launches = 0;
+  ~Plan() {
+    if (d_conv_probs) cudaFree(d_conv_probs);
+    if (d_resize_probs) cudaFree(d_resize_probs);
+  }
+};
+
+struct SegBox { int img; int L; int rect[5][4]; int mask_index; };
+
+// Grouped problems of one forward_seg call (built on the host by seg_prepare, uploaded once per call).
+struct SegPlan {
+  int N = 0, H = 0, W = 0;
+  bool valid = false;
+  size_t scratch_halfs = 0;      // elements per scratch plane (hi plane, then lo plane)
+  long long mask_floats = 0;
+  int n_masks = 0, n_boxes = 0;
+  struct Step {                  // level l: pre(level l+1) -> bilinear -> up conv -> cat(patch_l, up) -> 1x1
+    std::vector<ResizeProb> rs_raw, rs_scr;
+    std::vector<ConvProb> up, cat;
+    int pix_raw = 0, pix_scr = 0, pix = 0;
+  } steps[4];
+  std::vector<ConvProb> h0_raw, h0_scr, h1;
+  int pix_h0_raw = 0, pix_h0_scr = 0, pix_h1 = 0;
+};
+
+struct Net {
+  int blocks[3] = {3, 4, 6};
+  std::map<std::string, ConvW> convs;
+  bool finalized = false;
+  std::unique_ptr<Plan> plan;
+  SegPlan seg;
+  void* d_seg_probs = nullptr; size_t seg_probs_bytes = 0;
+  ~Net() {
+    for (auto& kv : convs) {
+      if (kv.second.d_w) cudaFree(kv.second.d_w);
+      if (kv.second.d_b) cudaFree(kv.second.d_b);
+      tc_free_weights(kv.second.tc);
+    }
+    if (d_seg_probs) cudaFree(d_seg_probs);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+static const int kPlanes[3] = {64, 128, 256};
+static const int kFeatC[5] = {64, 64, 256, 512, 1024};
+static const int kHeadC[4] = {64, 64, 256, 512};
+static const char* kHeadNames[3] = {"kp_head", "short_offset_head", "mid_offset_head"};
+static const int kHeadOut[3] = {5, 10, 40};
+
+static std::vector<std::string> expected_convs(const int* blocks) {
+  std::vector<std::string> v = {"conv1", "c0_conv.0", "c0_conv.2", "seg_head.0", "seg_head.2", "c4_up_conv.0", "c3_up_conv.0",
+                                "c2_up_conv.0", "c1_up_conv.0", "c3_cat_refine.0", "c2_cat_refine.0", "c1_cat_refine.0",
+                                "c0_cat_refine.0"};
+  for (int l = 0; l < 3; ++l)
+    for (int b = 0; b < blocks[l]; ++b) {
+      const std::string p = "layer" + std::to_string(l + 1) + "." + std::to_string(b);
+      v.push_back(p + ".conv1"); v.push_back(p + ".conv2"); v.push_back(p + ".conv3");
+      if (b == 0) v.push_back(p + ".downsample.0");
+    }
+  for (int l = 0; l < 4; ++l) {
+    v.push_back("skip_combine." + std::to_string(l) + ".up.0");
+    v.push_back("skip_combine." + std::to_string(l) + ".cat_conv.0");
+  }
+  for (int s = 0; s < 4; ++s)
+    for (int h = 0; h < 3; ++h) {
+      v.push_back(std::string(kHeadNames[h]) + "_c" + std::to_string(s) + ".0");
+      v.push_back(std::string(kHeadNames[h]) + "_c" + std::to_string(s) + ".2");
+    }
+  return v;
+}
+
+static int upload_conv(ConvW& c) {
+  if (c.d_w) { cudaFree(c.d_w); c.d_w = nullptr; }
+  if (c.d_b) { cudaFree(c.d_b); c.d_b = nullptr; }
+  KG_CUDA_CHECK(cudaMalloc(&c.d_w, c.h_w.size() * sizeof(float)));
+  KG_CUDA_CHECK(cudaMalloc(&c.d_b, c.h_b.size() * sizeof(float)));
+  KG_CUDA_CHECK(cudaMemcpy(c.d_w, c.h_w.data(), c.h_w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  KG_CUDA_CHECK(cudaMemcpy(c.d_b, c.h_b.data(), c.h_b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return KG_OK;
+}
+
+// nn.Conv2d weight [Cout,Cin,R,S] (+ bias) followed by an eval-mode nn.BatchNorm2d (KGnet.py:131-132,72-77) folded:
+// w' = w * g / sqrt(var + eps), b' = beta + (b - mean) * g / sqrt(var + eps); repacked tap-major [tap][cin][cout].
+static int set_conv(Net* net, const char* name, const float* w, int Cout, int Cin, int R, int S, const float* bias,
+                    const float* bn_w, const float* bn_b, const float* bn_mean, const float* bn_var, double eps) {
+  KG_REQUIRE(net && name && w, "kg_net_set_conv: null argument");
+  KG_REQUIRE(Cout > 0 && Cin > 0 && R > 0 && S > 0, "kg_net_set_conv(%s): bad shape", name);
+  ConvW& c = net->convs[name];
+  c.name = name; c.Cout = Cout; c.Cin = Cin; c.R = R; c.S = S;
+  c.h_w.assign((size_t)R * S * Cin * Cout, 0.f);
+  c.h_b.assign(Cout, 0.f);
+  for (int co = 0; co < Cout; ++co) {
+    double sc = 1.0, sh = bias ? (double)bias[co] : 0.0;
+    if (bn_w) {
+      sc = (double)bn_w[co] / std::sqrt((double)bn_var[co] + eps);
+      sh = (double)bn_b[co] + (sh - (double)bn_mean[co]) * sc;
+    }
+    c.h_b[co] = (float)sh;
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int t = 0; t < R * S; ++t)
+        c.h_w[((size_t)t * Cin + ci) * Cout + co] = (float)((double)w[((size_t)co * Cin + ci) * R * S + t] * sc);
+  }
+  net->finalized = false;
+  return KG_OK;
+}
+
+static int finalize(Net* net) {
+  for (const auto& nme : expected_convs(net->blocks))
+    KG_REQUIRE(net->convs.count(nme) == 1, "kg_net_finalize: weights of '%s' were not set", nme.c_str());
+  // fused first-layer head convs: the three heads of a scale share their input (KGnet.py:300-316) -> one conv, N = 3C
+  for (int s = 0; s < 4; ++s) {
+    const int C = kHeadC[s];
+    ConvW f;
+    f.name = "heads_l1_c" + std::to_string(s);
+    f.Cout = 3 * C; f.Cin = C; f.R = 7; f.S = 7;
+    f.h_w.assign((size_t)49 * C * 3 * C, 0.f);
+    f.h_b.assign(3 * C, 0.f);
+    for (int h = 0; h < 3; ++h) {
+      const ConvW& src = net->convs.at(std::string(kHeadNames[h]) + "_c" + std::to_string(s) + ".0");
+      KG_REQUIRE(src.Cout == C && src.Cin == C && src.R == 7 && src.S == 7, "head %s has an unexpected shape", src.name.c_str());
+      for (size_t tc = 0; tc < (size_t)49 * C; ++tc)
+        for (int co = 0; co < C; ++co) f.h_w[tc * 3 * C + h * C + co] = src.h_w[tc * C + co];
+      for (int co = 0; co < C; ++co) f.h_b[h * C + co] = src.h_b[co];
+    }
+    ConvW& dst = net->convs[f.name];
+    if (dst.d_w) cudaFree(dst.d_w);
+    if (dst.d_b) cudaFree(dst.d_b);
+    tc_free_weights(dst.tc);
+    dst = std::move(f);
+  }
+  for (auto& kv : net->convs) {
+    ConvW& c = kv.second;
+    KG_TRY(upload_conv(c));
+    if (tc_layer_supported(c.Cin, c.Cout, c.R, c.S)) KG_TRY(tc_pack_weights(c.h_w.data(), c.Cin, c.Cout, c.R, c.S, &c.tc));
+  }
+  net->plan.reset();
+  net->finalized = true;
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct PlanBuilder {
+  Net* net; Plan* p; size_t off = 0; int N;
+  int alloc(int H, int W, int C, bool lo = true) {
+    Tensor t; t.H = H; t.W = W; t.C = C;
+    const size_t bytes = align_up((size_t)N * H * W * C * sizeof(__half), 1024);
+    t.off_hi = off; off += bytes;
+    if (lo) { t.off_lo = off; off += bytes; } else { t.off_lo = (size_t)-1; }
+    p->tensors.push_back(t);
+    return (int)p->tensors.size() - 1;
+  }
+  const ConvW* W_(const std::string& n) { return &net->convs.at(n); }
+
+  // generic conv over the batch
+  int conv(const std::string& wname, int in0, int in1, int stride, int pad, bool relu, int stage, int res = -1, int out32_ext = -1,
+           bool sigmoid = false, int in0_coff = 0, bool x_input = false, int xH = 0, int xW = 0, bool want_out = true,
+           bool out_lo = true) {
+    const ConvW* w = W_(wname);
+    Op op; op.type = OP_CONV; op.w = w; op.in0 = in0; op.in1 = in1; op.res = res; op.stride = stride; op.pad = pad;
+    op.relu = relu; op.sigmoid = sigmoid; op.stage = stage; op.out32_ext = out32_ext; op.in0_coff = in0_coff; op.x_input = x_input;
+    int Hin, Win;
+    if (x_input) { Hin = xH; Win = xW; op.C0 = w->Cin; op.C1 = 0; }
+    else {
+      const Tensor& t0 = p->tensors[in0];
+      Hin = t0.H; Win = t0.W;
+      op.C1 = in1 >= 0 ? p->tensors[in1].C : 0;
+      op.C0 = w->Cin - op.C1;
+    }
+    op.Hout = (Hin + 2 * pad - w->R) / stride + 1;
+    op.Wout = (Win + 2 * pad - w->S) / stride + 1;
+    if (want_out) op.out = alloc(op.Hout, op.Wout, w->Cout, out_lo);
+    op.out_single = !out_lo;
+    op.prob_off = p->h_conv_probs.size(); op.nprob = N; op.max_pix = op.Hout * op.Wout;
+    for (int n = 0; n < N; ++n) {
+      ConvProb pb{};
+      pb.Hin = Hin; pb.Win = Win; pb.Hout = op.Hout; pb.Wout = op.Wout;
+      if (x_input) { pb.in0_off = (long long)n * w->Cin * Hin * Win; }
+      else {
+        const Tensor& t0 = p->tensors[in0];
+        pb.in0_off = (long long)n * Hin * Win * t0.C + in0_coff; pb.in0_pitch = Win * t0.C;
+        if (in1 >= 0) { const Tensor& t1 = p->tensors[in1]; pb.in1_off = (long long)n * Hin * Win * t1.C; pb.in1_pitch = Win * t1.C; }
+      }
+      pb.out_off = (long long)n * op.Hout * op.Wout * w->Cout; pb.out_pitch = op.Wout * w->Cout;
+      if (res >= 0) { const Tensor& tr = p->tensors[res]; pb.res_off = (long long)n * tr.H * tr.W * tr.C; pb.res_pitch = tr.W * tr.C; }
+      pb.out32_off = (long long)n * w->Cout * op.Hout * op.Wout;
+      p->h_conv_probs.push_back(pb);
+    }
+    p->ops.push_back(op);
+    return op.out;
+  }
+  int bilinear(int in, int Hout, int Wout) {
+    const Tensor t = p->tensors[in];
+    Op op; op.type = OP_BILINEAR; op.in0 = in; op.out = alloc(Hout, Wout, t.C); op.stage = ST_RESIZE;
+    op.prob_off = p->h_resize_probs.size(); op.nprob = N; op.max_pix = Hout * Wout; op.Hout = Hout; op.Wout = Wout;
+    for (int n = 0; n < N; ++n) {
+      ResizeProb pb{};
+      pb.in_off = (long long)n * t.H * t.W * t.C; pb.Hin = t.H; pb.Win = t.W; pb.in_pitch = t.W * t.C;
+      pb.out_off = (long long)n * Hout * Wout * t.C; pb.Hout = Hout; pb.Wout = Wout; pb.out_pitch = Wout * t.C;
+      p->h_resize_probs.push_back(pb);
+    }
+    p->ops.push_back(op);
+    return op.out;
+  }
+  int maxpool(int in) {
+    const Tensor t = p->tensors[in];
+    Op op; op.type = OP_MAXPOOL; op.in0 = in; op.stage = ST_POOL;
+    op.Hout = (t.H + 2 - 3) / 2 + 1; op.Wout = (t.W + 2 - 3) / 2 + 1;
+    op.out = alloc(op.Hout, op.Wout, t.C);
+    p->ops.push_back(op);
+    return op.out;
+  }
+  void exportf(int in, int ext) {
+    Op op; op.type = OP_EXPORT; op.in0 = in; op.out32_ext = ext; op.stage = ST_EXPORT;
+    p->ops.push_back(op);
+  }
+};
+
+// precision: 0 = CUDA-core fp32 everywhere (on-device reference), 1 = "fast": tensor cores, split-fp16 3-pass in the
+// backbone/decoder and single-pass fp16 in the heads, 2 = "exact": tensor cores, 3-pass everywhere.
+static void assign_tc(Plan* p, int precision) {
+  if (precision == 0 || !tc_available()) return;
+  for (auto& op : p->ops) {
+    if (op.type != OP_CONV || op.x_input) continue;
+    const ConvW* w = op.w;
+    if (!w->tc.valid || op.stride != 1) continue;
+    if (op.C0 % 64 != 0 || (op.C1 % 64) != 0) continue;
+    const bool head = op.stage == ST_HEAD1 || op.stage == ST_HEAD2;
+    op.tc_passes = (head && precision == 1) ? 1 : 3;
+  }
+}
+
+static int build_plan(Net* net, int N, int H, int W, int precision) {
+  KG_REQUIRE(N >= 1 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0,
+             "forward_dec: N=%d H=%d W=%d (H, W must be multiples of 16: the decoder's x2 upsampling assumes it)", N, H, W);
+  std::unique_ptr<Plan> p(new Plan());
+  p->N = N; p->H = H; p->W = W; p->precision = precision;
+  PlanBuilder b{net, p.get(), 0, N};
+  const bool fast_heads = precision == 1 && tc_available();
+  // KGnet.py:276-286
+  int c0a = b.conv("c0_conv.0", -1, -1, 1, 1, true, ST_STEM, -1, -1, false, 0, true, H, W);
+  int c0 = b.conv("c0_conv.2", c0a, -1, 1, 1, true, ST_DECODER);
+  int c1 = b.conv("conv1", -1, -1, 2, 3, true, ST_STEM, -1, -1, false, 0, true, H, W);
+  int x = b.maxpool(c1);
+  int feats[3];
+  for (int l = 0; l < 3; ++l) {
+    for (int blk = 0; blk < net->blocks[l]; ++blk) {
+      const std::string pre = "layer" + std::to_string(l + 1) + "." + std::to_string(blk);
+      const int stride = (blk == 0 && l > 0) ? 2 : 1;
+      int t1 = b.conv(pre + ".conv1", x, -1, 1, 0, true, ST_BACKBONE);
+      int t2 = b.conv(pre + ".conv2", t1, -1, stride, 1, true, ST_BACKBONE);
+      int idn = x;
+      if (blk == 0) idn = b.conv(pre + ".downsample.0", x, -1, stride, 0, false, ST_BACKBONE);
+      x = b.conv(pre + ".conv3", t2, -1, 1, 0, true, ST_BACKBONE, idn);
+    }
+    feats[l] = x;
+  }
+  const int c2 = feats[0], c3 = feats[1], c4 = feats[2];
+  auto T = [&](int id) -> const Tensor& { return p->tensors[id]; };
+  // KGnet.py:288-298 (cat order: upsampled first, skip second)
+  int u4 = b.bilinear(c4, T(c3).H, T(c3).W);
+  int c4u = b.conv("c4_up_conv.0", u4, -1, 1, 1, true, ST_DECODER);
+  int c3c = b.conv("c3_cat_refine.0", c4u, c3, 1, 0, true, ST_DECODER);
+  int u3 = b.bilinear(c3c, T(c2).H, T(c2).W);
+  int c3u = b.conv("c3_up_conv.0", u3, -1, 1, 1, true, ST_DECODER);
+  int c2c = b.conv("c2_cat_refine.0", c3u, c2, 1, 0, true, ST_DECODER);
+  int u2 = b.bilinear(c2c, T(c1).H, T(c1).W);
+  int c2u = b.conv("c2_up_conv.0", u2, -1, 1, 1, true, ST_DECODER);
+  int c1c = b.conv("c1_cat_refine.0", c2u, c1, 1, 0, true, ST_DECODER);
+  int u1 = b.bilinear(c1c, T(c0).H, T(c0).W);
+  int c1u = b.conv("c1_up_conv.0", u1, -1, 1, 1, true, ST_DECODER);
+  int c0c = b.conv("c0_cat_refine.0", c1u, c0, 1, 0, true, ST_DECODER);
+  // KGnet.py:300-316
+  const int cats[4] = {c0c, c1c, c2c, c3c};
+  for (int s = 0; s < 4; ++s) {
+    const int C = kHeadC[s];
+    int h1 = b.conv("heads_l1_c" + std::to_string(s), cats[s], -1, 1, 3, true, ST_HEAD1, -1, -1, false, 0, false, 0, 0, true,
+                    !fast_heads);
+    for (int h = 0; h < 3; ++h) {
+      const std::string nme = std::string(kHeadNames[h]) + "_c" + std::to_string(s) + ".2";
+      b.conv(nme, h1, -1, 1, 3, false, ST_HEAD2, -1, 3 * s + h, h == 0, h * C, false, 0, 0, false);
+      Op& op = p->ops.back();
+      op.C0 = C; op.C1 = 0; op.in_single = fast_heads;
+    }
+  }
+  const int fe[5] = {c0, c1, c2, c3, c4};
+  for (int l = 0; l < 5; ++l) { p->feat_ids[l] = fe[l]; b.exportf(fe[l], 12 + l); }
+  p->bytes = b.off;
+  assign_tc(p.get(), precision);
+  KG_CUDA_CHECK(cudaMalloc(&p->d_conv_probs, p->h_conv_probs.size() * sizeof(ConvProb)));
+  KG_CUDA_CHECK(cudaMemcpy(p->d_conv_probs, p->h_conv_probs.data(), p->h_conv_probs.size() * sizeof(ConvProb), cudaMemcpyHostToDevice));
+  KG_CUDA_CHECK(cudaMalloc(&p->d_resize_probs, p->h_resize_probs.size() * sizeof(ResizeProb)));
+  KG_CUDA_CHECK(cudaMemcpy(p->d_resize_probs, p->h_resize_probs.data(), p->h_resize_probs.size() * sizeof(ResizeProb),
+                           cudaMemcpyHostToDevice));
+  net->plan = std::move(p);
+  net->seg.valid = false;
+  return KG_OK;
+}
+
+static int ensure_plan(Net* net, int N, int H, int W, int precision) {
+  KG_REQUIRE(net != nullptr, "null net handle");
+  if (!net->finalized) { set_error("kg_net: call kg_net_finalize first"); return KG_ERR_STATE; }
+  KG_REQUIRE(precision >= 0 && precision <= 2, "precision=%d (0 cuda-core fp32, 1 fast, 2 exact)", precision);
+  if (precision != 0 && !tc_available()) {
+    set_error("precision=%d needs the tcgen05 path, which failed to initialise: %s", precision, tc_status());
+    return KG_ERR_STATE;
+  }
+  if (net->plan && net->plan->N == N && net->plan->H == H && net->plan->W == W && net->plan->precision == precision) return KG_OK;
+  return build_plan(net, N, H, W, precision);
+}
+
+struct Ptrs {
+  char* ws;
+  __half* hi(const Tensor& t) const { return reinterpret_cast<__half*>(ws + t.off_hi); }
+  __half* lo(const Tensor& t) const { return t.off_lo == (size_t)-1 ? nullptr : reinterpret_cast<__half*>(ws + t.off_lo); }
+};
+
+static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_feats, void* ws, cudaStream_t stream, int* n_launches) {
+  Plan* p = net->plan.get();
+  Ptrs P{(char*)ws};
+  int launches = 0;
+  if (p->tc_workspace != ws) {
+    // (re-)encode the TMA descriptors of every tensor-core op for this workspace base
+    p->tc_ops.clear();
+    for (auto& op : p->ops) {
+      if (op.type != OP_CONV || op.tc_passes == 0) continue;
+      const Tensor& t0 = p->tensors[op.in0];
+      TcConvOp t{};
+      t.w = &op.w->tc; t.bias = op.w->d_b;
+      t.N = p->N; t.H = op.Hout; t.W = op.Wout; t.R = op.w->R; t.S = op.w->S; t.pad = op.pad;
+      t.C0 = op.C0; t.C1 = op.C1; t.Cout = op.w->Cout; t.passes = op.tc_passes;
+      t.in0_hi = P.hi(t0); t.in0_lo = op.in_single ? nullptr : P.lo(t0); t.in0_C = t0.C; t.in0_coff = op.in0_coff;
+      if (op.in1 >= 0) { const Tensor& t1 = p->tensors[op.in1]; t.in1_hi = P.hi(t1); t.in1_lo = P.lo(t1); t.in1_C = t1.C; }
+      if (op.out >= 0) { const Tensor& to = p->tensors[op.out]; t.out_hi = P.hi(to); t.out_lo = op.out_single ? nullptr : P.lo(to); }
+      if (op.res >= 0) { const Tensor& tr = p->tensors[op.res]; t.res_hi = P.hi(tr); t.res_lo = P.lo(tr); }
+      t.relu = op.relu; t.sigmoid = op.sigmoid;
+      KG_TRY(tc_conv_prepare(&t));
+      op.tc_index = (int)p->tc_ops.size();
+      p->tc_ops.push_back(t);
+    }
+    p->tc_workspace = ws;
+  }
+  for (const Op& op : p->ops) {
+    if (op.type == OP_EXPORT && !want_feats) continue;
+    StageScope ts(op.stage, stream);
+    switch (op.type) {
+      case OP_CONV: {
+        float* out32 = op.out32_ext >= 0 ? ext[op.out32_ext] : nullptr;
+        if (op.tc_passes > 0) {
+          KG_TRY(tc_conv_launch(&p->tc_ops[op.tc_index], out32, stream));
+          ++launches;
+          break;
+        }
+        ConvArgs a{};
+        const ConvW* w = op.w;
+        if (op.x_input) { a.x32 = d_x; }
+        else {
+          const Tensor& t0 = p->tensors[op.in0];
+          a.in0_hi = P.hi(t0); a.in0_lo = op.in_single ? nullptr : P.lo(t0); a.in0_ps = t0.C;
+          if (op.in1 >= 0) { const Tensor& t1 = p->tensors[op.in1]; a.in1_hi = P.hi(t1); a.in1_lo = P.lo(t1); a.in1_ps = t1.C; }
+        }
+        a.C0 = op.C0; a.C1 = op.C1; a.w = w->d_w; a.bias = w->d_b; a.Cout = w->Cout; a.R = w->R; a.S = w->S;
+        a.stride = op.stride; a.pad = op.pad; a.relu = op.relu; a.sigmoid = op.sigmoid;
+        if (op.out >= 0) { const Tensor& to = p->tensors[op.out]; a.out_hi = P.hi(to); a.out_lo = op.out_single ? nullptr : P.lo(to); a.out_ps = to.C; }
+        if (op.res >= 0) { const Tensor& tr = p->tensors[op.res]; a.res_hi = P.hi(tr); a.res_lo = P.lo(tr); a.res_ps = tr.C; }
+        a.out32 = out32;
+        a.probs = p->d_conv_probs + op.prob_off;
+        KG_TRY(launch_conv_ffma(a, op.nprob, op.max_pix, stream));
+        ++launches;
+        break;
+      }
+      case OP_BILINEAR: {
+        const Tensor& ti = p->tensors[op.in0]; const Tensor& to = p->tensors[op.out];
+        KG_TRY(launch_bilinear(P.hi(ti), P.lo(ti), ti.C, P.hi(to), P.lo(to), to.C, ti.C, p->d_resize_probs + op.prob_off, op.nprob,
+                               op.max_pix, stream));
+        ++launches;
+        break;
+      }
+      case OP_MAXPOOL: {
+        const Tensor& ti = p->tensors[op.in0]; const Tensor& to = p->tensors[op.out];
+        KG_TRY(launch_maxpool3x3s2(P.hi(ti), P.lo(ti), P.hi(to), P.lo(to), p->N, ti.H, ti.W, ti.C, stream));
+        ++launches;
+        break;
+      }
+      case OP_EXPORT: {
+        const Tensor& ti = p->tensors[op.in0];
+        KG_TRY(launch_export_nchw(P.hi(ti), P.lo(ti), ext[op.out32_ext], p->N, ti.H * ti.W, ti.C, stream));
+        ++launches;
+        break;
+      }
+    }
+  }
+  if (n_launches) *n_launches = launches;
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward_seg (KGnet.py:246-267,321-350): per-box crops at up to 5 levels, variable-size top-down mini decoder.
+// All boxes of the batch run in grouped ("ragged") launches: one launch per layer, blockIdx.z = box.
+static bool patch_rect(float y1n, float x1n, float y2n, float x2n, int h, int w, int* r) {
+  // get_patches (KGnet.py:246-256): np.round is half-to-even, float32 arithmetic under NumPy 2 promotion rules
+  int y1 = (int)rintf(y1n * (float)h), x1 = (int)rintf(x1n * (float)w);
+  int y2 = (int)rintf(y2n * (float)h), x2 = (int)rintf(x2n * (float)w);
+  y1 = y1 > 0 ? y1 : 0; x1 = x1 > 0 ? x1 : 0;
+  y2 = y2 < h - 1 ? y2 : h - 1; x2 = x2 < w - 1 ? x2 : w - 1;
+  if (y2 < y1 || x2 < x1 || y2 - y1 < 2 || x2 - x1 < 2) return false;
+  r[0] = y1; r[1] = x1; r[2] = y2; r[3] = x2;
+  return true;
+}
+
+static const int kSegUpIn[4] = {64, 256, 512, 1024}, kSegOut[4] = {64, 64, 256, 512};
+
+static int seg_prepare(Net* net, int N, int H, int W, const int* counts, const double* boxes, size_t* ws_bytes, long long* mask_floats,
+                       int* n_masks, int* mask_index, int* mask_hw, long long* mask_off) {
+  KG_REQUIRE(net && counts && ws_bytes && mask_floats && n_masks, "kg_net_seg_prepare: null argument");
+  KG_REQUIRE(net->plan && net->plan->N == N && net->plan->H == H && net->plan->W == W,
+             "kg_net_seg_prepare: forward_dec (or kg_net_import_feats) must run first for N=%d H=%d W=%d", N, H, W);
+  Plan* p = net->plan.get();
+  SegPlan& sp = net->seg;
+  sp = SegPlan();
+  sp.N = N; sp.H = H; sp.W = W;
+  int fh[5], fw[5];
+  for (int l = 0; l < 5; ++l) { fh[l] = p->tensors[p->feat_ids[l]].H; fw[l] = p->tensors[p->feat_ids[l]].W; }
+  size_t off = 0;   // elements in one scratch plane
+  auto alloc = [&](int h, int w, int C) { const size_t o = off; off += align_up((size_t)h * w * C, 128); return (long long)o; };
+  std::vector<SegBox> sboxes;
+  int bi = 0, mi = 0;
+  long long moff = 0;
+  for (int n = 0; n < N; ++n) {
+    for (int k = 0; k < counts[n]; ++k, ++bi) {
+      KG_REQUIRE(boxes != nullptr, "kg_net_seg_prepare: null boxes");
+      const double* bx = boxes + (size_t)bi * 5;
+      SegBox sb{}; sb.img = n; sb.L = 0; sb.mask_index = -1;
+      const float y1 = (float)bx[0], x1 = (float)bx[1], y2 = (float)bx[2], x2 = (float)bx[3];   // np.asarray(box, np.float32) (KGnet.py:331)
+      const float h0 = (float)fh[0], w0 = (float)fw[0];
+      for (int l = 0; l < 5; ++l) {
+        if (!patch_rect(y1 / h0, x1 / w0, y2 / h0, x2 / w0, fh[l], fw[l], sb.rect[l])) break;   // (:333-340)
+        sb.L = l + 1;
+      }
+      if (sb.L > 0) {
+        sb.mask_index = mi;
+        const int mh = sb.rect[0][2] - sb.rect[0][0], mw = sb.rect[0][3] - sb.rect[0][1];
+        if (mask_hw) { mask_hw[2 * mi] = mh; mask_hw[2 * mi + 1] = mw; }
+        if (mask_off) mask_off[mi] = moff;
+        moff += (long long)mh * mw;
+        ++mi;
+      }
+      if (mask_index) mask_index[bi] = sb.mask_index;
+      sboxes.push_back(sb);
+    }
+  }
+  sp.n_boxes = bi;
+  auto raw_off = [&](const SegBox& sb, int l) {
+    return (((long long)sb.img * fh[l] + sb.rect[l][0]) * fw[l] + sb.rect[l][1]) * kFeatC[l];
+  };
+  struct Pre { bool raw; int level; long long off; int h, w, C; };
+  std::vector<Pre> pre(sboxes.size());
+  for (size_t i = 0; i < sboxes.size(); ++i) {
+    const SegBox& sb = sboxes[i];
+    if (sb.L == 0) continue;
+    const int l = sb.L - 1;
+    pre[i] = Pre{true, l, raw_off(sb, l), sb.rect[l][2] - sb.rect[l][0], sb.rect[l][3] - sb.rect[l][1], kFeatC[l]};
+  }
+  for (int l = 3; l >= 0; --l) {       // mask_forward (KGnet.py:258-267): deepest level first
+    SegPlan::Step& st = sp.steps[l];
+    for (size_t i = 0; i < sboxes.size(); ++i) {
+      const SegBox& sb = sboxes[i];
+      if (sb.L - 1 <= l) continue;      // this box has no level l+1
+      const int ph = sb.rect[l][2] - sb.rect[l][0], pw = sb.rect[l][3] - sb.rect[l][1];
+      const Pre pr = pre[i];
+      const long long u = alloc(ph, pw, kSegUpIn[l]), v = alloc(ph, pw, kSegOut[l]), c = alloc(ph, pw, kSegOut[l]);
+      ResizeProb rp{};                  // F.interpolate(inputs2, inputs1.shape[2:]) (:110)
+      rp.in_off = pr.off; rp.in_pitch = pr.raw ? fw[pr.level] * kFeatC[pr.level] : pr.w * pr.C;
+      rp.Hin = pr.h; rp.Win = pr.w; rp.Hout = ph; rp.Wout = pw; rp.out_off = u; rp.out_pitch = pw * kSegUpIn[l];
+      if (pr.raw) { st.rs_raw.push_back(rp); st.pix_raw = std::max(st.pix_raw, ph * pw); }
+      else { st.rs_scr.push_back(rp); st.pix_scr = std::max(st.pix_scr, ph * pw); }
+      ConvProb up{};                    // self.up: conv3x3 + ReLU
+      up.in0_off = u; up.in0_pitch = pw * kSegUpIn[l]; up.Hin = ph; up.Win = pw; up.Hout = ph; up.Wout = pw;
+      up.out_off = v; up.out_pitch = pw * kSegOut[l];
+      st.up.push_back(up);
+      ConvProb ct{};                    // self.cat_conv(torch.cat((inputs1, outputs2), 1)): patch first, upsampled second (:111)
+      ct.in0_off = raw_off(sb, l); ct.in0_pitch = fw[l] * kFeatC[l];
+      ct.in1_off = v; ct.in1_pitch = pw * kSegOut[l];
+      ct.Hin = ph; ct.Win = pw; ct.Hout = ph; ct.Wout = pw; ct.out_off = c; ct.out_pitch = pw * kSegOut[l];
+      st.cat.push_back(ct);
+      st.pix = std::max(st.pix, ph * pw);
+      pre[i] = Pre{false, l, c, ph, pw, kSegOut[l]};
+    }
+  }
+  for (size_t i = 0; i < sboxes.size(); ++i) {   // seg_head (KGnet.py:145-147,344-345)
+    const SegBox& sb = sboxes[i];
+    if (sb.L == 0) continue;
+    const Pre pr = pre[i];
+    const int ph = pr.h, pw = pr.w;
+    const long long t = alloc(ph, pw, 64);
+    ConvProb a{};
+    a.in0_off = pr.off; a.in0_pitch = pr.raw ? fw[0] * kFeatC[0] : pw * 64; a.Hin = ph; a.Win = pw; a.Hout = ph; a.Wout = pw;
+    a.out_off = t; a.out_pitch = pw * 64;
+    if (pr.raw) { sp.h0_raw.push_back(a); sp.pix_h0_raw = std::max(sp.pix_h0_raw, ph * pw); }
+    else { sp.h0_scr.push_back(a); sp.pix_h0_scr = std::max(sp.pix_h0_scr, ph * pw); }
+    ConvProb b{};
+    b.in0_off = t; b.in0_pitch = pw * 64; b.Hin = ph; b.Win = pw; b.Hout = ph; b.Wout = pw;
+    b.out32_off = mask_off ? mask_off[sb.mask_index] : 0;
+    sp.h1.push_back(b);
+    sp.pix_h1 = std::max(sp.pix_h1, ph * pw);
+  }
+  if (!mask_off) {   // offsets are needed internally even when the caller does not ask for them
+    long long o = 0; size_t k = 0;
+    for (size_t i = 0; i < sboxes.size(); ++i) {
+      if (sboxes[i].L == 0) continue;
+      sp.h1[k++].out32_off = o;
+      o += (long long)(sboxes[i].rect[0][2] - sboxes[i].rect[0][0]) * (sboxes[i].rect[0][3] - sboxes[i].rect[0][1]);
+    }
+  }
+  sp.scratch_halfs = off;
+  sp.mask_floats = moff;
+  sp.n_masks = mi;
+  sp.valid = true;
+  *ws_bytes = align_up(off * sizeof(__half), 256) * 2 + 256;
+  *mask_floats = moff;
+  *n_masks = mi;
+  return KG_OK;
+}
+
+static int seg_run(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes, float* d_masks, cudaStream_t stream, int* n_launches) {
+  SegPlan& sp = net->seg;
+  if (!sp.valid || !net->plan) { set_error("kg_net_forward_seg: call kg_net_seg_prepare first"); return KG_ERR_STATE; }
+  const size_t plane_bytes = align_up(sp.scratch_halfs * sizeof(__half), 256);
+  if (seg_bytes < plane_bytes * 2) { set_error("kg_net_forward_seg: workspace too small (%zu < %zu)", seg_bytes, plane_bytes * 2); return KG_ERR_WORKSPACE; }
+  if (sp.n_masks == 0) { if (n_launches) *n_launches = 0; return KG_OK; }
+  KG_REQUIRE(dec_ws && seg_ws && d_masks, "kg_net_forward_seg: null buffer");
+  Plan* p = net->plan.get();
+  Ptrs P{(char*)dec_ws};
+  __half* s_hi = reinterpret_cast<__half*>(seg_ws);
+  __half* s_lo = reinterpret_cast<__half*>((char*)seg_ws + plane_bytes);
+  // one upload of every problem descriptor
+  std::vector<char> blob;
+  auto put = [&](const void* src, size_t bytes) { const size_t o = align_up(blob.size(), 16); blob.resize(o + bytes); memcpy(blob.data() + o, src, bytes); return o; };
+  size_t o_rs_raw[4], o_rs_scr[4], o_up[4], o_cat[4];
+  for (int l = 0; l < 4; ++l) {
+    auto& st = sp.steps[l];
+    o_rs_raw[l] = put(st.rs_raw.data(), st.rs_raw.size() * sizeof(ResizeProb));
+    o_rs_scr[l] = put(st.rs_scr.data(), st.rs_scr.size() * sizeof(ResizeProb));
+    o_up[l] = put(st.up.data(), st.up.size() * sizeof(ConvProb));
+    o_cat[l] = put(st.cat.data(), st.cat.size() * sizeof(ConvProb));
+  }
+  const size_t o_h0r = put(sp.h0_raw.data(), sp.h0_raw.size() * sizeof(ConvProb));
+  const size_t o_h0s = put(sp.h0_scr.data(), sp.h0_scr.size() * sizeof(ConvProb));
+  const size_t o_h1 = put(sp.h1.data(), sp.h1.size() * sizeof(ConvProb));
+  if (net->seg_probs_bytes < blob.size()) {
+    if (net->d_seg_probs) cudaFree(net->d_seg_probs);
+    net->d_seg_probs = nullptr; net->seg_probs_bytes = 0;
+    KG_CUDA_CHECK(cudaMalloc(&net->d_seg_probs, blob.size() * 2));
+    net->seg_probs_bytes = blob.size() * 2;
+  }
+  KG_CUDA_CHECK(cudaMemcpyAsync(net->d_seg_probs, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
+  KG_CUDA_CHECK(cudaStreamSynchronize(stream));   // blob is a pageable temporary
+  char* dp = (char*)net->d_seg_probs;
+  int launches = 0;
+  StageScope ts(ST_SEG, stream);
+  auto feat = [&](int l) -> const Tensor& { return p->tensors[p->feat_ids[l]]; };
+  auto conv = [&](const std::string& wname, const __half* i0h, const __half* i0l, int C0, int ps0, const __half* i1h, const __half* i1l, int C1,
+                  int ps1, __half* oh, __half* ol, int ops, float* o32, bool relu, bool sig, const void* probs, int nprob, int pix) -> int {
+    if (nprob == 0) return KG_OK;
+    const ConvW& w = net->convs.at(wname);
+    ConvArgs a{};
+    a.in0_hi = i0h; a.in0_lo = i0l; a.C0 = C0; a.in0_ps = ps0; a.in1_hi = i1h; a.in1_lo = i1l; a.C1 = C1; a.in1_ps = ps1;
+    a.w = w.d_w; a.bias = w.d_b; a.Cout = w.Cout; a.R = w.R; a.S = w.S; a.stride = 1; a.pad = w.R / 2;
+    a.out_hi = oh; a.out_lo = ol; a.out_ps = ops; a.out32 = o32; a.relu = relu; a.sigmoid = sig;
+    a.probs = reinterpret_cast<const ConvProb*>(probs);
+    ++launches;
+    return launch_conv_ffma(a, nprob, pix, stream);
+  };
+  for (int l = 3; l >= 0; --l) {
+    auto& st = sp.steps[l];
+    if (st.up.empty()) continue;
+    const std::string pre = "skip_combine." + std::to_string(l);
+    const Tensor& fd = feat(l + 1);
+    if (!st.rs_raw.empty()) {
+      KG_TRY(launch_bilinear(P.hi(fd), P.lo(fd), fd.C, s_hi, s_lo, kSegUpIn[l], kSegUpIn[l],
+                             reinterpret_cast<const ResizeProb*>(dp + o_rs_raw[l]), (int)st.rs_raw.size(), st.pix_raw, stream));
+      ++launches;
+    }
+    if (!st.rs_scr.empty()) {
+      KG_TRY(launch_bilinear(s_hi, s_lo, kSegUpIn[l], s_hi, s_lo, kSegUpIn[l], kSegUpIn[l],
+                             reinterpret_cast<const ResizeProb*>(dp + o_rs_scr[l]), (int)st.rs_scr.size(), st.pix_scr, stream));
+      ++launches;
+    }
+    KG_TRY(conv(pre + ".up.0", s_hi, s_lo, kSegUpIn[l], kSegUpIn[l], nullptr, nullptr, 0, 0, s_hi, s_lo, kSegOut[l], nullptr, true, false,
+                dp + o_up[l], (int)st.up.size(), st.pix));
+    const Tensor& fl = feat(l);
+    KG_TRY(conv(pre + ".cat_conv.0", P.hi(fl), P.lo(fl), fl.C, fl.C, s_hi, s_lo, kSegOut[l], kSegOut[l], s_hi, s_lo, kSegOut[l], nullptr, true,
+                false, dp + o_cat[l], (int)st.cat.size(), st.pix));
+  }
+  const Tensor& f0 = feat(0);
+  KG_TRY(conv("seg_head.0", P.hi(f0), P.lo(f0), 64, 64, nullptr, nullptr, 0, 0, s_hi, s_lo, 64, nullptr, true, false, dp + o_h0r,
+              (int)sp.h0_raw.size(), sp.pix_h0_raw));
+  KG_TRY(conv("seg_head.0", s_hi, s_lo, 64, 64, nullptr, nullptr, 0, 0, s_hi, s_lo, 64, nullptr, true, false, dp + o_h0s,
+              (int)sp.h0_scr.size(), sp.pix_h0_scr));
+  KG_TRY(conv("seg_head.2", s_hi, s_lo, 64, 64, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, d_masks, false, true, dp + o_h1, (int)sp.h1.size(),
+              sp.pix_h1));
+  if (n_launches) *n_launches = launches;
+  return KG_OK;
+}
+
+// Single-layer entry used by the unit tests (one nn.Conv2d [+ReLU] [+residual], KGnet.py:45-61 style).
+static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R, int S,
+                       int stride, int pad, int relu, const float* d_res, int mode, float* d_y, cudaStream_t stream) {
+  KG_REQUIRE(d_x && h_w && d_y && N > 0 && Cin > 0 && Cout > 0, "kg_conv2d_nchw: bad arguments");
+  KG_REQUIRE(mode == 0 || mode == 1 || mode == 3, "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 or 3 (tensor-core passes)");
+  Net tmp;
+  KG_TRY(set_conv(&tmp, "c", h_w, Cout, Cin, R, S, h_bias, nullptr, nullptr, nullptr, nullptr, 0.0));
+  ConvW& w = tmp.convs.at("c");
+  KG_TRY(upload_conv(w));
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const size_t in_e = (size_t)N * H * W * Cin, out_e = (size_t)N * Ho * Wo * Cout;
+  __half *xh = nullptr, *xl = nullptr, *yh = nullptr, *yl = nullptr, *rh = nullptr, *rl = nullptr;
+  ConvProb* d_probs = nullptr;
+  auto cleanup = [&]() { cudaFree(xh); cudaFree(xl); cudaFree(yh); cudaFree(yl); cudaFree(rh); cudaFree(rl); cudaFree(d_probs); };
+  int rc = KG_OK;
+  do {
+    if (cudaMalloc(&xh, in_e * 2) || cudaMalloc(&xl, in_e * 2) || cudaMalloc(&yh, out_e * 2) || cudaMalloc(&yl, out_e * 2)) { rc = KG_ERR_CUDA; break; }
+    if ((rc = launch_import_nchw(d_x, xh, xl, N, H * W, Cin, stream)) != KG_OK) break;
+    if (d_res) {
+      if (cudaMalloc(&rh, out_e * 2) || cudaMalloc(&rl, out_e * 2)) { rc = KG_ERR_CUDA; break; }
+      if ((rc = launch_import_nchw(d_res, rh, rl, N, Ho * Wo, Cout, stream)) != KG_OK) break;
+    }
+    if (mode == 0) {
+      std::vector<ConvProb> probs(N);
+      for (int n = 0; n < N; ++n) {
+        ConvProb pb{};
+        pb.Hin = H; pb.Win = W; pb.Hout = Ho; pb.Wout = Wo; pb.in0_off = (long long)n * H * W * Cin; pb.in0_pitch = W * Cin;
+        pb.out_off = (long long)n * Ho * Wo * Cout; pb.out_pitch = Wo * Cout; pb.res_off = pb.out_off; pb.res_pitch = pb.out_pitch;
+        probs[n] = pb;
+      }
+      if (cudaMalloc(&d_probs, N * sizeof(ConvProb)) || cudaMemcpy(d_probs, probs.data(), N * sizeof(ConvProb), cudaMemcpyHostToDevice)) { rc = KG_ERR_CUDA; break; }
+      ConvArgs a{};
+      a.in0_hi = xh; a.in0_lo = xl; a.C0 = Cin; a.in0_ps = Cin; a.w = w.d_w; a.bias = w.d_b; a.Cout = Cout; a.R = R; a.S = S;
+      a.stride = stride; a.pad = pad; a.out_hi = yh; a.out_lo = yl; a.out_ps = Cout; a.res_hi = rh; a.res_lo = rl; a.res_ps = Cout;
+      a.relu = relu; a.probs = d_probs;
+      if ((rc = launch_conv_ffma(a, N, Ho * Wo, stream)) != KG_OK) break;
+    } else {
+      if (stride != 1 || !tc_layer_supported(Cin, Cout, R, S) || Cout % 16 != 0 || 2 * pad != R - 1 || R != S) {
+        set_error("kg_conv2d_nchw: shape not supported by the tensor-core path"); rc = KG_ERR_INVALID; break;
+      }
+      if ((rc = tc_pack_weights(w.h_w.data(), Cin, Cout, R, S, &w.tc)) != KG_OK) break;
+      TcConvOp t{};
+      t.w = &w.tc; t.bias = w.d_b; t.N = N; t.H = Ho; t.W = Wo; t.R = R; t.S = S; t.pad = pad; t.C0 = Cin; t.C1 = 0; t.Cout = Cout;
+      t.passes = mode; t.in0_hi = xh; t.in0_lo = xl; t.in0_C = Cin; t.out_hi = yh; t.out_lo = yl; t.res_hi = rh; t.res_lo = rl; t.relu = relu != 0;
+      if ((rc = tc_conv_prepare(&t)) != KG_OK) break;
+      if ((rc = tc_conv_launch(&t, nullptr, stream)) != KG_OK) break;
+    }
+    if ((rc = launch_export_nchw(yh, yl, d_y, N, Ho * Wo, Cout, stream)) != KG_OK) break;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("kg_conv2d_nchw: %s", cudaGetErrorString(cudaGetLastError())); rc = KG_ERR_CUDA; }
+  } while (0);
+  if (rc == KG_ERR_CUDA && cudaPeekAtLastError() != cudaSuccess) set_error("kg_conv2d_nchw: CUDA error %s", cudaGetErrorString(cudaGetLastError()));
+  cleanup();
+  return rc;
+}
+
+}  // namespace kg
+
+using namespace kg;
+
+extern "C" {
+
+int kg_net_create(kg_net** out, const int* blocks) {
+  KG_REQUIRE(out != nullptr, "kg_net_create: null out");
+  Net* n = new Net();
+  if (blocks) for (int i = 0; i < 3; ++i) { KG_REQUIRE(blocks[i] >= 1 && blocks[i] <= 64, "kg_net_create: blocks[%d]=%d", i, blocks[i]); n->blocks[i] = blocks[i]; }
+  *out = reinterpret_cast<kg_net*>(n);
+  return KG_OK;
+}
+
+void kg_net_destroy(kg_net* h) { delete reinterpret_cast<Net*>(h); }
+
+int kg_net_set_conv(kg_net* h, const char* name, const float* h_w, int Cout, int Cin, int R, int S, const float* h_bias,
+                    const float* h_bn_weight, const float* h_bn_bias, const float* h_bn_mean, const float* h_bn_var, double bn_eps) {
+  return set_conv(reinterpret_cast<Net*>(h), name, h_w, Cout, Cin, R, S, h_bias, h_bn_weight, h_bn_bias, h_bn_mean, h_bn_var, bn_eps);
+}
+
+int kg_net_finalize(kg_net* h) {
+  KG_REQUIRE(h != nullptr, "kg_net_finalize: null handle");
+  return finalize(reinterpret_cast<Net*>(h));
+}
+
+size_t kg_net_workspace_bytes(kg_net* h, int N, int H, int W, int precision) {
+  Net* net = reinterpret_cast<Net*>(h);
+  if (ensure_plan(net, N, H, W, precision) != KG_OK) return 0;
+  return net->plan->bytes;
+}
+
+int kg_net_forward_dec(kg_net* h, const float* d_x, int N, int H, int W, float* const* d_heads, float* const* d_feats, int precision,
+                       void* d_workspace, size_t workspace_bytes, void* stream, int* n_launches) {
+  Net* net = reinterpret_cast<Net*>(h);
+  KG_REQUIRE(d_x && d_heads && d_workspace, "kg_net_forward_dec: null argument");
+  KG_TRY(ensure_plan(net, N, H, W, precision));
+  if (workspace_bytes < net->plan->bytes) {
+    set_error("kg_net_forward_dec: workspace too small (%zu < %zu bytes)", workspace_bytes, net->plan->bytes);
+    return KG_ERR_WORKSPACE;
+  }
+  float* ext[17];
+  for (int i = 0; i < 12; ++i) { KG_REQUIRE(d_heads[i] != nullptr, "kg_net_forward_dec: d_heads[%d] is null", i); ext[i] = d_heads[i]; }
+  for (int i = 0; i < 5; ++i) ext[12 + i] = d_feats ? d_feats[i] : nullptr;
+  return run_plan(net, d_x, ext, d_feats != nullptr, d_workspace, (cudaStream_t)stream, n_launches);
+}
+
+int kg_net_import_feats(kg_net* h, const float* const* d_feats, int N, int H, int W, int precision, void* d_workspace, size_t workspace_bytes,
+                        void* stream) {
+  Net* net = reinterpret_cast<Net*>(h);
+  KG_REQUIRE(d_feats && d_workspace, "kg_net_import_feats: null argument");
+  KG_TRY(ensure_plan(net, N, H, W, precision));
+  if (workspace_bytes < net->plan->bytes) { set_error("kg_net_import_feats: workspace too small"); return KG_ERR_WORKSPACE; }
+  Ptrs P{(char*)d_workspace};
+  for (int l = 0; l < 5; ++l) {
+    const Tensor& t = net->plan->tensors[net->plan->feat_ids[l]];
+    KG_REQUIRE(d_feats[l] != nullptr, "kg_net_import_feats: d_feats[%d] is null", l);
+    KG_TRY(launch_import_nchw(d_feats[l], P.hi(t), P.lo(t), N, t.H * t.W, t.C, (cudaStream_t)stream));
+  }
+  return KG_OK;
+}
+
+int kg_net_seg_prepare(kg_net* h, int N, int H, int W, const int* box_counts, const double* h_boxes, size_t* seg_workspace_bytes,
+                       long long* mask_floats, int* n_masks, int* h_mask_index, int* h_mask_hw, long long* h_mask_off) {
+  return seg_prepare(reinterpret_cast<Net*>(h), N, H, W, box_counts, h_boxes, seg_workspace_bytes, mask_floats, n_masks, h_mask_index,
+                     h_mask_hw, h_mask_off);
+}
+
+int kg_net_forward_seg(kg_net* h, void* d_dec_workspace, void* d_seg_workspace, size_t seg_workspace_bytes, float* d_masks, void* stream,
+                       int* n_launches) {
+  KG_REQUIRE(h != nullptr, "kg_net_forward_seg: null handle");
+  return seg_run(reinterpret_cast<Net*>(h), d_dec_workspace, d_seg_workspace, seg_workspace_bytes, d_masks, (cudaStream_t)stream, n_launches);
+}
+
+int kg_conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R, int S, int stride,
+                   int pad, int relu, const float* d_res, int mode, float* d_y, void* stream) {
+  return conv2d_nchw(d_x, N, Cin, H, W, h_w, h_bias, Cout, R, S, stride, pad, relu, d_res, mode, d_y, (cudaStream_t)stream);
+}
+
+int kg_tc_available(void) { return tc_available() ? 1 : 0; }
+const char* kg_tc_status(void) { return tc_status(); }
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+// CUDA-core kernels of the KGnet forward: generic (ragged, windowed, two-source) FFMA convolution, bilinear
+// resize, 3x3/s2 max pool and layout import/export.  These cover the layers the tcgen05 implicit-GEMM kernel
+// (tc_conv.cu) does not take: Cin=3 stems, stride-2 convs, and the variable-size per-box mask branch.
+// They are also the on-device fp32 reference the tensor-core kernel is validated against.
+#include "net.cuh"
+
+namespace kg {
+
+__device__ __forceinline__ float ld_split(const __half* hi, const __half* lo, long long i) {
+  float v = __half2float(hi[i]);
+  if (lo != nullptr) v += __half2float(lo[i]);
+  return v;
+}
+
+__device__ __forceinline__ void st_split(__half* hi, __half* lo, long long i, float v) {
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
+  const __half h = __float2half_rn(v);
+  if (hi != nullptr) hi[i] = h;
+  if (lo != nullptr) lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic convolution (KGnet.py: every nn.Conv2d of the model).  Tile: 64 output pixels x 64 output channels
+// per CTA, 4x4 per thread, K chunks of 16 input channels per filter tap.  fp32 accumulation in tap-major,
+// channel-minor order.
+constexpr int FT_P = 64, FT_C = 64, FT_K = 16;
+
+template <bool X32>
+__global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs a) {
+  const ConvProb pb = a.probs[blockIdx.z];
+  const int npix = pb.Hout * pb.Wout;
+  const int p0 = blockIdx.x * FT_P;
+  if (p0 >= npix) return;
+  const int co0 = blockIdx.y * FT_C;
+  __shared__ float sA[FT_K][FT_P + 4];
+  __shared__ __align__(16) float sB[FT_K][FT_C];
+  const int tid = threadIdx.x;
+  const int lp = tid >> 2, lc = (tid & 3) * 4;
+  const int p = p0 + lp;
+  const bool pv = p < npix;
+  const int oy = pv ? p / pb.Wout : 0, ox = pv ? p - oy * pb.Wout : 0;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int Cin = a.C0 + a.C1;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ntaps = a.R * a.S;
+  for (int tap = 0; tap < ntaps; ++tap) {
+    const int r = tap / a.S, s = tap - r * a.S;
+    const int iy = oy * a.stride - a.pad + r, ix = ox * a.stride - a.pad + s;
+    const bool inb = pv && iy >= 0 && iy < pb.Hin && ix >= 0 && ix < pb.Win;
+    for (int c0 = 0; c0 < Cin; c0 += FT_K) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (inb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + lc + j;
+          if (c < Cin) {
+            if (X32) {
+              v[j] = __ldg(a.x32 + pb.in0_off + ((long long)c * pb.Hin + iy) * pb.Win + ix);
+            } else if (c < a.C0) {
+              v[j] = ld_split(a.in0_hi, a.in0_lo, pb.in0_off + (long long)iy * pb.in0_pitch + (long long)ix * a.in0_ps + c);
+            } else {
+              v[j] = ld_split(a.in1_hi, a.in1_lo, pb.in1_off + (long long)iy * pb.in1_pitch + (long long)ix * a.in1_ps + (c - a.C0));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sA[lc + j][lp] = v[j];
+      {
+        const int k = tid >> 4, n = (tid & 15) * 4;
+        const int c = c0 + k;
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < Cin) {
+          const float* wp = a.w + ((long long)tap * Cin + c) * a.Cout + co0 + n;
+          if (co0 + n + 3 < a.Cout && (a.Cout & 3) == 0) {
+            wv = __ldg(reinterpret_cast<const float4*>(wp));
+          } else {
+            if (co0 + n < a.Cout) wv.x = __ldg(wp);
+            if (co0 + n + 1 < a.Cout) wv.y = __ldg(wp + 1);
+            if (co0 + n + 2 < a.Cout) wv.z = __ldg(wp + 2);
+            if (co0 + n + 3 < a.Cout) wv.w = __ldg(wp + 3);
+          }
+        }
+        *reinterpret_cast<float4*>(&sB[k][n]) = wv;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < FT_K; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+        const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = p0 + ty * 4 + i;
+    if (q >= npix) continue;
+    const int qy = q / pb.Wout, qx = q - qy * pb.Wout;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co >= a.Cout) continue;
+      float v = acc[i][j] + (a.bias != nullptr ? __ldg(a.bias + co) : 0.f);
+      if (a.res_hi != nullptr)
+        v += ld_split(a.res_hi, a.res_lo, pb.res_off + (long long)qy * pb.res_pitch + (long long)qx * a.res_ps + co);
+      if (a.relu) v = fmaxf(v, 0.f);
+      if (a.sigmoid) v = 1.f / (1.f + expf(-v));
+      if (a.out_hi != nullptr || a.out_lo != nullptr)
+        st_split(a.out_hi, a.out_lo, pb.out_off + (long long)qy * pb.out_pitch + (long long)qx * a.out_ps + co, v);
+      if (a.out32 != nullptr) a.out32[pb.out32_off + ((long long)co * pb.Hout + qy) * pb.Wout + qx] = v;
+    }
+  }
+}
+
+int launch_conv_ffma(const ConvArgs& a, int nprob, int max_pix, cudaStream_t s) {
+  if (nprob <= 0 || max_pix <= 0) return KG_OK;
+  dim3 grid(ceil_div(max_pix, FT_P), ceil_div(a.Cout, FT_C), nprob);
+  KG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv_ffma: grid too large (%u, %u)", grid.y, grid.z);
+  if (a.x32 != nullptr) conv_ffma_kernel<true><<<grid, 256, 0, s>>>(a);
+  else conv_ffma_kernel<false><<<grid, 256, 0, s>>>(a);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// F.interpolate(mode='bilinear', align_corners=False) to an explicit size (KGnet.py:110,288-297), fp32 math.
+__global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                                       int in_ps, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                       int out_ps, int C, const ResizeProb* __restrict__ probs) {
+  const ResizeProb pb = probs[blockIdx.z];
+  const int cg = C >> 2;   // channel quads
+  const long long total = (long long)pb.Hout * pb.Wout * cg;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int c = (int)(e % cg) * 4;
+  const int q = (int)(e / cg);
+  const int oy = q / pb.Wout, ox = q - oy * pb.Wout;
+  const float rh = (float)pb.Hin / (float)pb.Hout, rw = (float)pb.Win / (float)pb.Wout;
+  float sy = rh * ((float)oy + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+  float sx = rw * ((float)ox + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int yp = y0 < pb.Hin - 1 ? 1 : 0, xp = x0 < pb.Win - 1 ? 1 : 0;
+  const float ly1 = sy - (float)y0, ly0 = 1.f - ly1, lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+  const long long b00 = pb.in_off + (long long)y0 * pb.in_pitch + (long long)x0 * in_ps + c;
+  const long long b01 = b00 + (long long)xp * in_ps, b10 = b00 + (long long)yp * pb.in_pitch, b11 = b10 + (long long)xp * in_ps;
+  const long long o = pb.out_off + (long long)oy * pb.out_pitch + (long long)ox * out_ps + c;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float v00 = ld_split(in_hi, in_lo, b00 + j), v01 = ld_split(in_hi, in_lo, b01 + j);
+    const float v10 = ld_split(in_hi, in_lo, b10 + j), v11 = ld_split(in_hi, in_lo, b11 + j);
+    const float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    st_split(out_hi, out_lo, o + j, v);
+  }
+}
+
+int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
+                    const ResizeProb* probs, int nprob, int max_pix, cudaStream_t s) {
+  if (nprob <= 0 || max_pix <= 0) return KG_OK;
+  KG_REQUIRE((C & 3) == 0, "bilinear: C=%d must be a multiple of 4", C);
+  dim3 grid((unsigned)(((long long)max_pix * (C >> 2) + 255) / 256), 1, nprob);
+  bilinear_kernel<<<grid, 256, 0, s>>>(in_hi, in_lo, in_ps, out_hi, out_lo, out_ps, C, probs);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (KGnet.py:134,282).
+__global__ void __launch_bounds__(256) maxpool_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                                      __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int Hin,
+                                                      int Win, int Hout, int Wout, int C) {
+  const long long total = (long long)N * Hout * Wout * C;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int c = (int)(e % C);
+  long long q = e / C;
+  const int ox = (int)(q % Wout); q /= Wout;
+  const int oy = (int)(q % Hout);
+  const int n = (int)(q / Hout);
+  float m = -INFINITY;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int iy = oy * 2 + dy;
+    if (iy < 0 || iy >= Hin) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ix = ox * 2 + dx;
+      if (ix < 0 || ix >= Win) continue;
+      m = fmaxf(m, ld_split(in_hi, in_lo, (((long long)n * Hin + iy) * Win + ix) * C + c));
+    }
+  }
+  st_split(out_hi, out_lo, e, m);
+}
+
+int launch_maxpool3x3s2(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int N, int Hin, int Win, int C,
+                        cudaStream_t s) {
+  const int Hout = (Hin + 2 - 3) / 2 + 1, Wout = (Win + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * Hout * Wout * C;
+  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, N, Hin, Win, Hout, Wout, C);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion at the API edge: split-fp16 NHWC <-> fp32 NCHW, 32 pixels x 32 channels per CTA via smem.
+__global__ void __launch_bounds__(256) export_nchw_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                                          float* __restrict__ out, int HW, int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    tile[i][tx] = (p < HW && c < C) ? ld_split(in_hi, in_lo, ((long long)n * HW + p) * C + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    if (p < HW && c < C) out[((long long)n * C + c) * HW + p] = tile[tx][i];
+  }
+}
+
+__global__ void __launch_bounds__(256) import_nchw_kernel(const float* __restrict__ in, __half* __restrict__ out_hi,
+                                                          __half* __restrict__ out_lo, int HW, int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    tile[i][tx] = (p < HW && c < C) ? in[((long long)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    if (p < HW && c < C) st_split(out_hi, out_lo, ((long long)n * HW + p) * C + c, tile[tx][i]);
+  }
+}
+
+int launch_export_nchw(const __half* in_hi, const __half* in_lo, float* out, int N, int HW, int C, cudaStream_t s) {
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N);
+  export_nchw_kernel<<<grid, 256, 0, s>>>(in_hi, in_lo, out, HW, C);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+int launch_import_nchw(const float* in, __half* out_hi, __half* out_lo, int N, int HW, int C, cudaStream_t s) {
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N);
+  import_nchw_kernel<<<grid, 256, 0, s>>>(in, out_hi, out_lo, HW, C);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+}  // namespace kg

@@ -1,0 +1,476 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores of sm_100a (KGnet.py: every stride-1 conv with
+// Cin % 64 == 0 — backbone 1x1/3x3, decoder 3x3 / concat-1x1, the 7x7 heads).
+//
+//   GEMM view      M = output pixels (a BH x BW patch of one image = 128 rows), N = output channels (<= 256 per CTA),
+//                  K = taps x input channels, walked as (tap, 64-channel chunk) steps.
+//   A operand      no im2col buffer: for filter tap (r, s) the 128 x 64 activation tile is ONE 4-D TMA box load of the
+//                  NHWC tensor at (c0, x0 + s - pad, y0 + r - pad, n); out-of-image coordinates are zero-filled by
+//                  TMA, which is exactly the conv's zero padding.  The box lands in shared memory as 128 rows of
+//                  128 B with the 128-byte swizzle, i.e. the canonical K-major UMMA layout.
+//   B operand      weights pre-packed [tap][cout][cin] fp16, one 3-D TMA box (64 x BN x 1) per step.
+//   MMA            tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, K = 16 x 4 per step, fp32 accumulators in
+//                  TMEM (MT accumulators of BN columns; MT = 2 shares each weight tile between two pixel tiles).
+//   precision      passes = 1: fp16 x fp16.  passes = 3: split-fp16 (hi*hi + lo*hi + hi*lo), ~fp32 accuracy.
+//   concat         torch.cat((a, b), 1) feeding a conv = two TMA sources walked back to back along K.
+//   epilogue       tcgen05.ld -> * 1/scale + bias (+ residual) -> ReLU / sigmoid -> split-fp16 NHWC and/or fp32 NCHW.
+//   roles          warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue (one TMEM lane quadrant each);
+//                  smem full/empty mbarrier ring between producer and MMA, one tmem_full barrier to the epilogue.
+#include "tc_conv.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+namespace kg {
+
+constexpr int TC_BM = 128;          // rows (pixels) per accumulator tile
+constexpr int TC_BK = 64;           // channels per K step (one 128-byte swizzle row)
+constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KiB
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_SMEM = 227 * 1024;
+
+struct TcParams {
+  CUtensorMap a_map[2][2];          // [source][plane hi/lo]
+  CUtensorMap w_map[2];             // [plane hi/lo]
+  const float* bias;
+  __half* out_hi; __half* out_lo;
+  float* out32;
+  const __half* res_hi; const __half* res_lo;
+  float inv_scale;
+  int N, H, W, Cout;
+  int R, S, pad;
+  int chunks0, chunks1, coff0;
+  int BN, BW, BH, tiles_x, tiles_y, m_tiles;
+  int MT, NPL, passes, stages;
+  int relu, sigmoid;
+  unsigned tmem_cols;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major; canonical value 1)
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                  // descriptor version
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 128B swizzle atoms need 1024-byte alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = (uint32_t)(p.MT * p.NPL) * TC_A_TILE;
+  const uint32_t w_tile = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)p.NPL * w_tile;
+  const uint32_t bars = smem0 + (uint32_t)p.stages * stage_bytes;
+  const uint32_t bar_tmem_full = bars + 16u * p.stages;
+  const uint32_t tmem_slot = bar_tmem_full + 8u;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.a_map[0][0]); prefetch_tmap(&p.w_map[0]);
+    if (p.NPL == 2) { prefetch_tmap(&p.a_map[0][1]); prefetch_tmap(&p.w_map[1]); }
+    if (p.chunks1 > 0) { prefetch_tmap(&p.a_map[1][0]); if (p.NPL == 2) prefetch_tmap(&p.a_map[1][1]); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(bar_tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int chunks = p.chunks0 + p.chunks1;
+  const int ksteps = p.R * p.S * chunks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int m_first = blockIdx.x * p.MT;
+  const int n0 = blockIdx.y * p.BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int tn[2], ty0[2], tx0[2];
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int m = m_first + mt;
+        if (m < p.m_tiles) {
+          const int n = m / tiles_per_img, rem = m - n * tiles_per_img;
+          const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+          tn[mt] = n; ty0[mt] = ty * p.BH; tx0[mt] = tx * p.BW;
+        } else { tn[mt] = p.N; ty0[mt] = 0; tx0[mt] = 0; }       // out-of-range tile: TMA zero-fills
+      }
+      int stage = 0; uint32_t phase = 0;
+      int tap = 0, ch = 0;
+      for (int i = 0; i < ksteps; ++i) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sbase = smem0 + (uint32_t)stage * stage_bytes;
+        mbar_expect_tx(full_bar(stage), stage_bytes);
+        const int r = tap / p.S, s = tap - r * p.S;
+        const int src = ch < p.chunks0 ? 0 : 1;
+        const int c = src == 0 ? p.coff0 + ch * TC_BK : (ch - p.chunks0) * TC_BK;
+        for (int mt = 0; mt < p.MT; ++mt)
+          for (int pl = 0; pl < p.NPL; ++pl)
+            tma_load_4d(sbase + (uint32_t)(mt * p.NPL + pl) * TC_A_TILE, &p.a_map[src][pl], c, tx0[mt] + s - p.pad,
+                        ty0[mt] + r - p.pad, tn[mt], full_bar(stage));
+        for (int pl = 0; pl < p.NPL; ++pl)
+          tma_load_3d(sbase + a_bytes + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, tap, full_bar(stage));
+        if (++ch == chunks) { ch = 0; ++tap; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < ksteps; ++i) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sbase = smem0 + (uint32_t)stage * stage_bytes;
+        for (int mt = 0; mt < p.MT; ++mt) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(mt * p.BN);
+          for (int ps = 0; ps < p.passes; ++ps) {
+            const int apl = ps == 1 ? 1 : 0, wpl = ps == 2 ? 1 : 0;      // hi*hi, lo*hi, hi*lo
+            const uint32_t a_addr = sbase + (uint32_t)(mt * p.NPL + apl) * TC_A_TILE;
+            const uint32_t b_addr = sbase + a_bytes + (uint32_t)wpl * w_tile;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_f16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, (i | ps | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(bar_tmem_full);
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    mbar_wait(bar_tmem_full, 0);
+    tc_fence_after();
+    const int HW = p.H * p.W;
+    for (int mt = 0; mt < p.MT; ++mt) {
+      const int m = m_first + mt;
+      if (m >= p.m_tiles) break;
+      const int n = m / tiles_per_img, rem = m - n * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int oy = ty * p.BH + row / p.BW, ox = tx * p.BW + row % p.BW;
+      const bool valid = oy < p.H && ox < p.W;
+      const long long pix = (long long)n * HW + (long long)oy * p.W + ox;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.BN + c0), raw);
+        const int co0 = n0 + c0;
+        if (!valid || co0 >= p.Cout) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * p.inv_scale;
+        if (co0 + 16 <= p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+          if (p.res_hi != nullptr) {
+            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.Cout + co0);
+            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.Cout + co0);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const uint4 a = __ldg(rh + q), b = __ldg(rl + q);
+              const __half2* ah = reinterpret_cast<const __half2*>(&a);
+              const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
+                v[q * 8 + 2 * e] += fa.x + fb.x; v[q * 8 + 2 * e + 1] += fa.y + fb.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (p.relu) v[j] = fmaxf(v[j], 0.f);
+            if (p.sigmoid) v[j] = 1.f / (1.f + expf(-v[j]));
+          }
+          if (p.out_hi != nullptr) {
+            uint4 hi4[2], lo4[2];
+            __half2* hh = reinterpret_cast<__half2*>(hi4);
+            __half2* ll = reinterpret_cast<__half2*>(lo4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float a = fminf(fmaxf(v[2 * e], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * e + 1], -65504.f), 65504.f);
+              const __half2 h = __floats2half2_rn(a, b);
+              const float2 hf = __half22float2(h);
+              hh[e] = h;
+              ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0);
+            oh[0] = hi4[0]; oh[1] = hi4[1];
+            if (p.out_lo != nullptr) {
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + co0);
+              ol[0] = lo4[0]; ol[1] = lo4[1];
+            }
+          }
+          if (p.out32 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) p.out32[((long long)n * p.Cout + co0 + j) * HW + (long long)oy * p.W + ox] = v[j];
+          }
+        } else {
+          // ragged tail of output channels (head convs: Cout = 5 / 10 / 40): fp32 NCHW output only
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = co0 + j;
+            if (co < p.Cout) {
+              float x = v[j] + __ldg(p.bias + co);
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (p.sigmoid) x = 1.f / (1.f + expf(-x));
+              if (p.out32 != nullptr) p.out32[((long long)n * p.Cout + co) * HW + (long long)oy * p.W + ox] = x;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_tc_state = 0;   // 0 unknown, 1 ok, -1 unavailable
+static char g_tc_msg[256] = "not initialised";
+
+static void tc_init() {
+  if (g_tc_state != 0) return;
+  const char* off = getenv("KG_DISABLE_TC");
+  if (off && off[0] == '1') { g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "disabled by KG_DISABLE_TC"); return; }
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "no CUDA device"); return;
+  }
+  if (major != 10) { g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "compute capability %d.x is not sm_100", major); return; }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+      qres != cudaDriverEntryPointSuccess) {
+    g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "cuTensorMapEncodeTiled not found in the driver"); return;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  if (cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess) {
+    g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
+    return;
+  }
+  g_tc_state = 1; snprintf(g_tc_msg, sizeof(g_tc_msg), "ok");
+}
+
+bool tc_available() { tc_init(); return g_tc_state == 1; }
+const char* tc_status() { tc_init(); return g_tc_msg; }
+bool tc_layer_supported(int cin, int cout, int R, int S) { return cin % TC_BK == 0 && cout >= 1 && R >= 1 && S >= 1 && R * S <= 64; }
+
+void tc_free_weights(TcWeights& w) {
+  if (w.d_hi) cudaFree(w.d_hi);
+  if (w.d_lo) cudaFree(w.d_lo);
+  w = TcWeights();
+}
+
+int tc_pack_weights(const float* w, int cin, int cout, int R, int S, TcWeights* out) {
+  tc_free_weights(*out);
+  const int taps = R * S;
+  const int cout_pad = cout <= 256 ? (int)align_up(cout, 16) : (int)align_up(cout, 256);
+  float mx = 0.f;
+  const size_t n = (size_t)taps * cin * cout;
+  for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+  int e = 0;
+  if (mx > 0.f && std::isfinite(mx)) { int ex; frexpf(mx, &ex); e = 10 - ex; }   // max |w| * 2^e in [512, 1024)
+  if (e > 40) e = 40;
+  if (e < -40) e = -40;
+  const float scale = ldexpf(1.f, e);
+  std::vector<__half> hi((size_t)taps * cout_pad * cin, __float2half_rn(0.f)), lo(hi.size(), __float2half_rn(0.f));
+  for (int t = 0; t < taps; ++t)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co) {
+        const float v = w[((size_t)t * cin + ci) * cout + co] * scale;
+        const __half h = __float2half_rn(v);
+        const size_t o = ((size_t)t * cout_pad + co) * cin + ci;
+        hi[o] = h;
+        lo[o] = __float2half_rn(v - __half2float(h));
+      }
+  KG_CUDA_CHECK(cudaMalloc(&out->d_hi, hi.size() * sizeof(__half)));
+  KG_CUDA_CHECK(cudaMalloc(&out->d_lo, lo.size() * sizeof(__half)));
+  KG_CUDA_CHECK(cudaMemcpy(out->d_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  KG_CUDA_CHECK(cudaMemcpy(out->d_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  out->cin = cin; out->cout = cout; out->cout_pad = cout_pad; out->taps = taps; out->inv_scale = ldexpf(1.f, -e);
+  out->valid = true;
+  return KG_OK;
+}
+
+static int encode_act_map(CUtensorMap* m, const __half* base, int C, int W, int H, int N, int BW, int BH) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations C=%d W=%d H=%d N=%d box %dx%d) failed: %d", C, W, H, N, BW, BH, (int)r); return KG_ERR_CUDA; }
+  return KG_OK;
+}
+
+static int encode_w_map(CUtensorMap* m, const __half* base, int cin, int cout_pad, int taps, int BN) {
+  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout_pad * cin * 2};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights cin=%d cout=%d taps=%d BN=%d) failed: %d", cin, cout_pad, taps, BN, (int)r); return KG_ERR_CUDA; }
+  return KG_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+int tc_conv_prepare(TcConvOp* op) {
+  if (!tc_available()) { set_error("tensor-core path unavailable: %s", tc_status()); return KG_ERR_STATE; }
+  KG_REQUIRE(op && op->w && op->w->valid, "tc_conv_prepare: weights not packed");
+  KG_REQUIRE(op->C0 % TC_BK == 0 && op->C1 % TC_BK == 0 && op->C0 + op->C1 == op->w->cin, "tc_conv_prepare: channel split %d+%d vs cin %d",
+             op->C0, op->C1, op->w->cin);
+  KG_REQUIRE(op->passes == 1 || op->passes == 3, "tc_conv_prepare: passes=%d", op->passes);
+  KG_REQUIRE(op->passes == 1 || (op->in0_lo != nullptr && (op->C1 == 0 || op->in1_lo != nullptr)), "tc_conv_prepare: 3-pass needs lo planes");
+  KG_REQUIRE(op->out_hi == nullptr || op->Cout % 16 == 0, "tc_conv_prepare: NHWC output needs Cout %% 16 == 0 (Cout=%d)", op->Cout);
+  std::shared_ptr<TcParams> sp(new TcParams());
+  TcParams& p = *sp;
+  memset(&p, 0, sizeof(p));
+  p.N = op->N; p.H = op->H; p.W = op->W; p.Cout = op->Cout; p.R = op->R; p.S = op->S; p.pad = op->pad;
+  p.chunks0 = op->C0 / TC_BK; p.chunks1 = op->C1 / TC_BK; p.coff0 = op->in0_coff;
+  p.BN = op->w->cout_pad <= 256 ? op->w->cout_pad : 256;
+  int bw = 1;
+  while (bw * 2 <= op->W && bw * 2 <= TC_BM) bw *= 2;
+  p.BW = bw; p.BH = TC_BM / bw;
+  p.tiles_x = ceil_div(op->W, p.BW); p.tiles_y = ceil_div(op->H, p.BH);
+  p.m_tiles = p.tiles_x * p.tiles_y * op->N;
+  p.passes = op->passes; p.NPL = op->passes == 3 ? 2 : 1;
+  int mt = (op->passes == 1 && 2 * p.BN <= 512) ? 2 : 1;
+  mt = env_int("KG_TC_MT", mt);
+  if (mt < 1) mt = 1;
+  if (mt > 2) mt = 2;
+  if (mt * p.BN > 512) mt = 1;
+  p.MT = mt;
+  const size_t stage_bytes = (size_t)p.MT * p.NPL * TC_A_TILE + (size_t)p.NPL * p.BN * 128;
+  int stages = (int)((TC_MAX_SMEM - 2048) / stage_bytes);
+  if (stages > 8) stages = 8;
+  stages = env_int("KG_TC_STAGES", stages) < stages ? env_int("KG_TC_STAGES", stages) : stages;
+  if (stages < 2 && p.MT == 2) {   // fall back to one accumulator tile
+    p.MT = 1;
+    stages = (int)((TC_MAX_SMEM - 2048) / ((size_t)p.NPL * TC_A_TILE + (size_t)p.NPL * p.BN * 128));
+    if (stages > 8) stages = 8;
+  }
+  KG_REQUIRE(stages >= 1, "tc_conv_prepare: tile does not fit in shared memory");
+  p.stages = stages;
+  unsigned cols = 32;
+  while (cols < (unsigned)(p.MT * p.BN)) cols *= 2;
+  p.tmem_cols = cols;
+  p.bias = op->bias; p.inv_scale = op->w->inv_scale;
+  p.out_hi = op->out_hi; p.out_lo = op->out_lo; p.res_hi = op->res_hi; p.res_lo = op->res_lo;
+  p.relu = op->relu; p.sigmoid = op->sigmoid;
+  KG_TRY(encode_act_map(&p.a_map[0][0], op->in0_hi, op->in0_C, op->W, op->H, op->N, p.BW, p.BH));
+  if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[0][1], op->in0_lo, op->in0_C, op->W, op->H, op->N, p.BW, p.BH));
+  if (op->C1 > 0) {
+    KG_TRY(encode_act_map(&p.a_map[1][0], op->in1_hi, op->in1_C, op->W, op->H, op->N, p.BW, p.BH));
+    if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[1][1], op->in1_lo, op->in1_C, op->W, op->H, op->N, p.BW, p.BH));
+  }
+  KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.BN));
+  if (p.NPL == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN));
+  op->grid_x = (unsigned)ceil_div(p.m_tiles, p.MT);
+  op->grid_y = (unsigned)(op->w->cout_pad / p.BN);
+  op->smem_bytes = (unsigned)((size_t)p.stages * stage_bytes + 16 * p.stages + 64 + 1024);
+  KG_REQUIRE(op->smem_bytes <= (unsigned)TC_MAX_SMEM, "tc_conv_prepare: smem %u > %d", op->smem_bytes, TC_MAX_SMEM);
+  op->params = sp;
+  return KG_OK;
+}
+
+int tc_conv_launch(const TcConvOp* op, float* out32, cudaStream_t stream) {
+  KG_REQUIRE(op && op->params, "tc_conv_launch: op not prepared");
+  TcParams p = *reinterpret_cast<const TcParams*>(op->params.get());
+  p.out32 = out32;
+  dim3 grid(op->grid_x, op->grid_y, 1);
+  tc_conv_kernel<<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+}  // namespace kg
