@@ -87,8 +87,8 @@ class ClockSampler:
 
 def planted_batch(n_distinct=4):
     """Teacher-forced decode load: planted 40-cell scenes, bs 32 built from n_distinct scenes."""
-    from oracle import kg_oracle as O   # input GENERATOR only (synthetic data), never on the measured path
-    base = [O.planted_scene(100 + i, HW_IN, HW_IN, CELLS)[0] for i in range(n_distinct)]
+    from kg_instance_segmentation_b200 import synthetic
+    base = [synthetic.planted_scene(100 + i, HW_IN, HW_IN, CELLS)[0] for i in range(n_distinct)]
     scenes = [base[i % n_distinct] for i in range(BS)]
     return base, [tuple(np.stack([sc[s][k] for sc in scenes]) for k in range(3)) for s in range(4)]
 
@@ -196,6 +196,158 @@ def run_decode(args, rank, world, dist):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------
+# FLOPs of forward_dec per image at 512x512 come from the plan census (kg_net_plan_info); SURVEY.md §8d: 1357.31 GF.
+STAGE_NAMES = {0: "vote", 1: "blur_peak", 2: "group", 3: "nms", 8: "conv_cuda_core", 9: "tc_backbone", 10: "tc_decoder",
+               11: "tc_heads_l1", 12: "tc_heads_l2", 13: "bilinear", 14: "maxpool", 15: "export_feats", 16: "forward_seg"}
+
+
+def run_pipeline(args, rank, world, dist):
+    import ctypes as C
+    import torch
+    from kg_instance_segmentation_b200 import _cabi, synthetic
+    from kg_instance_segmentation_b200.inference import InstanceHeat
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sd = synthetic.make_state_dict(seed=0)
+    engine = InstanceHeat(precision=args.precision, device=dev)
+    engine.model.load_state_dict(sd, strict=True)
+    del sd
+    torch.manual_seed(0)
+    x_host = (torch.rand(BS, 3, HW_IN, HW_IN) - 0.5).pin_memory()          # test.py:92 input range
+    x_dev = x_host.to(dev)
+    x_stage = torch.empty_like(x_dev)
+    base, host = planted_batch()
+    forced = [tuple(torch.from_numpy(a).to(dev) for a in h) for h in host] if not args.free_running else None
+    det_host = torch.empty(BS, MAX_DETS, 5, dtype=torch.float64).pin_memory()
+    mask_host = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+    gathered = torch.empty(world * BS, MAX_DETS, 5, dtype=torch.float64, device=dev) if world > 1 else None
+    gathered_cnt = torch.empty(world * BS, dtype=torch.int32, device=dev) if world > 1 else None
+    state = {}
+
+    def gather(res):
+        if world > 1:   # the single collective of the path: all-gather of the padded final detection list
+            dist.all_gather_into_tensor(gathered, res.dets[:, :MAX_DETS].contiguous())
+            dist.all_gather_into_tensor(gathered_cnt, res.det_count)
+
+    def step_device():
+        dets, seg = engine.detect_batch(x_dev, head_override=forced)
+        gather(engine.last_result)
+        state["dets"] = dets
+        return dets
+
+    def step_e2e():
+        x_stage.copy_(x_host, non_blocking=True)                            # H2D of the step's input from pinned memory
+        dets, seg = engine.detect_batch(x_stage, head_override=forced)
+        gather(engine.last_result)
+        det_host.copy_(engine.last_result.dets[:, :MAX_DETS], non_blocking=True)
+        m = engine.model.last_masks
+        n = min(m.numel(), mask_host.numel())
+        mask_host[:n].copy_(m[:n], non_blocking=True)                       # D2H of the step's result: detections + mask patches
+        state["mask_floats"] = n
+        torch.cuda.current_stream().synchronize()
+        return dets
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_device()
+    n_det = sum(0 if d is None else len(d) for d in state["dets"])
+    launches_per_step = engine.last_launches
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    ms = timed(step_device, args.steps)
+    clocks = sampler.stop() if sampler else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-stage device time, live, CUDA events on the launching stream (separate pass: events serialise nothing but
+    # add host work, so they are kept out of the headline timing)
+    _cabi.timing_enable(True)
+    for _ in range(args.steps):
+        step_device()
+    st_ms, st_cnt = _cabi.timing_collect()
+    _cabi.timing_enable(False)
+    info = np.zeros(8, np.float64)
+    _cabi.check(_cabi.lib().kg_net_plan_info(engine.model._handle, info.ctypes.data, 8))
+    stages = {STAGE_NAMES[i]: {"ms_per_step": round(float(st_ms[i]) / args.steps, 4), "launches_per_step": int(st_cnt[i]) // args.steps}
+              for i in STAGE_NAMES if st_cnt[i] > 0}
+    tc_ms = float(st_ms[9:13].sum()) / args.steps
+    tc_launches = int(st_cnt[9:13].sum()) // args.steps
+    pk, pk_kind = peaks()
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    achieved = info[0] / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    per_class = {}
+    for j, nme in enumerate(("tc_backbone", "tc_decoder", "tc_heads_l1", "tc_heads_l2")):
+        t = float(st_ms[9 + j]) / args.steps
+        if t > 0:
+            per_class[nme] = {"tflops": round(info[4 + j] / (t * 1e-3) / 1e12, 1), "frac": round(info[4 + j] / (t * 1e-3) / 1e12 / peak_tf, 4)}
+    roofline = {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv, all tensor-core launches of forward_dec)", "bound": "tensor",
+                "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None,
+                "peak_kind": pk_kind + " (cuBLAS bf16 sustained; kernel timed inside a long step)",
+                "algorithmic_flops_per_step": info[0], "launches_per_step": tc_launches, "avg_launch_ms": round(tc_ms / max(1, tc_launches), 4),
+                "cuda_core_conv_flops_per_step": info[1], "per_class": per_class, "stages": stages}
+    out = {
+        "metric": METRIC, "value": round(world * BS * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 operands (split hi+lo x3 in backbone/decoder, single pass in heads), fp32 accumulate; fp64 decode"
+                 if args.precision == "fast" else args.precision,
+        "data": "synthetic (seeded Kaiming weights with calibrated heads; rand-0.5 images; planted 40-cell scenes)",
+        "config": {"workload": "bs32/GPU 512x512: forward_dec (ResNet-50 trunk + decoder + 12 heads) -> vote/blur/peak/group/boxes/NMS -> forward_seg"
+                               + ("; decode teacher-forced with planted 40-cell head maps (SURVEY.md 8d-ii)" if forced is not None else "; free-running decode"),
+                   "global_batch": world * BS, "precision": args.precision, "detections_per_step": n_det,
+                   "l2_note": "activations of one step (>20 GB) exceed L2; no flush needed"},
+        "e2e": {"value": round(world * BS * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                "d2h_bytes_per_step": det_host.numel() * 8 + int(state.get("mask_floats", 0)) * 4},
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_pipeline(base, n_images=1, warm=0)
+    return out
+
+
+def cpu_pipeline(base, n_images, warm=0):
+    """The reference path on host cores via the oracle port: forward_dec (torch fp32, all cores) -> 4x decode -> refine ->
+    gather -> NMS -> forward_seg, one image at a time like test.py:88-125."""
+    import torch
+    from oracle import kg_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.make_state_dict(seed=0)
+    torch.manual_seed(0)
+    xs = torch.rand(max(1, n_images), 3, HW_IN, HW_IN) - 0.5
+    def one(i):
+        out = O.forward_dec(sd, xs[i % len(xs)][None])
+        det, _, _ = O.decode_image(base[i % len(base)])
+        O.forward_seg(sd, out[4], [det if det is not None else []])
+    for i in range(warm):
+        one(i)
+    t0 = time.time()
+    for i in range(n_images):
+        one(i)
+    dt = time.time() - t0
+    return {"value": round(n_images / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_images} image(s) 512x512 of the same workload, bs=1 like test.py: torch fp32 forward_dec on {cores} threads + "
+                      "NumPy decode (1 thread) + forward_seg (oracle/kg_oracle.py)", "seconds": round(dt, 2)}
+
+
 def cpu_baseline_decode(base, budget_s=12.0):
     from oracle import kg_oracle as O
     t0 = time.time(); n = 0
@@ -216,33 +368,30 @@ def run_reference(args):
     from oracle import kg_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    base, _ = planted_batch()
-    per_step = 1
-    for _ in range(min(args.warmup, 1)):
-        O.decode_image(base[0])
-    t0 = time.time()
-    for k in range(args.steps):
-        for j in range(per_step):
-            O.decode_image(base[(k + j) % len(base)])
-    dt = time.time() - t0
-    v = round(args.steps * per_step / dt, 4)
-    sample = f"{per_step} image per step (bounded sample of the bs32 512x512 planted workload), decode-only, NumPy oracle port"
-    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "decode-only (same as the own arm)", "global_batch": per_step},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+    base, _ = planted_batch(n_distinct=2)
+    steps = min(args.steps, 6)           # bounded: ~5 s of CPU work per step
+    r = cpu_pipeline(base, n_images=steps, warm=min(args.warmup, 1))
+    v = r["value"]
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32 (torch CPU) + fp64 decode", "data": "synthetic",
+            "config": {"workload": "same path as the own arm, one 512x512 image per step (the reference is batch-size-1 by construction, "
+                                   "postprocessing.py:138-140); oracle port of the reference (pure-Python reference cannot travel to the GPU box)",
+                       "global_batch": 1},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own")
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fast", choices=["fast", "exact", "reference"])
+    ap.add_argument("--free-running", action="store_true", help="decode the network's own head outputs instead of planted maps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,16 +409,9 @@ def main():
         torch.cuda.set_device(0)
     from kg_instance_segmentation_b200 import _cabi
     _cabi.lib()   # fail loudly when the CUDA library is missing
-    workload = args.workload
-    if workload == "auto":
-        try:
-            from kg_instance_segmentation_b200 import KGnet  # noqa: F401
-            workload = "pipeline"
-        except ImportError:
-            workload = "decode"
+    workload = "pipeline" if args.workload == "auto" else args.workload
     if workload == "pipeline":
-        from kg_instance_segmentation_b200 import bench_pipeline
-        out = bench_pipeline.run(args, rank, world, dist)
+        out = run_pipeline(args, rank, world, dist)
     else:
         out = run_decode(args, rank, world, dist)
     if rank == 0:

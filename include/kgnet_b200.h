@@ -171,6 +171,11 @@ int kg_net_forward_seg(kg_net* net, void* d_dec_workspace, void* d_seg_workspace
 int kg_conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R,
                    int S, int stride, int pad, int relu, const float* d_res, int mode, float* d_y, void* stream);
 
+/* Work census of the current forward_dec plan: out[0]/out[1] = algorithmic FLOPs (2*MACs, real channel counts, one
+ * pass) of the tensor-core / CUDA-core convs, out[2]/out[3] = their launch counts, out[4..7] = tensor-core FLOPs
+ * of the backbone, decoder, first-layer heads, second-layer heads.  n >= 8. */
+int kg_net_plan_info(kg_net* net, double* out, int n);
+
 /* 1 when the tcgen05/TMA path initialised on the current device; kg_tc_status() says why not otherwise. */
 int kg_tc_available(void);
 const char* kg_tc_status(void);

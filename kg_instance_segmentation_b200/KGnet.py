@@ -283,6 +283,7 @@ class ResNet(nn.Module):
             _cabi.check(L.kg_net_forward_seg(self._handle, ws.data_ptr(), self._seg_ws.data_ptr(), self._seg_ws.numel(),
                                              masks.data_ptr(), torch.cuda.current_stream().cuda_stream, C.byref(nl)))
         self.last_launches = nl.value
+        self.last_masks = masks
         k = 0
         for i in range(nimg):
             for j in range(counts[i]):

@@ -41,6 +41,12 @@ void stage_begin(int id, cudaStream_t s) {
   cudaEventRecord(e, s);
   g_timing.open_ev[id] = e;
 }
+void StageScope::restage(int new_id) {
+  if (!timing_enabled() || new_id == id) return;
+  std::lock_guard<std::mutex> lock(g_timing.mu);
+  g_timing.open_ev[new_id] = g_timing.open_ev[id];
+  id = new_id;
+}
 void stage_end(int id, cudaStream_t s) {
   std::lock_guard<std::mutex> lock(g_timing.mu);
   cudaEvent_t e = g_timing.get();

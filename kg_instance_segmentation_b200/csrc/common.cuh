@@ -64,6 +64,7 @@ void stage_end(int id, cudaStream_t s);
 struct StageScope {
   int id; cudaStream_t s;
   StageScope(int id_, cudaStream_t s_) : id(id_), s(s_) { if (timing_enabled()) stage_begin(id, s); }
+  void restage(int new_id);   // re-attribute the open interval to another stage
   ~StageScope() { if (timing_enabled()) stage_end(id, s); }
 };
 

@@ -410,6 +410,7 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
     StageScope ts(op.stage, stream);
     switch (op.type) {
       case OP_CONV: {
+        if (op.tc_passes == 0) ts.restage(ST_STEM);   // stage 8 collects every CUDA-core conv, 9..12 are tensor-core only
         float* out32 = op.out32_ext >= 0 ? ext[op.out32_ext] : nullptr;
         if (op.tc_passes > 0) {
           KG_TRY(tc_conv_launch(&p->tc_ops[op.tc_index], out32, stream));
@@ -800,6 +801,22 @@ int kg_net_forward_seg(kg_net* h, void* d_dec_workspace, void* d_seg_workspace, 
 int kg_conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R, int S, int stride,
                    int pad, int relu, const float* d_res, int mode, float* d_y, void* stream) {
   return conv2d_nchw(d_x, N, Cin, H, W, h_w, h_bias, Cout, R, S, stride, pad, relu, d_res, mode, d_y, (cudaStream_t)stream);
+}
+
+/* out[0] = algorithmic FLOPs (2*MACs, real channel counts, one pass) of the tensor-core convs of the current plan,
+ * out[1] = same for the CUDA-core convs, out[2] / out[3] = their launch counts, out[4..7] = tensor-core FLOPs by
+ * stage (backbone, decoder, head layer 1, head layer 2). */
+int kg_net_plan_info(kg_net* h, double* out, int n) {
+  Net* net = reinterpret_cast<Net*>(h);
+  KG_REQUIRE(net && net->plan && out && n >= 8, "kg_net_plan_info: no plan (run forward_dec first)");
+  for (int i = 0; i < n; ++i) out[i] = 0.0;
+  for (const Op& op : net->plan->ops) {
+    if (op.type != OP_CONV) continue;
+    const double f = 2.0 * net->plan->N * op.Hout * op.Wout * (double)op.w->Cout * (op.C0 + op.C1) * op.w->R * op.w->S;
+    if (op.tc_passes > 0) { out[0] += f; out[2] += 1; if (op.stage >= ST_BACKBONE && op.stage <= ST_HEAD2) out[4 + op.stage - ST_BACKBONE] += f; }
+    else { out[1] += f; out[3] += 1; }
+  }
+  return KG_OK;
 }
 
 int kg_tc_available(void) { return tc_available() ? 1 : 0; }

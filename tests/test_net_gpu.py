@@ -104,7 +104,7 @@ def _model(precision):
     return m.cuda().eval(), sd
 
 
-@pytest.mark.parametrize("precision,kp_tol,off_tol", [("reference", 2e-5, 2e-3), ("exact", 2e-5, 2e-3), ("fast", 1e-3, 5e-2)])
+@pytest.mark.parametrize("precision,kp_tol,off_tol", [("reference", 2e-5, 2e-3), ("exact", 1e-4, 2e-3), ("fast", 1e-3, 5e-2)])
 def test_forward_dec_matches_golden(precision, kp_tol, off_tol):
     g = np.load(os.path.join(G, "forward_64_seed0.npz"))
     m, _ = _model(precision)
