@@ -159,10 +159,13 @@ int kg_net_import_feats(kg_net* net, const float* const* d_feats, int N, int H, 
 /* ResNet.forward_seg (KGnet.py:321-350), two calls.  prepare: host boxes ([sum(box_counts),5] fp64 rows
  * y1,x1,y2,x2,score, image-major) -> crop rectangles (get_patches, :246-256), grouped problem lists, required
  * scratch bytes and the mask layout: h_mask_index[box] = mask slot or -1 when the box is skipped (:341-342),
- * h_mask_hw[slot] = (h, w), h_mask_off[slot] = float offset into d_masks.  run: all boxes in grouped launches. */
+ * h_mask_hw[slot] = (h, w), h_mask_off[slot] = float offset of the patch's first element in d_masks,
+ * h_mask_pitch[slot] = its row stride in floats (the tensor-core path packs all patches into one atlas image).
+ * run: all boxes together — dense tcgen05 convs over the per-level atlases (precision 1, 2) or grouped CUDA-core
+ * launches (precision 0). */
 int kg_net_seg_prepare(kg_net* net, int N, int H, int W, const int* box_counts, const double* h_boxes,
                        size_t* seg_workspace_bytes, long long* mask_floats, int* n_masks, int* h_mask_index,
-                       int* h_mask_hw, long long* h_mask_off);
+                       int* h_mask_hw, long long* h_mask_off, int* h_mask_pitch);
 int kg_net_forward_seg(kg_net* net, void* d_dec_workspace, void* d_seg_workspace, size_t seg_workspace_bytes,
                        float* d_masks, void* stream, int* n_launches);
 

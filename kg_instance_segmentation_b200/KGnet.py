@@ -272,10 +272,11 @@ class ResNet(nn.Module):
         boxes = np.ascontiguousarray(np.concatenate(rows, 0))
         seg_bytes, mask_floats, n_masks = C.c_size_t(0), C.c_longlong(0), C.c_int(0)
         mask_index = np.zeros(total, np.int32); mask_hw = np.zeros((total, 2), np.int32); mask_off = np.zeros(total, np.int64)
+        mask_pitch = np.zeros(total, np.int32)
         with torch.cuda.device(device):
             _cabi.check(L.kg_net_seg_prepare(self._handle, N, H, W, counts.ctypes.data, boxes.ctypes.data, C.byref(seg_bytes),
                                              C.byref(mask_floats), C.byref(n_masks), mask_index.ctypes.data, mask_hw.ctypes.data,
-                                             mask_off.ctypes.data))
+                                             mask_off.ctypes.data, mask_pitch.ctypes.data))
             if self._seg_ws is None or self._seg_ws.numel() < seg_bytes.value or self._seg_ws.device != device:
                 self._seg_ws = torch.empty(int(seg_bytes.value * 1.25) + 1024, dtype=torch.uint8, device=device)
             masks = torch.empty(max(1, mask_floats.value), dtype=torch.float32, device=device)
@@ -291,7 +292,7 @@ class ResNet(nn.Module):
                 if slot >= 0:
                     h, w = mask_hw[slot]
                     o = int(mask_off[slot])
-                    mask_patches[i].append(masks[o:o + int(h) * int(w)].view(int(h), int(w)))
+                    mask_patches[i].append(torch.as_strided(masks, (int(h), int(w)), (int(mask_pitch[slot]), 1), o))
                     mask_dets[i].append(torch.Tensor(np.append(boxes[k, :4], boxes[k, 4])))
                 k += 1
         return [mask_patches, mask_dets]

@@ -91,7 +91,7 @@ def _bind_net(L):
     L.kg_net_import_feats.restype = ci
     L.kg_net_import_feats.argtypes = [vp, vp, ci, ci, ci, ci, vp, cs, vp]
     L.kg_net_seg_prepare.restype = ci
-    L.kg_net_seg_prepare.argtypes = [vp, ci, ci, ci, vp, vp, C.POINTER(cs), C.POINTER(C.c_longlong), C.POINTER(ci), vp, vp, vp]
+    L.kg_net_seg_prepare.argtypes = [vp, ci, ci, ci, vp, vp, C.POINTER(cs), C.POINTER(C.c_longlong), C.POINTER(ci), vp, vp, vp, vp]
     L.kg_net_forward_seg.restype = ci
     L.kg_net_forward_seg.argtypes = [vp, vp, vp, cs, vp, vp, C.POINTER(ci)]
     L.kg_conv2d_nchw.restype = ci

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -87,6 +88,17 @@ struct SegPlan {
   } steps[4];
   std::vector<ConvProb> h0_raw, h0_scr, h1;
   int pix_h0_raw = 0, pix_h0_scr = 0, pix_h1 = 0;
+  // ---- tensor-core path: every level's crops packed into one "atlas" image (1-px zero gaps between boxes) ----
+  bool atlas = false;
+  struct Level {
+    int HA = 0, WA = 0;
+    size_t P = 0, U = 0, V = 0, Cc = 0, T = 0;     // element offsets of the atlas tensors inside one scratch plane
+    size_t mask = 0;                               // byte offset of the uint8 validity mask
+    std::vector<ResizeProb> crop, deepest, up;     // feature crop -> P; P -> C for boxes whose deepest level this is; pre -> U
+    std::vector<RectProb> rects;
+    int pix_crop = 0, pix_deepest = 0, pix_up = 0;
+  } lv[5];
+  size_t mask_base = 0;                            // byte offset of the mask region inside the seg workspace
 };
 
 struct Net {
@@ -288,7 +300,7 @@ static void assign_tc(Plan* p, int precision) {
   for (auto& op : p->ops) {
     if (op.type != OP_CONV || op.x_input) continue;
     const ConvW* w = op.w;
-    if (!w->tc.valid || op.stride != 1) continue;
+    if (!w->tc.valid || (op.stride != 1 && !(op.stride == 2 && tc_stride2_enabled()))) continue;
     if (op.C0 % 64 != 0 || (op.C1 % 64) != 0) continue;
     const bool head = op.stage == ST_HEAD1 || op.stage == ST_HEAD2;
     op.tc_passes = (head && precision == 1) ? 1 : 3;
@@ -393,6 +405,7 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
       TcConvOp t{};
       t.w = &op.w->tc; t.bias = op.w->d_b;
       t.N = p->N; t.H = op.Hout; t.W = op.Wout; t.R = op.w->R; t.S = op.w->S; t.pad = op.pad;
+      t.stride = op.stride; t.Hin = t0.H; t.Win = t0.W;
       t.C0 = op.C0; t.C1 = op.C1; t.Cout = op.w->Cout; t.passes = op.tc_passes;
       t.in0_hi = P.hi(t0); t.in0_lo = op.in_single ? nullptr : P.lo(t0); t.in0_C = t0.C; t.in0_coff = op.in0_coff;
       if (op.in1 >= 0) { const Tensor& t1 = p->tensors[op.in1]; t.in1_hi = P.hi(t1); t.in1_lo = P.lo(t1); t.in1_C = t1.C; }
@@ -417,8 +430,15 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
           ++launches;
           break;
         }
-        ConvArgs a{};
         const ConvW* w = op.w;
+        if (op.x_input && w->Cin == 3 && w->Cout == 64 && op.relu && op.out >= 0 && !op.out_single && out32 == nullptr &&
+            ((w->R == 3 && op.stride == 1) || (w->R == 7 && op.stride == 2)) && w->R == w->S && op.pad == w->R / 2) {
+          const Tensor& to = p->tensors[op.out];
+          KG_TRY(launch_stem_conv(d_x, w->d_w, w->d_b, P.hi(to), P.lo(to), p->N, p->H, p->W, w->R, op.stride, stream));
+          ++launches;
+          break;
+        }
+        ConvArgs a{};
         if (op.x_input) { a.x32 = d_x; }
         else {
           const Tensor& t0 = p->tensors[op.in0];
@@ -476,9 +496,14 @@ static bool patch_rect(float y1n, float x1n, float y2n, float x2n, int h, int w,
 
 static const int kSegUpIn[4] = {64, 256, 512, 1024}, kSegOut[4] = {64, 64, 256, 512};
 
+static int seg_prepare_atlas(Net* net, int N, int H, int W, const int* counts, const double* boxes, size_t* ws_bytes, long long* mask_floats,
+                             int* n_masks, int* mask_index, int* mask_hw, long long* mask_off, int* mask_pitch);
+
 static int seg_prepare(Net* net, int N, int H, int W, const int* counts, const double* boxes, size_t* ws_bytes, long long* mask_floats,
-                       int* n_masks, int* mask_index, int* mask_hw, long long* mask_off) {
+                       int* n_masks, int* mask_index, int* mask_hw, long long* mask_off, int* mask_pitch) {
   KG_REQUIRE(net && counts && ws_bytes && mask_floats && n_masks, "kg_net_seg_prepare: null argument");
+  if (net->plan && net->plan->precision != 0 && tc_available() && getenv("KG_SEG_FFMA") == nullptr)
+    return seg_prepare_atlas(net, N, H, W, counts, boxes, ws_bytes, mask_floats, n_masks, mask_index, mask_hw, mask_off, mask_pitch);
   KG_REQUIRE(net->plan && net->plan->N == N && net->plan->H == H && net->plan->W == W,
              "kg_net_seg_prepare: forward_dec (or kg_net_import_feats) must run first for N=%d H=%d W=%d", N, H, W);
   Plan* p = net->plan.get();
@@ -507,6 +532,7 @@ static int seg_prepare(Net* net, int N, int H, int W, const int* counts, const d
         sb.mask_index = mi;
         const int mh = sb.rect[0][2] - sb.rect[0][0], mw = sb.rect[0][3] - sb.rect[0][1];
         if (mask_hw) { mask_hw[2 * mi] = mh; mask_hw[2 * mi + 1] = mw; }
+        if (mask_pitch) mask_pitch[mi] = mw;
         if (mask_off) mask_off[mi] = moff;
         moff += (long long)mh * mw;
         ++mi;
@@ -588,9 +614,12 @@ static int seg_prepare(Net* net, int N, int H, int W, const int* counts, const d
   return KG_OK;
 }
 
+static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes, float* d_masks, cudaStream_t stream, int* n_launches);
+
 static int seg_run(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes, float* d_masks, cudaStream_t stream, int* n_launches) {
   SegPlan& sp = net->seg;
   if (!sp.valid || !net->plan) { set_error("kg_net_forward_seg: call kg_net_seg_prepare first"); return KG_ERR_STATE; }
+  if (sp.atlas) return seg_run_atlas(net, dec_ws, seg_ws, seg_bytes, d_masks, stream, n_launches);
   const size_t plane_bytes = align_up(sp.scratch_halfs * sizeof(__half), 256);
   if (seg_bytes < plane_bytes * 2) { set_error("kg_net_forward_seg: workspace too small (%zu < %zu)", seg_bytes, plane_bytes * 2); return KG_ERR_WORKSPACE; }
   if (sp.n_masks == 0) { if (n_launches) *n_launches = 0; return KG_OK; }
@@ -669,6 +698,225 @@ static int seg_run(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes, float
   return KG_OK;
 }
 
+// ---- forward_seg on the tensor cores --------------------------------------------------------------------------
+// The per-box mini decoders all share weights, so the crops of every box are packed, level by level, into one "atlas"
+// image per level (shelf packing, >= 1 pixel of zeros around every box = the zero padding of the per-box 3x3 convs).
+// Each layer then is ONE dense tcgen05 conv over the atlas; an uint8 validity mask zeroes the gap pixels in the
+// epilogue so that the next 3x3 conv again sees zero padding.  Mask patches are strided windows of the fp32 atlas.
+static int seg_prepare_atlas(Net* net, int N, int H, int W, const int* counts, const double* boxes, size_t* ws_bytes, long long* mask_floats,
+                             int* n_masks, int* mask_index, int* mask_hw, long long* mask_off, int* mask_pitch) {
+  KG_REQUIRE(net->plan && net->plan->N == N && net->plan->H == H && net->plan->W == W,
+             "kg_net_seg_prepare: forward_dec (or kg_net_import_feats) must run first for N=%d H=%d W=%d", N, H, W);
+  Plan* p = net->plan.get();
+  SegPlan& sp = net->seg;
+  sp = SegPlan();
+  sp.N = N; sp.H = H; sp.W = W; sp.atlas = true;
+  int fh[5], fw[5];
+  for (int l = 0; l < 5; ++l) { fh[l] = p->tensors[p->feat_ids[l]].H; fw[l] = p->tensors[p->feat_ids[l]].W; }
+  std::vector<SegBox> sboxes;
+  int bi = 0, mi = 0;
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < counts[n]; ++k, ++bi) {
+      KG_REQUIRE(boxes != nullptr, "kg_net_seg_prepare: null boxes");
+      const double* bx = boxes + (size_t)bi * 5;
+      SegBox sb{}; sb.img = n; sb.L = 0; sb.mask_index = -1;
+      const float y1 = (float)bx[0], x1 = (float)bx[1], y2 = (float)bx[2], x2 = (float)bx[3];
+      const float h0 = (float)fh[0], w0 = (float)fw[0];
+      for (int l = 0; l < 5; ++l) {
+        if (!patch_rect(y1 / h0, x1 / w0, y2 / h0, x2 / w0, fh[l], fw[l], sb.rect[l])) break;
+        sb.L = l + 1;
+      }
+      if (sb.L > 0) sb.mask_index = mi++;
+      if (mask_index) mask_index[bi] = sb.mask_index;
+      sboxes.push_back(sb);
+    }
+  sp.n_boxes = bi; sp.n_masks = mi;
+  const int nb = (int)sboxes.size();
+  // shelf packing per level (boxes sorted by height, tallest first; stable => deterministic)
+  std::vector<int> px[5], py[5];
+  for (int l = 0; l < 5; ++l) {
+    px[l].assign(nb, -1); py[l].assign(nb, -1);
+    std::vector<int> idx;
+    int maxw = 0; long long area = 0;
+    for (int i = 0; i < nb; ++i)
+      if (sboxes[i].L > l) {
+        idx.push_back(i);
+        const int h = sboxes[i].rect[l][2] - sboxes[i].rect[l][0], w = sboxes[i].rect[l][3] - sboxes[i].rect[l][1];
+        maxw = std::max(maxw, w); area += (long long)(h + 1) * (w + 1);
+      }
+    SegPlan::Level& L = sp.lv[l];
+    if (idx.empty()) continue;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+      return sboxes[a].rect[l][2] - sboxes[a].rect[l][0] > sboxes[b].rect[l][2] - sboxes[b].rect[l][0];
+    });
+    int WA = 128;
+    while ((long long)WA * WA < area && WA < 4096) WA *= 2;      // roughly square atlas, power-of-two width >= 128
+    while (WA < maxw + 2) WA *= 2;
+    int x = 1, y = 1, shelf_h = 0;
+    for (int i : idx) {
+      const int h = sboxes[i].rect[l][2] - sboxes[i].rect[l][0], w = sboxes[i].rect[l][3] - sboxes[i].rect[l][1];
+      if (x + w + 1 > WA) { x = 1; y += shelf_h + 1; shelf_h = 0; }
+      px[l][i] = x; py[l][i] = y;
+      x += w + 1; shelf_h = std::max(shelf_h, h);
+    }
+    L.WA = WA; L.HA = y + shelf_h + 1;
+  }
+  // scratch layout: one plane of halfs (x2 for hi/lo), then the masks
+  size_t off = 0;
+  auto alloc = [&](const SegPlan::Level& L, int C) { const size_t o = off; off += align_up((size_t)L.HA * L.WA * C, 512); return o; };
+  for (int l = 0; l < 5; ++l) {
+    SegPlan::Level& L = sp.lv[l];
+    if (L.HA == 0) continue;
+    L.P = alloc(L, kFeatC[l]);
+    if (l < 4) { L.U = alloc(L, kSegUpIn[l]); L.V = alloc(L, kSegOut[l]); L.Cc = alloc(L, kSegOut[l]); }
+    if (l == 0) L.T = alloc(L, 64);
+  }
+  sp.scratch_halfs = off;
+  size_t moff = 0;
+  for (int l = 0; l < 5; ++l) { sp.lv[l].mask = moff; moff += align_up((size_t)sp.lv[l].HA * sp.lv[l].WA, 256); }
+  sp.mask_base = align_up(off * sizeof(__half), 256) * 2;
+  // problem lists
+  for (int i = 0; i < nb; ++i) {
+    const SegBox& sb = sboxes[i];
+    for (int l = 0; l < sb.L; ++l) {
+      SegPlan::Level& L = sp.lv[l];
+      const int h = sb.rect[l][2] - sb.rect[l][0], w = sb.rect[l][3] - sb.rect[l][1];
+      const long long apos = (long long)py[l][i] * L.WA + px[l][i];
+      ResizeProb cp{};      // exact copy (same size) of the feature crop into the atlas
+      cp.in_off = (((long long)sb.img * fh[l] + sb.rect[l][0]) * fw[l] + sb.rect[l][1]) * kFeatC[l]; cp.in_pitch = fw[l] * kFeatC[l];
+      cp.Hin = h; cp.Win = w; cp.Hout = h; cp.Wout = w; cp.out_off = (long long)L.P + apos * kFeatC[l]; cp.out_pitch = L.WA * kFeatC[l];
+      L.crop.push_back(cp); L.pix_crop = std::max(L.pix_crop, h * w);
+      RectProb rp{}; rp.off = apos; rp.h = h; rp.w = w; rp.pitch = L.WA;
+      L.rects.push_back(rp);
+      if (l == sb.L - 1 && l < 4) {     // deepest level of this box: its running tensor is the raw crop (mask_forward, KGnet.py:261-262)
+        ResizeProb dp = cp;
+        dp.in_off = (long long)L.P + apos * kFeatC[l]; dp.in_pitch = L.WA * kFeatC[l];
+        dp.out_off = (long long)L.Cc + apos * kSegOut[l]; dp.out_pitch = L.WA * kSegOut[l];
+        L.deepest.push_back(dp); L.pix_deepest = std::max(L.pix_deepest, h * w);
+      }
+      if (l + 1 < sb.L) {               // pre(level l+1) -> bilinear -> U_l (KGnet.py:110)
+        SegPlan::Level& D = sp.lv[l + 1];
+        const int dh = sb.rect[l + 1][2] - sb.rect[l + 1][0], dw = sb.rect[l + 1][3] - sb.rect[l + 1][1];
+        const long long dpos = (long long)py[l + 1][i] * D.WA + px[l + 1][i];
+        ResizeProb up{};
+        const int Cs = kSegUpIn[l];
+        up.in_off = (long long)(l + 1 == 4 ? D.P : D.Cc) + dpos * Cs; up.in_pitch = D.WA * Cs; up.Hin = dh; up.Win = dw;
+        up.Hout = h; up.Wout = w; up.out_off = (long long)L.U + apos * Cs; up.out_pitch = L.WA * Cs;
+        L.up.push_back(up); L.pix_up = std::max(L.pix_up, h * w);
+      }
+    }
+    if (sb.L > 0) {
+      const int m = sb.mask_index;
+      const int h = sb.rect[0][2] - sb.rect[0][0], w = sb.rect[0][3] - sb.rect[0][1];
+      if (mask_hw) { mask_hw[2 * m] = h; mask_hw[2 * m + 1] = w; }
+      if (mask_pitch) mask_pitch[m] = sp.lv[0].WA;
+      if (mask_off) mask_off[m] = (long long)py[0][i] * sp.lv[0].WA + px[0][i];
+    }
+  }
+  sp.mask_floats = (long long)sp.lv[0].HA * sp.lv[0].WA;
+  sp.valid = true;
+  *ws_bytes = sp.mask_base + moff + 256;
+  *mask_floats = sp.mask_floats;
+  *n_masks = mi;
+  return KG_OK;
+}
+
+static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes, float* d_masks, cudaStream_t stream, int* n_launches) {
+  SegPlan& sp = net->seg;
+  Plan* p = net->plan.get();
+  size_t need = sp.mask_base + 256;
+  for (int l = 0; l < 5; ++l) need += align_up((size_t)sp.lv[l].HA * sp.lv[l].WA, 256);
+  if (seg_bytes < need) { set_error("kg_net_forward_seg: workspace too small (%zu < %zu)", seg_bytes, need); return KG_ERR_WORKSPACE; }
+  if (sp.n_masks == 0) { if (n_launches) *n_launches = 0; return KG_OK; }
+  KG_REQUIRE(dec_ws && seg_ws && d_masks, "kg_net_forward_seg: null buffer");
+  Ptrs P{(char*)dec_ws};
+  const size_t plane_bytes = align_up(sp.scratch_halfs * sizeof(__half), 256);
+  __half* s_hi = reinterpret_cast<__half*>(seg_ws);
+  __half* s_lo = reinterpret_cast<__half*>((char*)seg_ws + plane_bytes);
+  uint8_t* masks = reinterpret_cast<uint8_t*>((char*)seg_ws + sp.mask_base);
+  // upload every problem list in one blob
+  std::vector<char> blob;
+  auto put = [&](const void* src, size_t bytes) { const size_t o = align_up(blob.size(), 16); blob.resize(o + bytes); if (bytes) memcpy(blob.data() + o, src, bytes); return o; };
+  size_t o_crop[5], o_deep[5], o_up[5], o_rect[5];
+  for (int l = 0; l < 5; ++l) {
+    auto& L = sp.lv[l];
+    o_crop[l] = put(L.crop.data(), L.crop.size() * sizeof(ResizeProb));
+    o_deep[l] = put(L.deepest.data(), L.deepest.size() * sizeof(ResizeProb));
+    o_up[l] = put(L.up.data(), L.up.size() * sizeof(ResizeProb));
+    o_rect[l] = put(L.rects.data(), L.rects.size() * sizeof(RectProb));
+  }
+  if (net->seg_probs_bytes < blob.size()) {
+    if (net->d_seg_probs) cudaFree(net->d_seg_probs);
+    net->d_seg_probs = nullptr; net->seg_probs_bytes = 0;
+    KG_CUDA_CHECK(cudaMalloc(&net->d_seg_probs, blob.size() * 2));
+    net->seg_probs_bytes = blob.size() * 2;
+  }
+  KG_CUDA_CHECK(cudaMemcpyAsync(net->d_seg_probs, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
+  KG_CUDA_CHECK(cudaStreamSynchronize(stream));   // blob is a pageable temporary
+  const char* dp = (const char*)net->d_seg_probs;
+  int launches = 0;
+  StageScope ts(ST_SEG, stream);
+  const int passes = (p->precision == 1 && getenv("KG_SEG_3PASS") == nullptr) ? 1 : 3;
+  size_t mask_total = 0;
+  for (int l = 0; l < 5; ++l) mask_total += align_up((size_t)sp.lv[l].HA * sp.lv[l].WA, 256);
+  KG_CUDA_CHECK(cudaMemsetAsync(masks, 0, mask_total, stream));
+  // crops -> P_l, validity masks
+  for (int l = 0; l < 5; ++l) {
+    auto& L = sp.lv[l];
+    if (L.crop.empty()) continue;
+    const Tensor& f = p->tensors[p->feat_ids[l]];
+    KG_TRY(launch_bilinear(P.hi(f), P.lo(f), f.C, s_hi, s_lo, f.C, f.C, reinterpret_cast<const ResizeProb*>(dp + o_crop[l]), (int)L.crop.size(),
+                           L.pix_crop, stream));
+    KG_TRY(launch_fill_rects(masks + L.mask, reinterpret_cast<const RectProb*>(dp + o_rect[l]), (int)L.rects.size(), stream));
+    launches += 2;
+  }
+  auto conv = [&](const std::string& wname, const SegPlan::Level& L, size_t in0, int C0, size_t in1, int C1, size_t out, int Cout_t,
+                  float* out32, bool relu, bool sig) -> int {
+    const ConvW& w = net->convs.at(wname);
+    TcConvOp t{};
+    t.w = &w.tc; t.bias = w.d_b; t.N = 1; t.H = L.HA; t.W = L.WA; t.R = w.R; t.S = w.S; t.pad = w.R / 2;
+    t.C0 = C0; t.C1 = C1; t.Cout = w.Cout; t.passes = passes;
+    t.in0_hi = s_hi + in0; t.in0_lo = s_lo + in0; t.in0_C = C0;
+    if (C1 > 0) { t.in1_hi = s_hi + in1; t.in1_lo = s_lo + in1; t.in1_C = C1; }
+    if (out32 == nullptr) { t.out_hi = s_hi + out; t.out_lo = s_lo + out; }
+    (void)Cout_t;
+    t.relu = relu; t.sigmoid = sig; t.mask = masks + L.mask;
+    KG_TRY(tc_conv_prepare(&t));
+    ++launches;
+    return tc_conv_launch(&t, out32, stream);
+  };
+  for (int l = 3; l >= 0; --l) {
+    auto& L = sp.lv[l];
+    if (L.HA == 0) continue;
+    if (!L.up.empty()) {
+      const size_t ubytes = (size_t)L.HA * L.WA * kSegUpIn[l] * sizeof(__half);
+      KG_CUDA_CHECK(cudaMemsetAsync(s_hi + L.U, 0, ubytes, stream));
+      KG_CUDA_CHECK(cudaMemsetAsync(s_lo + L.U, 0, ubytes, stream));
+      KG_TRY(launch_bilinear(s_hi, s_lo, kSegUpIn[l], s_hi, s_lo, kSegUpIn[l], kSegUpIn[l], reinterpret_cast<const ResizeProb*>(dp + o_up[l]),
+                             (int)L.up.size(), L.pix_up, stream));
+      ++launches;
+      const std::string pre = "skip_combine." + std::to_string(l);
+      KG_TRY(conv(pre + ".up.0", L, L.U, kSegUpIn[l], 0, 0, L.V, kSegOut[l], nullptr, true, false));
+      KG_TRY(conv(pre + ".cat_conv.0", L, L.P, kFeatC[l], L.V, kSegOut[l], L.Cc, kSegOut[l], nullptr, true, false));   // cat((patch, up), 1) (:111)
+    }
+    if (L.up.empty()) {   // no conv wrote C_l: clear it so that the gaps read by the next 3x3 conv are zeros
+      const size_t cbytes = (size_t)L.HA * L.WA * kSegOut[l] * sizeof(__half);
+      KG_CUDA_CHECK(cudaMemsetAsync(s_hi + L.Cc, 0, cbytes, stream));
+      KG_CUDA_CHECK(cudaMemsetAsync(s_lo + L.Cc, 0, cbytes, stream));
+    }
+    if (!L.deepest.empty()) {
+      KG_TRY(launch_bilinear(s_hi, s_lo, kFeatC[l], s_hi, s_lo, kSegOut[l], kFeatC[l], reinterpret_cast<const ResizeProb*>(dp + o_deep[l]),
+                             (int)L.deepest.size(), L.pix_deepest, stream));
+      ++launches;
+    }
+  }
+  const auto& L0 = sp.lv[0];
+  KG_TRY(conv("seg_head.0", L0, L0.Cc, 64, 0, 0, L0.T, 64, nullptr, true, false));
+  KG_TRY(conv("seg_head.2", L0, L0.T, 64, 0, 0, 0, 1, d_masks, false, true));
+  if (n_launches) *n_launches = launches;
+  return KG_OK;
+}
+
 // Single-layer entry used by the unit tests (one nn.Conv2d [+ReLU] [+residual], KGnet.py:45-61 style).
 static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R, int S,
                        int stride, int pad, int relu, const float* d_res, int mode, float* d_y, cudaStream_t stream) {
@@ -706,12 +954,13 @@ static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const flo
       a.relu = relu; a.probs = d_probs;
       if ((rc = launch_conv_ffma(a, N, Ho * Wo, stream)) != KG_OK) break;
     } else {
-      if (stride != 1 || !tc_layer_supported(Cin, Cout, R, S) || Cout % 16 != 0 || 2 * pad != R - 1 || R != S) {
+      if ((stride != 1 && stride != 2) || !tc_layer_supported(Cin, Cout, R, S) || Cout % 16 != 0 || 2 * pad != R - 1 || R != S) {
         set_error("kg_conv2d_nchw: shape not supported by the tensor-core path"); rc = KG_ERR_INVALID; break;
       }
       if ((rc = tc_pack_weights(w.h_w.data(), Cin, Cout, R, S, &w.tc)) != KG_OK) break;
       TcConvOp t{};
       t.w = &w.tc; t.bias = w.d_b; t.N = N; t.H = Ho; t.W = Wo; t.R = R; t.S = S; t.pad = pad; t.C0 = Cin; t.C1 = 0; t.Cout = Cout;
+      t.stride = stride; t.Hin = H; t.Win = W;
       t.passes = mode; t.in0_hi = xh; t.in0_lo = xl; t.in0_C = Cin; t.out_hi = yh; t.out_lo = yl; t.res_hi = rh; t.res_lo = rl; t.relu = relu != 0;
       if ((rc = tc_conv_prepare(&t)) != KG_OK) break;
       if ((rc = tc_conv_launch(&t, nullptr, stream)) != KG_OK) break;
@@ -787,9 +1036,9 @@ int kg_net_import_feats(kg_net* h, const float* const* d_feats, int N, int H, in
 }
 
 int kg_net_seg_prepare(kg_net* h, int N, int H, int W, const int* box_counts, const double* h_boxes, size_t* seg_workspace_bytes,
-                       long long* mask_floats, int* n_masks, int* h_mask_index, int* h_mask_hw, long long* h_mask_off) {
+                       long long* mask_floats, int* n_masks, int* h_mask_index, int* h_mask_hw, long long* h_mask_off, int* h_mask_pitch) {
   return seg_prepare(reinterpret_cast<Net*>(h), N, H, W, box_counts, h_boxes, seg_workspace_bytes, mask_floats, n_masks, h_mask_index,
-                     h_mask_hw, h_mask_off);
+                     h_mask_hw, h_mask_off, h_mask_pitch);
 }
 
 int kg_net_forward_seg(kg_net* h, void* d_dec_workspace, void* d_seg_workspace, size_t seg_workspace_bytes, float* d_masks, void* stream,

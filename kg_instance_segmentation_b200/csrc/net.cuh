@@ -37,8 +37,13 @@ struct ResizeProb {
   int Hin, Win, in_pitch, Hout, Wout, out_pitch;
 };
 
+struct RectProb { long long off; int h, w, pitch; };
+
 // launchers (net_kernels.cu)
+int launch_fill_rects(uint8_t* mask, const RectProb* rects, int nrect, cudaStream_t s);
 int launch_conv_ffma(const ConvArgs& a, int nprob, int max_pix, cudaStream_t s);
+int launch_stem_conv(const float* x, const float* w, const float* bias, __half* out_hi, __half* out_lo, int N, int H, int W, int K,
+                     int stride, cudaStream_t s);
 int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
                     const ResizeProb* probs, int nprob, int max_pix, cudaStream_t s);
 int launch_maxpool3x3s2(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int N, int Hin, int Win,

@@ -134,6 +134,79 @@ int launch_conv_ffma(const ConvArgs& a, int nprob, int max_pix, cudaStream_t s) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem convolutions on the raw image (KGnet.py:139-141 c0_conv.0: 3->64 3x3/s1, KGnet.py:131-133 conv1+bn1: 3->64
+// 7x7/s2), fp32 NCHW in, split-fp16 NHWC out, ReLU fused.  Cin = 3 makes these HBM-bound on the output write, so one
+// thread owns one output pixel and all 64 output channels (128 B contiguous per plane); weights are broadcast from smem.
+template <int K, int STRIDE>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, __half* __restrict__ out_hi,
+                                                        __half* __restrict__ out_lo, int N, int H, int W, int Ho, int Wo) {
+  __shared__ __align__(16) float sw[K * K * 3 * 64];
+  for (int e = threadIdx.x; e < K * K * 3 * 64; e += 128) sw[e] = w[e];
+  __syncthreads();
+  const long long total = (long long)N * Ho * Wo;
+  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (p >= total) return;
+  const int ox = (int)(p % Wo);
+  const int oy = (int)((p / Wo) % Ho);
+  const int n = (int)(p / ((long long)Wo * Ho));
+  constexpr int PAD = K / 2;
+  float acc[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc[j] = __ldg(bias + j);
+  const float* xn = x + (long long)n * 3 * H * W;
+  for (int r = 0; r < K; ++r) {
+    const int iy = oy * STRIDE - PAD + r;
+    if (iy < 0 || iy >= H) continue;
+    for (int s = 0; s < K; ++s) {
+      const int ix = ox * STRIDE - PAD + s;
+      if (ix < 0 || ix >= W) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = __ldg(xn + ((long long)c * H + iy) * W + ix);
+        const float4* wr = reinterpret_cast<const float4*>(&sw[((r * K + s) * 3 + c) * 64]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 w4 = wr[j];
+          acc[4 * j] = fmaf(v, w4.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  uint4* oh = reinterpret_cast<uint4*>(out_hi + p * 64);
+  uint4* ol = reinterpret_cast<uint4*>(out_lo + p * 64);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 h4, l4;
+    __half2* hh = reinterpret_cast<__half2*>(&h4);
+    __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = fminf(fmaxf(acc[q * 8 + 2 * e], 0.f), 65504.f), b = fminf(fmaxf(acc[q * 8 + 2 * e + 1], 0.f), 65504.f);
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(h);
+      hh[e] = h;
+      ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+    }
+    oh[q] = h4; ol[q] = l4;
+  }
+}
+
+int launch_stem_conv(const float* x, const float* w, const float* bias, __half* out_hi, __half* out_lo, int N, int H, int W, int K,
+                     int stride, cudaStream_t s) {
+  const int pad = K / 2;
+  const int Ho = (H + 2 * pad - K) / stride + 1, Wo = (W + 2 * pad - K) / stride + 1;
+  const long long total = (long long)N * Ho * Wo;
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  if (K == 3 && stride == 1) stem_conv_kernel<3, 1><<<grid, 128, 0, s>>>(x, w, bias, out_hi, out_lo, N, H, W, Ho, Wo);
+  else if (K == 7 && stride == 2) stem_conv_kernel<7, 2><<<grid, 128, 0, s>>>(x, w, bias, out_hi, out_lo, N, H, W, Ho, Wo);
+  else { set_error("stem conv: unsupported k=%d stride=%d", K, stride); return KG_ERR_INVALID; }
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // F.interpolate(mode='bilinear', align_corners=False) to an explicit size (KGnet.py:110,288-297), fp32 math.
 __global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                                                        int in_ps, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
@@ -170,6 +243,23 @@ int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half*
   KG_REQUIRE((C & 3) == 0, "bilinear: C=%d must be a multiple of 4", C);
   dim3 grid((unsigned)(((long long)max_pix * (C >> 2) + 255) / 256), 1, nprob);
   bilinear_kernel<<<grid, 256, 0, s>>>(in_hi, in_lo, in_ps, out_hi, out_lo, out_ps, C, probs);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// validity mask of the forward_seg atlas: 1 inside every packed box rectangle
+__global__ void __launch_bounds__(128) fill_rects_kernel(uint8_t* __restrict__ mask, const RectProb* __restrict__ rects) {
+  const RectProb r = rects[blockIdx.x];
+  for (int e = threadIdx.x; e < r.h * r.w; e += 128) {
+    const int y = e / r.w, x = e - y * r.w;
+    mask[r.off + (long long)y * r.pitch + x] = 1;
+  }
+}
+
+int launch_fill_rects(uint8_t* mask, const RectProb* rects, int nrect, cudaStream_t s) {
+  if (nrect <= 0) return KG_OK;
+  fill_rects_kernel<<<nrect, 128, 0, s>>>(mask, rects);
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;
 }

@@ -37,9 +37,10 @@ struct TcParams {
   __half* out_hi; __half* out_lo;
   float* out32;
   const __half* res_hi; const __half* res_lo;
+  const uint8_t* mask;
   float inv_scale;
   int N, H, W, Cout;
-  int R, S, pad;
+  int R, S, pad, stride;
   int chunks0, chunks1, coff0;
   int BN, BW, BH, tiles_x, tiles_y, m_tiles;
   int MT, NPL, passes, stages;
@@ -176,8 +177,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const int c = src == 0 ? p.coff0 + ch * TC_BK : (ch - p.chunks0) * TC_BK;
         for (int mt = 0; mt < p.MT; ++mt)
           for (int pl = 0; pl < p.NPL; ++pl)
-            tma_load_4d(sbase + (uint32_t)(mt * p.NPL + pl) * TC_A_TILE, &p.a_map[src][pl], c, tx0[mt] + s - p.pad,
-                        ty0[mt] + r - p.pad, tn[mt], full_bar(stage));
+            tma_load_4d(sbase + (uint32_t)(mt * p.NPL + pl) * TC_A_TILE, &p.a_map[src][pl], c, tx0[mt] * p.stride + s - p.pad,
+                        ty0[mt] * p.stride + r - p.pad, tn[mt], full_bar(stage));
         for (int pl = 0; pl < p.NPL; ++pl)
           tma_load_3d(sbase + a_bytes + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, tap, full_bar(stage));
         if (++ch == chunks) { ch = 0; ++tap; }
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const int oy = ty * p.BH + row / p.BW, ox = tx * p.BW + row % p.BW;
       const bool valid = oy < p.H && ox < p.W;
       const long long pix = (long long)n * HW + (long long)oy * p.W + ox;
+      const bool keep = valid && (p.mask == nullptr || p.mask[pix] != 0);
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.BN + c0), raw);
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           for (int j = 0; j < 16; ++j) {
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
             if (p.sigmoid) v[j] = 1.f / (1.f + expf(-v[j]));
+            if (!keep) v[j] = 0.f;
           }
           if (p.out_hi != nullptr) {
             uint4 hi4[2], lo4[2];
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               float x = v[j] + __ldg(p.bias + co);
               if (p.relu) x = fmaxf(x, 0.f);
               if (p.sigmoid) x = 1.f / (1.f + expf(-x));
+              if (!keep) x = 0.f;
               if (p.out32 != nullptr) p.out32[((long long)n * p.Cout + co) * HW + (long long)oy * p.W + ox] = x;
             }
           }
@@ -337,6 +341,7 @@ static void tc_init() {
 }
 
 bool tc_available() { tc_init(); return g_tc_state == 1; }
+bool tc_stride2_enabled() { const char* v = getenv("KG_TC_STRIDE2"); return !(v && v[0] == '0'); }
 const char* tc_status() { tc_init(); return g_tc_msg; }
 bool tc_layer_supported(int cin, int cout, int R, int S) { return cin % TC_BK == 0 && cout >= 1 && R >= 1 && S >= 1 && R * S <= 64; }
 
@@ -377,11 +382,12 @@ int tc_pack_weights(const float* w, int cin, int cout, int R, int S, TcWeights* 
   return KG_OK;
 }
 
-static int encode_act_map(CUtensorMap* m, const __half* base, int C, int W, int H, int N, int BW, int BH) {
+static int encode_act_map(CUtensorMap* m, const __half* base, int C, int W, int H, int N, int BW, int BH, int stride = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)BW, (cuuint32_t)BH, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  // strided convs: the box spans stride*B input pixels and TMA picks every stride-th one (elementStrides)
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(BW * stride), (cuuint32_t)(BH * stride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations C=%d W=%d H=%d N=%d box %dx%d) failed: %d", C, W, H, N, BW, BH, (int)r); return KG_ERR_CUDA; }
@@ -416,6 +422,9 @@ int tc_conv_prepare(TcConvOp* op) {
   TcParams& p = *sp;
   memset(&p, 0, sizeof(p));
   p.N = op->N; p.H = op->H; p.W = op->W; p.Cout = op->Cout; p.R = op->R; p.S = op->S; p.pad = op->pad;
+  p.stride = op->stride;
+  const int Hin = op->stride == 1 ? op->H : op->Hin, Win = op->stride == 1 ? op->W : op->Win;
+  KG_REQUIRE(op->stride == 1 || (op->stride == 2 && op->C1 == 0 && Hin > 0 && Win > 0), "tc_conv_prepare: unsupported stride %d", op->stride);
   p.chunks0 = op->C0 / TC_BK; p.chunks1 = op->C1 / TC_BK; p.coff0 = op->in0_coff;
   p.BN = op->w->cout_pad <= 256 ? op->w->cout_pad : 256;
   int bw = 1;
@@ -446,9 +455,9 @@ int tc_conv_prepare(TcConvOp* op) {
   p.tmem_cols = cols;
   p.bias = op->bias; p.inv_scale = op->w->inv_scale;
   p.out_hi = op->out_hi; p.out_lo = op->out_lo; p.res_hi = op->res_hi; p.res_lo = op->res_lo;
-  p.relu = op->relu; p.sigmoid = op->sigmoid;
-  KG_TRY(encode_act_map(&p.a_map[0][0], op->in0_hi, op->in0_C, op->W, op->H, op->N, p.BW, p.BH));
-  if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[0][1], op->in0_lo, op->in0_C, op->W, op->H, op->N, p.BW, p.BH));
+  p.relu = op->relu; p.sigmoid = op->sigmoid; p.mask = op->mask;
+  KG_TRY(encode_act_map(&p.a_map[0][0], op->in0_hi, op->in0_C, Win, Hin, op->N, p.BW, p.BH, op->stride));
+  if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[0][1], op->in0_lo, op->in0_C, Win, Hin, op->N, p.BW, p.BH, op->stride));
   if (op->C1 > 0) {
     KG_TRY(encode_act_map(&p.a_map[1][0], op->in1_hi, op->in1_C, op->W, op->H, op->N, p.BW, p.BH));
     if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[1][1], op->in1_lo, op->in1_C, op->W, op->H, op->N, p.BW, p.BH));

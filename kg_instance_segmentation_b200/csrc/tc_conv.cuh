@@ -25,19 +25,22 @@ struct TcParams;   // kernel parameter block (tensor maps + scalars), defined in
 struct TcConvOp {
   const TcWeights* w = nullptr;
   const float* bias = nullptr;
-  int N = 0, H = 0, W = 0, R = 0, S = 0, pad = 0;   // H, W: output (= input) spatial size
+  int N = 0, H = 0, W = 0, R = 0, S = 0, pad = 0;   // H, W: output spatial size
+  int stride = 1, Hin = 0, Win = 0;                  // input spatial size (== H, W when stride is 1)
   int C0 = 0, C1 = 0, Cout = 0, passes = 1;
   const __half *in0_hi = nullptr, *in0_lo = nullptr, *in1_hi = nullptr, *in1_lo = nullptr;
   int in0_C = 0, in0_coff = 0, in1_C = 0;            // channel counts (pixel strides) of the source tensors
   __half *out_hi = nullptr, *out_lo = nullptr;
   const __half *res_hi = nullptr, *res_lo = nullptr;
   bool relu = false, sigmoid = false;
+  const uint8_t* mask = nullptr;                     // optional per-pixel validity mask: outputs of masked-out pixels are 0
   // filled by tc_conv_prepare
   std::shared_ptr<void> params;                      // host copy of TcParams (tensor maps + scalars)
   unsigned grid_x = 0, grid_y = 0, smem_bytes = 0;
 };
 
 bool tc_available();
+bool tc_stride2_enabled();
 const char* tc_status();
 bool tc_layer_supported(int cin, int cout, int R, int S);
 int tc_pack_weights(const float* w_tap_cin_cout, int cin, int cout, int R, int S, TcWeights* out);

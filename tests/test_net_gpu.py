@@ -82,6 +82,22 @@ TC_CASES = [
 ]
 
 
+TC_STRIDE2_CASES = [
+    (2, 128, 16, 16, 128, 3, 2, True, False),   # layer2.0.conv2
+    (1, 256, 32, 32, 512, 1, 2, False, False),  # layer2.0.downsample
+    (1, 256, 16, 24, 256, 3, 2, True, False),
+]
+
+
+@pytest.mark.parametrize("case", TC_STRIDE2_CASES)
+def test_conv_tensor_core_stride2(case):
+    x, w, b, pad, r, y = _case(4, *case)
+    got = _conv(x, w, b, 2, pad, case[7], r, 3)
+    scale = float(y.abs().max())
+    err = float((got - y).abs().max())
+    assert err <= 2e-4 * scale + 1e-5, f"max err {err}"
+
+
 @pytest.mark.parametrize("case", TC_CASES)
 @pytest.mark.parametrize("mode", [3, 1])
 def test_conv_tensor_core_path(case, mode):
