@@ -43,7 +43,11 @@ struct TcParams {
   int R, S, pad, stride;
   int chunks0, chunks1, coff0;
   int BN, BW, BH, tiles_x, tiles_y, m_tiles;
-  int MT, NPL, passes, stages;
+  int MT, NPL, passes;
+  int NA, NW;                       // slots of the activation ring / weight ring
+  int strip;                        // 1: A slot = (BW + S - 1)-pixel strip shared by the S taps of a filter row
+  unsigned a_tile_bytes, a_tx_bytes;   // smem bytes reserved per A tile (1024-aligned) / bytes TMA delivers per A tile
+  int base_offset_mode;
   int relu, sigmoid;
   unsigned tmem_cols;
 };
@@ -94,6 +98,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
   return d;
 }
+// A-operand descriptor whose start address may sit s rows (s * 128 B) inside a 1024-byte swizzle atom (strip mode):
+// the descriptor's base-offset field carries (start >> 7) & 7 so that the hardware applies the same XOR pattern TMA used.
+__device__ __forceinline__ uint64_t umma_desc_a(uint32_t saddr, int base_offset_mode) {
+  uint64_t d = umma_desc(saddr);
+  if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -115,18 +126,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
+// Two independent smem rings: the A ring holds activation tiles, the W ring holds weight tiles.  In "strip" mode
+// (tile = one image row of 128 pixels, filter wider than 1) one A slot holds the 128+S-1 pixel strip of filter row r and
+// is reused by the S horizontal taps: tap s reads it through a descriptor whose start address is advanced by s rows
+// (s * 128 B), so the activations are fetched from L2 once per filter ROW instead of once per tap.
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 128B swizzle atoms need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_bytes = (uint32_t)(p.MT * p.NPL) * TC_A_TILE;
+  const uint32_t a_tile = p.a_tile_bytes;                             // one plane of one pixel tile (or strip)
+  const uint32_t a_slot = (uint32_t)(p.MT * p.NPL) * a_tile;
   const uint32_t w_tile = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)p.NPL * w_tile;
-  const uint32_t bars = smem0 + (uint32_t)p.stages * stage_bytes;
-  const uint32_t bar_tmem_full = bars + 16u * p.stages;
+  const uint32_t w_slot = (uint32_t)p.NPL * w_tile;
+  const uint32_t a_ring = smem0, w_ring = smem0 + (uint32_t)p.NA * a_slot;
+  const uint32_t bars = w_ring + (uint32_t)p.NW * w_slot;
+  auto a_full = [&](int s) { return bars + 8u * s; };
+  auto a_empty = [&](int s) { return bars + 8u * (p.NA + s); };
+  auto w_full = [&](int s) { return bars + 16u * p.NA + 8u * s; };
+  auto w_empty = [&](int s) { return bars + 16u * p.NA + 8u * (p.NW + s); };
+  const uint32_t bar_tmem_full = bars + 16u * (p.NA + p.NW);
   const uint32_t tmem_slot = bar_tmem_full + 8u;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.a_map[0][0]); prefetch_tmap(&p.w_map[0]);
@@ -134,7 +153,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     if (p.chunks1 > 0) { prefetch_tmap(&p.a_map[1][0]); if (p.NPL == 2) prefetch_tmap(&p.a_map[1][1]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     mbar_init(bar_tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -149,7 +169,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   const int chunks = p.chunks0 + p.chunks1;
-  const int ksteps = p.R * p.S * chunks;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int m_first = blockIdx.x * p.MT;
   const int n0 = blockIdx.y * p.BN;
@@ -166,48 +185,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           tn[mt] = n; ty0[mt] = ty * p.BH; tx0[mt] = tx * p.BW;
         } else { tn[mt] = p.N; ty0[mt] = 0; tx0[mt] = 0; }       // out-of-range tile: TMA zero-fills
       }
-      int stage = 0; uint32_t phase = 0;
-      int tap = 0, ch = 0;
-      for (int i = 0; i < ksteps; ++i) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sbase = smem0 + (uint32_t)stage * stage_bytes;
-        mbar_expect_tx(full_bar(stage), stage_bytes);
-        const int r = tap / p.S, s = tap - r * p.S;
-        const int src = ch < p.chunks0 ? 0 : 1;
-        const int c = src == 0 ? p.coff0 + ch * TC_BK : (ch - p.chunks0) * TC_BK;
-        for (int mt = 0; mt < p.MT; ++mt)
-          for (int pl = 0; pl < p.NPL; ++pl)
-            tma_load_4d(sbase + (uint32_t)(mt * p.NPL + pl) * TC_A_TILE, &p.a_map[src][pl], c, tx0[mt] * p.stride + s - p.pad,
-                        ty0[mt] * p.stride + r - p.pad, tn[mt], full_bar(stage));
-        for (int pl = 0; pl < p.NPL; ++pl)
-          tma_load_3d(sbase + a_bytes + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, tap, full_bar(stage));
-        if (++ch == chunks) { ch = 0; ++tap; }
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      }
+      int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
+      for (int r = 0; r < p.R; ++r)
+        for (int ch = 0; ch < chunks; ++ch) {
+          const int src = ch < p.chunks0 ? 0 : 1;
+          const int c = src == 0 ? p.coff0 + ch * TC_BK : (ch - p.chunks0) * TC_BK;
+          for (int s = 0; s < p.S; ++s) {
+            if (!p.strip || s == 0) {
+              mbar_wait(a_empty(ai), aph ^ 1u);
+              mbar_expect_tx(a_full(ai), (uint32_t)(p.MT * p.NPL) * p.a_tx_bytes);
+              const uint32_t abase = a_ring + (uint32_t)ai * a_slot;
+              for (int mt = 0; mt < p.MT; ++mt)
+                for (int pl = 0; pl < p.NPL; ++pl)
+                  tma_load_4d(abase + (uint32_t)(mt * p.NPL + pl) * a_tile, &p.a_map[src][pl], c,
+                              tx0[mt] * p.stride + (p.strip ? 0 : s) - p.pad, ty0[mt] * p.stride + r - p.pad, tn[mt], a_full(ai));
+              if (++ai == p.NA) { ai = 0; aph ^= 1u; }
+            }
+            mbar_wait(w_empty(wi), wph ^ 1u);
+            mbar_expect_tx(w_full(wi), w_slot);
+            const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
+            for (int pl = 0; pl < p.NPL; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
+            if (++wi == p.NW) { wi = 0; wph ^= 1u; }
+          }
+        }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
-      int stage = 0; uint32_t phase = 0;
-      for (int i = 0; i < ksteps; ++i) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint32_t sbase = smem0 + (uint32_t)stage * stage_bytes;
-        for (int mt = 0; mt < p.MT; ++mt) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(mt * p.BN);
-          for (int ps = 0; ps < p.passes; ++ps) {
-            const int apl = ps == 1 ? 1 : 0, wpl = ps == 2 ? 1 : 0;      // hi*hi, lo*hi, hi*lo
-            const uint32_t a_addr = sbase + (uint32_t)(mt * p.NPL + apl) * TC_A_TILE;
-            const uint32_t b_addr = sbase + a_bytes + (uint32_t)wpl * w_tile;
+      int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
+      uint32_t first = 0;
+      for (int r = 0; r < p.R; ++r)
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int s = 0; s < p.S; ++s) {
+            if (!p.strip || s == 0) mbar_wait(a_full(ai), aph);
+            mbar_wait(w_full(wi), wph);
+            tc_fence_after();
+            const uint32_t abase = a_ring + (uint32_t)ai * a_slot + (p.strip ? (uint32_t)s * 128u : 0u);
+            const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(mt * p.BN);
+              for (int ps = 0; ps < p.passes; ++ps) {
+                const int apl = ps == 1 ? 1 : 0, wpl = ps == 2 ? 1 : 0;      // hi*hi, lo*hi, hi*lo
+                const uint32_t a_addr = abase + (uint32_t)(mt * p.NPL + apl) * a_tile;
+                const uint32_t b_addr = wbase + (uint32_t)wpl * w_tile;
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k)
-              umma_f16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, (i | ps | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < TC_BK / 16; ++k)
+                  umma_f16(d_tmem, umma_desc_a(a_addr + k * 32, p.base_offset_mode), umma_desc(b_addr + k * 32), idesc,
+                           (first | (uint32_t)ps | (uint32_t)k) != 0 ? 1u : 0u);
+              }
+            }
+            first = 1;
+            umma_commit(w_empty(wi));           // frees the weight slot once these MMAs have read it
+            if (++wi == p.NW) { wi = 0; wph ^= 1u; }
+            if (!p.strip || s == p.S - 1) {
+              umma_commit(a_empty(ai));
+              if (++ai == p.NA) { ai = 0; aph ^= 1u; }
+            }
           }
-        }
-        umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      }
       umma_commit(bar_tmem_full);
     }
   } else {
@@ -439,34 +474,57 @@ int tc_conv_prepare(TcConvOp* op) {
   if (mt > 2) mt = 2;
   if (mt * p.BN > 512) mt = 1;
   p.MT = mt;
-  const size_t stage_bytes = (size_t)p.MT * p.NPL * TC_A_TILE + (size_t)p.NPL * p.BN * 128;
-  int stages = (int)((TC_MAX_SMEM - 2048) / stage_bytes);
-  if (stages > 8) stages = 8;
-  stages = env_int("KG_TC_STAGES", stages) < stages ? env_int("KG_TC_STAGES", stages) : stages;
-  if (stages < 2 && p.MT == 2) {   // fall back to one accumulator tile
-    p.MT = 1;
-    stages = (int)((TC_MAX_SMEM - 2048) / ((size_t)p.NPL * TC_A_TILE + (size_t)p.NPL * p.BN * 128));
-    if (stages > 8) stages = 8;
+  // strip mode: tile = one 128-pixel image row, the S taps of a filter row share one (128 + S - 1)-pixel strip
+  const bool strip = op->stride == 1 && op->S > 1 && p.BW == TC_BM && env_int("KG_TC_STRIP", 1) != 0;
+  p.strip = strip ? 1 : 0;
+  p.base_offset_mode = env_int("KG_TC_BASEOFF", 0);
+  const int strip_px = strip ? TC_BM + op->S - 1 : TC_BM;
+  p.a_tx_bytes = (unsigned)(strip ? strip_px * 128 : TC_A_TILE);
+  p.a_tile_bytes = (unsigned)align_up(p.a_tx_bytes, 1024);
+  const size_t budget = TC_MAX_SMEM - 2048;
+  auto fit = [&](int mtv, int* na, int* nw) {
+    const size_t a_slot = (size_t)mtv * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.NPL * p.BN * 128;
+    if (strip) {
+      *na = 2;
+      if (2 * a_slot + 2 * w_slot > budget) return false;
+      *nw = (int)((budget - 2 * a_slot) / w_slot);
+      if (*nw > 8) *nw = 8;
+      if (*nw >= 6 && 3 * a_slot + 4 * w_slot <= budget) { *na = 3; *nw = (int)((budget - 3 * a_slot) / w_slot); if (*nw > 8) *nw = 8; }
+      return *nw >= 2;
+    }
+    int st = (int)(budget / (a_slot + w_slot));
+    if (st > 8) st = 8;
+    *na = *nw = st;
+    return st >= 2;
+  };
+  int na = 0, nw = 0;
+  if (!fit(p.MT, &na, &nw) && p.MT == 2) { p.MT = 1; }
+  if (!fit(p.MT, &na, &nw)) {
+    const size_t a_slot = (size_t)p.MT * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.NPL * p.BN * 128;
+    KG_REQUIRE(a_slot + w_slot <= budget, "tc_conv_prepare: tile does not fit in shared memory");
+    na = nw = 1;
   }
-  KG_REQUIRE(stages >= 1, "tc_conv_prepare: tile does not fit in shared memory");
-  p.stages = stages;
+  const int cap = env_int("KG_TC_STAGES", 0);
+  if (cap > 0) { if (na > cap) na = cap; if (nw > cap) nw = cap; }
+  p.NA = na; p.NW = nw;
   unsigned cols = 32;
   while (cols < (unsigned)(p.MT * p.BN)) cols *= 2;
   p.tmem_cols = cols;
   p.bias = op->bias; p.inv_scale = op->w->inv_scale;
   p.out_hi = op->out_hi; p.out_lo = op->out_lo; p.res_hi = op->res_hi; p.res_lo = op->res_lo;
   p.relu = op->relu; p.sigmoid = op->sigmoid; p.mask = op->mask;
-  KG_TRY(encode_act_map(&p.a_map[0][0], op->in0_hi, op->in0_C, Win, Hin, op->N, p.BW, p.BH, op->stride));
-  if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[0][1], op->in0_lo, op->in0_C, Win, Hin, op->N, p.BW, p.BH, op->stride));
+  const int box_w = strip ? strip_px : p.BW;
+  KG_TRY(encode_act_map(&p.a_map[0][0], op->in0_hi, op->in0_C, Win, Hin, op->N, box_w, p.BH, op->stride));
+  if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[0][1], op->in0_lo, op->in0_C, Win, Hin, op->N, box_w, p.BH, op->stride));
   if (op->C1 > 0) {
-    KG_TRY(encode_act_map(&p.a_map[1][0], op->in1_hi, op->in1_C, op->W, op->H, op->N, p.BW, p.BH));
-    if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[1][1], op->in1_lo, op->in1_C, op->W, op->H, op->N, p.BW, p.BH));
+    KG_TRY(encode_act_map(&p.a_map[1][0], op->in1_hi, op->in1_C, op->W, op->H, op->N, box_w, p.BH));
+    if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[1][1], op->in1_lo, op->in1_C, op->W, op->H, op->N, box_w, p.BH));
   }
   KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.BN));
   if (p.NPL == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN));
   op->grid_x = (unsigned)ceil_div(p.m_tiles, p.MT);
   op->grid_y = (unsigned)(op->w->cout_pad / p.BN);
-  op->smem_bytes = (unsigned)((size_t)p.stages * stage_bytes + 16 * p.stages + 64 + 1024);
+  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 64 + 1024);
   KG_REQUIRE(op->smem_bytes <= (unsigned)TC_MAX_SMEM, "tc_conv_prepare: smem %u > %d", op->smem_bytes, TC_MAX_SMEM);
   op->params = sp;
   return KG_OK;

@@ -79,6 +79,10 @@ TC_CASES = [
     (1, 256, 8, 8, 768, 7, 1, True, False),     # fused first-layer heads c2 (3 N tiles)
     (2, 64, 4, 4, 64, 3, 1, False, False),      # tiny map: tile taller than the image
     (3, 64, 8, 8, 64, 1, 1, False, False),      # odd number of M tiles
+    (1, 64, 6, 128, 64, 3, 1, True, False),     # W >= 128: strip mode (taps of a filter row share one activation strip)
+    (2, 64, 5, 256, 192, 7, 1, True, False),    # strip mode, 7x7, two tiles per row
+    (1, 128, 3, 200, 128, 3, 1, False, False),  # strip mode with a partial last tile
+    (1, 64, 4, 128, 16, 7, 1, False, False),    # strip mode, narrow N (second-layer heads class)
 ]
 
 
@@ -152,7 +156,8 @@ def test_forward_seg_matches_golden(precision):
             ref = g[f"ref_mask{i}_{j}"]
             got = seg[0][i][j].cpu().numpy()
             assert got.shape == ref.shape
-            assert np.abs(got - ref).max() <= 2e-3, (i, j, np.abs(got - ref).max())
+            # masks: CUDA-core path 2e-3; "fast" runs the mask branch in single-pass fp16 (10 layers deep): 6e-3
+            assert np.abs(got - ref).max() <= (2e-3 if precision == "reference" else 6e-3), (i, j, np.abs(got - ref).max())
             assert np.array_equal(seg[1][i][j].numpy(), g[f"ref_det{i}_{j}"])
 
 

@@ -39,12 +39,13 @@ def run(N, Cin, H, W, Cout, k, mode, relu=False, seed=0, ident=False):
 
 
 for mode in (1, 3):
-    run(1, 64, 16, 8, 64, 1, mode, ident=True)
     run(1, 64, 16, 8, 64, 1, mode)
-    run(1, 64, 16, 8, 64, 3, mode, ident=True)
     run(1, 64, 16, 16, 64, 3, mode)
-    run(2, 128, 16, 16, 128, 3, mode, relu=True)
-    run(1, 64, 32, 32, 192, 7, mode)
+    run(1, 64, 8, 128, 64, 3, mode, ident=True)     # strip mode (W >= 128)
+    run(1, 64, 8, 128, 64, 3, mode)
+    run(2, 64, 4, 256, 64, 3, mode, relu=True)
+    run(1, 64, 6, 128, 192, 7, mode)
+    run(1, 128, 5, 384, 128, 3, mode)
     run(1, 256, 16, 16, 512, 3, mode)
 torch.cuda.synchronize()
 print("done")
