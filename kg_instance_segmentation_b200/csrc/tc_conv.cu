@@ -17,6 +17,7 @@
 //                  smem full/empty mbarrier ring between producer and MMA, one tmem_full barrier to the epilogue.
 #include "tc_conv.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -45,6 +46,10 @@ struct TcParams {
   int BN, BW, BH, tiles_x, tiles_y, m_tiles;
   int MT, NPL, passes;
   int NA, NW;                       // slots of the activation ring / weight ring
+  int n_tiles, num_work;            // N tiles; work items = ceil(m_tiles / MT) * n_tiles, walked persistently
+  int acc_stages;                   // TMEM accumulator buffers (2 = epilogue of tile i overlaps the MMAs of tile i+1)
+  int KS;                           // independent accumulator chains per pixel tile (partials are summed in the epilogue):
+                                    // back-to-back MMAs into ONE accumulator serialise on its latency when N is small
   int strip;                        // 1: A slot = (BW + S - 1)-pixel strip shared by the S taps of a filter row
   unsigned a_tile_bytes, a_tx_bytes;   // smem bytes reserved per A tile (1024-aligned) / bytes TMA delivers per A tile
   int base_offset_mode;
@@ -130,32 +135,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 // (tile = one image row of 128 pixels, filter wider than 1) one A slot holds the 128+S-1 pixel strip of filter row r and
 // is reused by the S horizontal taps: tap s reads it through a descriptor whose start address is advanced by s rows
 // (s * 128 B), so the activations are fetched from L2 once per filter ROW instead of once per tap.
+template <int MT, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
+  constexpr int NPL = PASSES == 3 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 128B swizzle atoms need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_tile = p.a_tile_bytes;                             // one plane of one pixel tile (or strip)
-  const uint32_t a_slot = (uint32_t)(p.MT * p.NPL) * a_tile;
+  const uint32_t a_slot = (uint32_t)(MT * NPL) * a_tile;
   const uint32_t w_tile = (uint32_t)p.BN * 128u;
-  const uint32_t w_slot = (uint32_t)p.NPL * w_tile;
+  const uint32_t w_slot = (uint32_t)NPL * w_tile;
   const uint32_t a_ring = smem0, w_ring = smem0 + (uint32_t)p.NA * a_slot;
   const uint32_t bars = w_ring + (uint32_t)p.NW * w_slot;
   auto a_full = [&](int s) { return bars + 8u * s; };
   auto a_empty = [&](int s) { return bars + 8u * (p.NA + s); };
   auto w_full = [&](int s) { return bars + 16u * p.NA + 8u * s; };
   auto w_empty = [&](int s) { return bars + 16u * p.NA + 8u * (p.NW + s); };
-  const uint32_t bar_tmem_full = bars + 16u * (p.NA + p.NW);
-  const uint32_t tmem_slot = bar_tmem_full + 8u;
+  const uint32_t bar_tmem = bars + 16u * (p.NA + p.NW);
+  auto tmem_full = [&](int a) { return bar_tmem + 8u * a; };
+  auto tmem_empty = [&](int a) { return bar_tmem + 16u + 8u * a; };
+  const uint32_t tmem_slot = bar_tmem + 32u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.a_map[0][0]); prefetch_tmap(&p.w_map[0]);
-    if (p.NPL == 2) { prefetch_tmap(&p.a_map[0][1]); prefetch_tmap(&p.w_map[1]); }
-    if (p.chunks1 > 0) { prefetch_tmap(&p.a_map[1][0]); if (p.NPL == 2) prefetch_tmap(&p.a_map[1][1]); }
+    if (NPL == 2) { prefetch_tmap(&p.a_map[0][1]); prefetch_tmap(&p.w_map[1]); }
+    if (p.chunks1 > 0) { prefetch_tmap(&p.a_map[1][0]); if (NPL == 2) prefetch_tmap(&p.a_map[1][1]); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    mbar_init(bar_tmem_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }   // 4 epilogue warps release a buffer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -170,14 +179,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 
   const int chunks = p.chunks0 + p.chunks1;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int m_first = blockIdx.x * p.MT;
-  const int n0 = blockIdx.y * p.BN;
+  const uint32_t acc_cols = (uint32_t)(MT * p.KS * p.BN);
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
+      for (int work = blockIdx.x; work < p.num_work; work += gridDim.x) {
+      const int m_first = (work / p.n_tiles) * MT;
+      const int n0 = (work % p.n_tiles) * p.BN;
       int tn[2], ty0[2], tx0[2];
-      for (int mt = 0; mt < p.MT; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         const int m = m_first + mt;
         if (m < p.m_tiles) {
           const int n = m / tiles_per_img, rem = m - n * tiles_per_img;
@@ -185,7 +197,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           tn[mt] = n; ty0[mt] = ty * p.BH; tx0[mt] = tx * p.BW;
         } else { tn[mt] = p.N; ty0[mt] = 0; tx0[mt] = 0; }       // out-of-range tile: TMA zero-fills
       }
-      int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
       for (int r = 0; r < p.R; ++r)
         for (int ch = 0; ch < chunks; ++ch) {
           const int src = ch < p.chunks0 ? 0 : 1;
@@ -193,28 +204,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           for (int s = 0; s < p.S; ++s) {
             if (!p.strip || s == 0) {
               mbar_wait(a_empty(ai), aph ^ 1u);
-              mbar_expect_tx(a_full(ai), (uint32_t)(p.MT * p.NPL) * p.a_tx_bytes);
+              mbar_expect_tx(a_full(ai), (uint32_t)(MT * NPL) * p.a_tx_bytes);
               const uint32_t abase = a_ring + (uint32_t)ai * a_slot;
-              for (int mt = 0; mt < p.MT; ++mt)
-                for (int pl = 0; pl < p.NPL; ++pl)
-                  tma_load_4d(abase + (uint32_t)(mt * p.NPL + pl) * a_tile, &p.a_map[src][pl], c,
+              for (int mt = 0; mt < MT; ++mt)
+                for (int pl = 0; pl < NPL; ++pl)
+                  tma_load_4d(abase + (uint32_t)(mt * NPL + pl) * a_tile, &p.a_map[src][pl], c,
                               tx0[mt] * p.stride + (p.strip ? 0 : s) - p.pad, ty0[mt] * p.stride + r - p.pad, tn[mt], a_full(ai));
               if (++ai == p.NA) { ai = 0; aph ^= 1u; }
             }
             mbar_wait(w_empty(wi), wph ^ 1u);
             mbar_expect_tx(w_full(wi), w_slot);
             const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
-            for (int pl = 0; pl < p.NPL; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
+            for (int pl = 0; pl < NPL; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
             if (++wi == p.NW) { wi = 0; wph ^= 1u; }
           }
         }
+      }   // work loop
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
       int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
-      uint32_t first = 0;
+      int it = 0;
+      for (int work = blockIdx.x; work < p.num_work; work += gridDim.x, ++it) {
+      const int acc = p.acc_stages == 2 ? (it & 1) : 0;
+      const uint32_t acc_phase = p.acc_stages == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+      mbar_wait(tmem_empty(acc), acc_phase ^ 1u);      // the epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t acc_base = tmem_base + (uint32_t)acc * acc_cols;
+      // The single issuing thread is the critical resource: keep the per-MMA instruction count minimal (descriptor
+      // constants hoisted, everything unrolled at compile time).
+      uint32_t cnt = 0;                                  // MMAs issued per pixel tile of this work item
+      const uint32_t ks_mask = (uint32_t)p.KS - 1u;      // KS is a power of two
+      const uint32_t bn = (uint32_t)p.BN;
       for (int r = 0; r < p.R; ++r)
         for (int ch = 0; ch < chunks; ++ch)
           for (int s = 0; s < p.S; ++s) {
@@ -223,19 +246,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             tc_fence_after();
             const uint32_t abase = a_ring + (uint32_t)ai * a_slot + (p.strip ? (uint32_t)s * 128u : 0u);
             const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
-            for (int mt = 0; mt < p.MT; ++mt) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)(mt * p.BN);
-              for (int ps = 0; ps < p.passes; ++ps) {
-                const int apl = ps == 1 ? 1 : 0, wpl = ps == 2 ? 1 : 0;      // hi*hi, lo*hi, hi*lo
-                const uint32_t a_addr = abase + (uint32_t)(mt * p.NPL + apl) * a_tile;
-                const uint32_t b_addr = wbase + (uint32_t)wpl * w_tile;
+            uint64_t adesc[MT][NPL], bdesc[NPL];
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)
-                  umma_f16(d_tmem, umma_desc_a(a_addr + k * 32, p.base_offset_mode), umma_desc(b_addr + k * 32), idesc,
-                           (first | (uint32_t)ps | (uint32_t)k) != 0 ? 1u : 0u);
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int pl = 0; pl < NPL; ++pl) adesc[mt][pl] = umma_desc(abase + (uint32_t)(mt * NPL + pl) * a_tile);
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) bdesc[pl] = umma_desc(wbase + (uint32_t)pl * w_tile);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+#pragma unroll
+              for (int ps = 0; ps < PASSES; ++ps) {
+                constexpr int kAPl[3] = {0, 1, 0}, kWPl[3] = {0, 0, 1};     // hi*hi, lo*hi, hi*lo
+                const uint32_t chain = cnt & ks_mask;
+                const uint32_t accum = cnt > ks_mask ? 1u : 0u;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)                              // innermost: consecutive MMAs hit different accumulators
+                  umma_f16(acc_base + ((uint32_t)mt * (uint32_t)p.KS + chain) * bn, adesc[mt][kAPl[ps] % NPL] + (uint64_t)(2 * k),
+                           bdesc[kWPl[ps] % NPL] + (uint64_t)(2 * k), idesc, accum);
+                ++cnt;
               }
             }
-            first = 1;
             umma_commit(w_empty(wi));           // frees the weight slot once these MMAs have read it
             if (++wi == p.NW) { wi = 0; wph ^= 1u; }
             if (!p.strip || s == p.S - 1) {
@@ -243,16 +274,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               if (++ai == p.NA) { ai = 0; aph ^= 1u; }
             }
           }
-      umma_commit(bar_tmem_full);
+      umma_commit(tmem_full(acc));
+      }   // work loop
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    mbar_wait(bar_tmem_full, 0);
-    tc_fence_after();
     const int HW = p.H * p.W;
-    for (int mt = 0; mt < p.MT; ++mt) {
+    int it = 0;
+    for (int work = blockIdx.x; work < p.num_work; work += gridDim.x, ++it) {
+    const int m_first = (work / p.n_tiles) * MT;
+    const int n0 = (work % p.n_tiles) * p.BN;
+    const int acc = p.acc_stages == 2 ? (it & 1) : 0;
+    const uint32_t acc_phase = p.acc_stages == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+    mbar_wait(tmem_full(acc), acc_phase);
+    tc_fence_after();
+    const uint32_t acc_base = tmem_base + (uint32_t)acc * acc_cols;
+    for (int mt = 0; mt < MT; ++mt) {
       const int m = m_first + mt;
       if (m >= p.m_tiles) break;
       const int n = m / tiles_per_img, rem = m - n * tiles_per_img;
@@ -263,12 +302,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const bool keep = valid && (p.mask == nullptr || p.mask[pix] != 0);
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t raw[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.BN + c0), raw);
+        float v[16];
+        tmem_ld16(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.KS * p.BN + c0), raw);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        for (int ks = 1; ks < p.KS; ++ks) {
+          tmem_ld16(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((mt * p.KS + ks) * p.BN + c0), raw);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(raw[j]);
+        }
         const int co0 = n0 + c0;
         if (!valid || co0 >= p.Cout) continue;
-        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * p.inv_scale;
+        for (int j = 0; j < 16; ++j) v[j] *= p.inv_scale;
         if (co0 + 16 <= p.Cout) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -335,6 +381,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
       }
     }
+    // this warp has read its quadrant of the accumulator buffer: hand it back to the MMA issuer
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
+    }   // work loop
   }
   tc_fence_before();
   __syncthreads();
@@ -350,6 +401,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_tc_state = 0;   // 0 unknown, 1 ok, -1 unavailable
+static int g_num_sms = 148;
 static char g_tc_msg[256] = "not initialised";
 
 static void tc_init() {
@@ -360,6 +412,7 @@ static void tc_init() {
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
     g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "no CUDA device"); return;
   }
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (major != 10) { g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "compute capability %d.x is not sm_100", major); return; }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -368,7 +421,10 @@ static void tc_init() {
     g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "cuTensorMapEncodeTiled not found in the driver"); return;
   }
   g_encode = (EncodeTiledFn)fn;
-  if (cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess) {
+  if (cudaFuncSetAttribute(tc_conv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(tc_conv_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(tc_conv_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(tc_conv_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess) {
     g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
     return;
   }
@@ -468,12 +524,16 @@ int tc_conv_prepare(TcConvOp* op) {
   p.tiles_x = ceil_div(op->W, p.BW); p.tiles_y = ceil_div(op->H, p.BH);
   p.m_tiles = p.tiles_x * p.tiles_y * op->N;
   p.passes = op->passes; p.NPL = op->passes == 3 ? 2 : 1;
-  int mt = (op->passes == 1 && 2 * p.BN <= 512) ? 2 : 1;
+  // TMEM budget: acc_stages x MT x BN fp32 columns <= 512.  Two accumulator buffers let the epilogue of one tile overlap
+  // the MMAs of the next; MT = 2 (two pixel tiles share each weight tile) only where that still fits.
+  p.acc_stages = env_int("KG_TC_ACC", 2) >= 2 ? 2 : 1;
+  int mt = (op->passes == 1 && p.acc_stages * 2 * p.BN <= 512) ? 2 : 1;
   mt = env_int("KG_TC_MT", mt);
   if (mt < 1) mt = 1;
   if (mt > 2) mt = 2;
-  if (mt * p.BN > 512) mt = 1;
+  if (p.acc_stages * mt * p.BN > 512) mt = 1;
   p.MT = mt;
+  p.KS = 1;
   // strip mode: tile = one 128-pixel image row, the S taps of a filter row share one (128 + S - 1)-pixel strip
   const bool strip = op->stride == 1 && op->S > 1 && p.BW == TC_BM && env_int("KG_TC_STRIP", 1) != 0;
   p.strip = strip ? 1 : 0;
@@ -507,9 +567,23 @@ int tc_conv_prepare(TcConvOp* op) {
   const int cap = env_int("KG_TC_STAGES", 0);
   if (cap > 0) { if (na > cap) na = cap; if (nw > cap) nw = cap; }
   p.NA = na; p.NW = nw;
+  {
+    int ks = 512 / (p.acc_stages * p.MT * p.BN);
+    const int want = p.BN <= 64 ? 4 / p.MT : (p.BN <= 128 ? 2 : 1);     // target ~4 independent chains when N is small
+    if (ks > want) ks = want;
+    const int ks_env = env_int("KG_TC_KS", 0);
+    if (ks_env > 0 && ks_env < ks) ks = ks_env;
+    if (ks < 1) ks = 1;
+    const int total_mmas = op->R * op->S * (p.chunks0 + p.chunks1) * 4 * p.passes;
+    while (ks > 1 && total_mmas < ks) --ks;                               // every chain must receive at least one MMA
+    if (ks == 3) ks = 2;                                                  // power of two (chain = counter & (KS - 1))
+    p.KS = ks;
+  }
   unsigned cols = 32;
-  while (cols < (unsigned)(p.MT * p.BN)) cols *= 2;
+  while (cols < (unsigned)(p.acc_stages * p.MT * p.KS * p.BN)) cols *= 2;
   p.tmem_cols = cols;
+  p.n_tiles = op->w->cout_pad / p.BN;
+  p.num_work = ceil_div(p.m_tiles, p.MT) * p.n_tiles;
   p.bias = op->bias; p.inv_scale = op->w->inv_scale;
   p.out_hi = op->out_hi; p.out_lo = op->out_lo; p.res_hi = op->res_hi; p.res_lo = op->res_lo;
   p.relu = op->relu; p.sigmoid = op->sigmoid; p.mask = op->mask;
@@ -522,9 +596,10 @@ int tc_conv_prepare(TcConvOp* op) {
   }
   KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.BN));
   if (p.NPL == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN));
-  op->grid_x = (unsigned)ceil_div(p.m_tiles, p.MT);
-  op->grid_y = (unsigned)(op->w->cout_pad / p.BN);
-  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 64 + 1024);
+  const int persist = env_int("KG_TC_CTAS", g_num_sms);
+  op->grid_x = (unsigned)std::min(p.num_work, std::max(1, persist));
+  op->grid_y = 1;
+  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024);
   KG_REQUIRE(op->smem_bytes <= (unsigned)TC_MAX_SMEM, "tc_conv_prepare: smem %u > %d", op->smem_bytes, TC_MAX_SMEM);
   op->params = sp;
   return KG_OK;
@@ -535,7 +610,10 @@ int tc_conv_launch(const TcConvOp* op, float* out32, cudaStream_t stream) {
   TcParams p = *reinterpret_cast<const TcParams*>(op->params.get());
   p.out32 = out32;
   dim3 grid(op->grid_x, op->grid_y, 1);
-  tc_conv_kernel<<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
+  if (p.MT == 1 && p.passes == 1) tc_conv_kernel<1, 1><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
+  else if (p.MT == 2 && p.passes == 1) tc_conv_kernel<2, 1><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
+  else if (p.MT == 1 && p.passes == 3) tc_conv_kernel<1, 3><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
+  else tc_conv_kernel<2, 3><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;
 }
