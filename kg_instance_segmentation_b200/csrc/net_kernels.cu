@@ -208,15 +208,28 @@ int launch_stem_conv(const float* x, const float* w, const float* bias, __half* 
 
 // ------------------------------------------------------------------------------------------------
 // F.interpolate(mode='bilinear', align_corners=False) to an explicit size (KGnet.py:110,288-297), fp32 math.
+__device__ __forceinline__ void ld8_split(const __half* hi, const __half* lo, long long i, float* v) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + i));
+  const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(ah[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+  if (lo != nullptr) {
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(lo + i));
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(bh[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+  }
+}
+
 __global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                                                        int in_ps, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                        int out_ps, int C, const ResizeProb* __restrict__ probs) {
   const ResizeProb pb = probs[blockIdx.z];
-  const int cg = C >> 2;   // channel quads
+  const int cg = C >> 3;   // channel octets: one 16-byte load per plane per corner
   const long long total = (long long)pb.Hout * pb.Wout * cg;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
-  const int c = (int)(e % cg) * 4;
+  const int c = (int)(e % cg) * 8;
   const int q = (int)(e / cg);
   const int oy = q / pb.Wout, ox = q - oy * pb.Wout;
   const float rh = (float)pb.Hin / (float)pb.Hout, rw = (float)pb.Win / (float)pb.Wout;
@@ -228,20 +241,35 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict_
   const long long b00 = pb.in_off + (long long)y0 * pb.in_pitch + (long long)x0 * in_ps + c;
   const long long b01 = b00 + (long long)xp * in_ps, b10 = b00 + (long long)yp * pb.in_pitch, b11 = b10 + (long long)xp * in_ps;
   const long long o = pb.out_off + (long long)oy * pb.out_pitch + (long long)ox * out_ps + c;
+  float v00[8], v01[8], v10[8], v11[8];
+  ld8_split(in_hi, in_lo, b00, v00); ld8_split(in_hi, in_lo, b01, v01);
+  ld8_split(in_hi, in_lo, b10, v10); ld8_split(in_hi, in_lo, b11, v11);
+  uint4 h4, l4;
+  __half2* hh = reinterpret_cast<__half2*>(&h4);
+  __half2* ll = reinterpret_cast<__half2*>(&l4);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float v00 = ld_split(in_hi, in_lo, b00 + j), v01 = ld_split(in_hi, in_lo, b01 + j);
-    const float v10 = ld_split(in_hi, in_lo, b10 + j), v11 = ld_split(in_hi, in_lo, b11 + j);
-    const float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-    st_split(out_hi, out_lo, o + j, v);
+    float r[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int k = 2 * j + t;
+      const float v = ly0 * (lx0 * v00[k] + lx1 * v01[k]) + ly1 * (lx0 * v10[k] + lx1 * v11[k]);
+      r[t] = fminf(fmaxf(v, -65504.f), 65504.f);
+    }
+    const __half2 h = __floats2half2_rn(r[0], r[1]);
+    const float2 hf = __half22float2(h);
+    hh[j] = h;
+    ll[j] = __floats2half2_rn(r[0] - hf.x, r[1] - hf.y);
   }
+  *reinterpret_cast<uint4*>(out_hi + o) = h4;
+  if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + o) = l4;
 }
 
 int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
                     const ResizeProb* probs, int nprob, int max_pix, cudaStream_t s) {
   if (nprob <= 0 || max_pix <= 0) return KG_OK;
-  KG_REQUIRE((C & 3) == 0, "bilinear: C=%d must be a multiple of 4", C);
-  dim3 grid((unsigned)(((long long)max_pix * (C >> 2) + 255) / 256), 1, nprob);
+  KG_REQUIRE((C & 7) == 0 && (in_ps & 7) == 0 && (out_ps & 7) == 0, "bilinear: channel counts must be multiples of 8 (C=%d)", C);
+  dim3 grid((unsigned)(((long long)max_pix * (C >> 3) + 255) / 256), 1, nprob);
   bilinear_kernel<<<grid, 256, 0, s>>>(in_hi, in_lo, in_ps, out_hi, out_lo, out_ps, C, probs);
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;

@@ -90,6 +90,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -182,8 +192,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const uint32_t acc_cols = (uint32_t)(MT * p.KS * p.BN);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
+    {
+      // ===== TMA producer: converged warp, one elected lane issues =====
+      const bool leader = elect_one();
       int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
       for (int work = blockIdx.x; work < p.num_work; work += gridDim.x) {
       const int m_first = (work / p.n_tiles) * MT;
@@ -204,26 +215,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           for (int s = 0; s < p.S; ++s) {
             if (!p.strip || s == 0) {
               mbar_wait(a_empty(ai), aph ^ 1u);
-              mbar_expect_tx(a_full(ai), (uint32_t)(MT * NPL) * p.a_tx_bytes);
-              const uint32_t abase = a_ring + (uint32_t)ai * a_slot;
-              for (int mt = 0; mt < MT; ++mt)
-                for (int pl = 0; pl < NPL; ++pl)
-                  tma_load_4d(abase + (uint32_t)(mt * NPL + pl) * a_tile, &p.a_map[src][pl], c,
-                              tx0[mt] * p.stride + (p.strip ? 0 : s) - p.pad, ty0[mt] * p.stride + r - p.pad, tn[mt], a_full(ai));
+              if (leader) {
+                mbar_expect_tx(a_full(ai), (uint32_t)(MT * NPL) * p.a_tx_bytes);
+                const uint32_t abase = a_ring + (uint32_t)ai * a_slot;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                  for (int pl = 0; pl < NPL; ++pl)
+                    tma_load_4d(abase + (uint32_t)(mt * NPL + pl) * a_tile, &p.a_map[src][pl], c,
+                                tx0[mt] * p.stride + (p.strip ? 0 : s) - p.pad, ty0[mt] * p.stride + r - p.pad, tn[mt], a_full(ai));
+              }
+              __syncwarp();
               if (++ai == p.NA) { ai = 0; aph ^= 1u; }
             }
             mbar_wait(w_empty(wi), wph ^ 1u);
-            mbar_expect_tx(w_full(wi), w_slot);
-            const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
-            for (int pl = 0; pl < NPL; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
+            if (leader) {
+              mbar_expect_tx(w_full(wi), w_slot);
+              const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
+#pragma unroll
+              for (int pl = 0; pl < NPL; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
+            }
+            __syncwarp();
             if (++wi == p.NW) { wi = 0; wph ^= 1u; }
           }
         }
       }   // work loop
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer: the whole warp walks the loop (converged), one elected lane issues =====
+      const bool leader = elect_one();
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
       int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
       int it = 0;
@@ -253,6 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               for (int pl = 0; pl < NPL; ++pl) adesc[mt][pl] = umma_desc(abase + (uint32_t)(mt * NPL + pl) * a_tile);
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl) bdesc[pl] = umma_desc(wbase + (uint32_t)pl * w_tile);
+            if (leader) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
 #pragma unroll
@@ -268,13 +290,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               }
             }
             umma_commit(w_empty(wi));           // frees the weight slot once these MMAs have read it
+            if (!p.strip || s == p.S - 1) umma_commit(a_empty(ai));
+            }
+            __syncwarp();
             if (++wi == p.NW) { wi = 0; wph ^= 1u; }
             if (!p.strip || s == p.S - 1) {
-              umma_commit(a_empty(ai));
               if (++ai == p.NA) { ai = 0; aph ^= 1u; }
             }
           }
-      umma_commit(tmem_full(acc));
+      if (leader) umma_commit(tmem_full(acc));
+      __syncwarp();
       }   // work loop
     }
   } else {
