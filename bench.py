@@ -205,7 +205,7 @@ STAGE_NAMES = {0: "vote", 1: "blur_peak", 2: "group", 3: "nms", 8: "conv_cuda_co
 def run_pipeline(args, rank, world, dist):
     import ctypes as C
     import torch
-    from kg_instance_segmentation_b200 import _cabi, synthetic
+    from kg_instance_segmentation_b200 import _cabi, parallel, synthetic
     from kg_instance_segmentation_b200.inference import InstanceHeat
     dev = torch.device("cuda", torch.cuda.current_device())
     sd = synthetic.make_state_dict(seed=0)
@@ -220,24 +220,21 @@ def run_pipeline(args, rank, world, dist):
     forced = [tuple(torch.from_numpy(a).to(dev) for a in h) for h in host] if not args.free_running else None
     det_host = torch.empty(BS, MAX_DETS, 5, dtype=torch.float64).pin_memory()
     mask_host = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
-    gathered = torch.empty(world * BS, MAX_DETS, 5, dtype=torch.float64, device=dev) if world > 1 else None
-    gathered_cnt = torch.empty(world * BS, dtype=torch.int32, device=dev) if world > 1 else None
     state = {}
 
     def gather(res):
-        if world > 1:   # the single collective of the path: all-gather of the padded final detection list
-            dist.all_gather_into_tensor(gathered, res.dets[:, :MAX_DETS].contiguous())
-            dist.all_gather_into_tensor(gathered_cnt, res.det_count)
+        if world > 1:   # the single collective of the path: all-gather of the padded final detection list (NCCL)
+            state["gathered"] = parallel.all_gather_detections(res.dets[:, :MAX_DETS].contiguous(), res.det_count, BS)
 
     def step_device():
-        dets, seg = engine.detect_batch(x_dev, head_override=forced)
+        dets, seg = engine.detect_batch(x_dev, head_override=forced, packed=True)
         gather(engine.last_result)
         state["dets"] = dets
         return dets
 
     def step_e2e():
         x_stage.copy_(x_host, non_blocking=True)                            # H2D of the step's input from pinned memory
-        dets, seg = engine.detect_batch(x_stage, head_override=forced)
+        dets, seg = engine.detect_batch(x_stage, head_override=forced, packed=True)
         gather(engine.last_result)
         det_host.copy_(engine.last_result.dets[:, :MAX_DETS], non_blocking=True)
         m = engine.model.last_masks

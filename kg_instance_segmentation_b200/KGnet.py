@@ -230,6 +230,12 @@ class ResNet(nn.Module):
         """feat_seg: the list returned by forward_dec (any list of 5 fp32 NCHW CUDA tensors works too);
         bboxes: per image an (M,5) array [y1,x1,y2,x2,score] or an empty list.
         Returns [mask_patches, mask_dets] with the reference's nesting."""
+        return self.forward_seg_packed(feat_seg, bboxes).as_lists()
+
+    def forward_seg_packed(self, feat_seg, bboxes):
+        """Same computation as forward_seg, but returns a SegResult: all mask patches in ONE device buffer plus their
+        geometry, without creating a Python tensor object per box (the reference-style nested lists are built on demand
+        by SegResult.as_lists())."""
         nimg = len(bboxes)
         L = _cabi.lib()
         internal = (isinstance(feat_seg, _FeatList) and self._last is not None and feat_seg.owner_key == self._last[0] and
@@ -265,10 +271,11 @@ class ResNet(nn.Module):
             counts[i] = len(b)
             rows.append(b)
         total = int(counts.sum())
-        mask_patches = [[] for _ in range(nimg)]
-        mask_dets = [[] for _ in range(nimg)]
         if total == 0:
-            return [mask_patches, mask_dets]
+            self.last_launches = 0
+            self.last_masks = torch.empty(0, dtype=torch.float32, device=device)
+            return SegResult(nimg, counts, np.zeros((0, 5)), self.last_masks, np.zeros(0, np.int32), np.zeros((0, 2), np.int32),
+                             np.zeros(0, np.int64), np.zeros(0, np.int32))
         boxes = np.ascontiguousarray(np.concatenate(rows, 0))
         seg_bytes, mask_floats, n_masks = C.c_size_t(0), C.c_longlong(0), C.c_int(0)
         mask_index = np.zeros(total, np.int32); mask_hw = np.zeros((total, 2), np.int32); mask_off = np.zeros(total, np.int64)
@@ -285,23 +292,43 @@ class ResNet(nn.Module):
                                              masks.data_ptr(), torch.cuda.current_stream().cuda_stream, C.byref(nl)))
         self.last_launches = nl.value
         self.last_masks = masks
-        k = 0
-        for i in range(nimg):
-            for j in range(counts[i]):
-                slot = mask_index[k]
-                if slot >= 0:
-                    h, w = mask_hw[slot]
-                    o = int(mask_off[slot])
-                    mask_patches[i].append(torch.as_strided(masks, (int(h), int(w)), (int(mask_pitch[slot]), 1), o))
-                    mask_dets[i].append(torch.Tensor(np.append(boxes[k, :4], boxes[k, 4])))
-                k += 1
-        return [mask_patches, mask_dets]
+        return SegResult(nimg, counts, boxes, masks, mask_index, mask_hw, mask_off, mask_pitch)
 
     # ---- KGnet.py:269-272 -----------------------------------------------------------------------
     def forward(self, x, bboxes):
         dec0, dec1, dec2, dec3, feat_seg = self.forward_dec(x)
         seg = self.forward_seg(feat_seg, bboxes)
         return dec0, dec1, dec2, dec3, seg
+
+
+class SegResult:
+    """Packed output of forward_seg: `masks` is one fp32 device buffer; patch k of the concatenated box list lives at
+    masks[off[slot] + y * pitch[slot] + x] for slot = index[k] >= 0 (index -1: the box was skipped, KGnet.py:341-342)."""
+
+    def __init__(self, nimg, counts, boxes, masks, index, hw, off, pitch):
+        self.nimg, self.counts, self.boxes, self.masks = nimg, counts, boxes, masks
+        self.index, self.hw, self.off, self.pitch = index, hw, off, pitch
+
+    def patch(self, k):
+        slot = int(self.index[k])
+        if slot < 0:
+            return None
+        h, w = int(self.hw[slot, 0]), int(self.hw[slot, 1])
+        return torch.as_strided(self.masks, (h, w), (int(self.pitch[slot]), 1), int(self.off[slot]))
+
+    def as_lists(self):
+        """[mask_patches, mask_dets] nested like the reference's forward_seg return value (KGnet.py:346-350)."""
+        mask_patches = [[] for _ in range(self.nimg)]
+        mask_dets = [[] for _ in range(self.nimg)]
+        k = 0
+        for i in range(self.nimg):
+            for _ in range(int(self.counts[i])):
+                pt = self.patch(k)
+                if pt is not None:
+                    mask_patches[i].append(pt)
+                    mask_dets[i].append(torch.Tensor(np.append(self.boxes[k, :4], self.boxes[k, 4])))
+                k += 1
+        return [mask_patches, mask_dets]
 
 
 class _FeatList(list):

@@ -33,10 +33,11 @@ class InstanceHeat:
                                                              max_boxes=max_boxes, device=self.device)
         return d
 
-    def detect_batch(self, x, nms_thresh=0.5, with_masks=True, head_override=None, max_peaks=4096, max_boxes=4096):
+    def detect_batch(self, x, nms_thresh=0.5, with_masks=True, head_override=None, max_peaks=4096, max_boxes=4096, packed=False):
         """x: [N,3,H,W] fp32 CUDA tensor in the reference's input convention (BGR/255 - 0.5, test.py:92).
         Returns (detections, seg): detections[i] = (M_i,5) float64 array or None (nms.py convention);
-        seg = [mask_patches, mask_dets] of forward_seg (None when with_masks is False).
+        seg = [mask_patches, mask_dets] of forward_seg, or the packed KGnet.SegResult when packed=True (None when
+        with_masks is False).
         head_override: optional per-scale (kp, short, mid) CUDA tensors decoded INSTEAD of the network's own head
         outputs (teacher-forced decode load for benchmarking; the network still computes all of its heads)."""
         model = self.model
@@ -56,7 +57,9 @@ class InstanceHeat:
         self.last_result = res
         seg = None
         if with_masks:
-            seg = model.forward_seg(out[4], [d if d is not None else [] for d in dets])
+            seg = model.forward_seg_packed(out[4], [d if d is not None else [] for d in dets])
+            if not packed:
+                seg = seg.as_lists()
             launches += model.last_launches
         self.last_launches = launches
         return dets, seg
