@@ -174,6 +174,12 @@ int kg_net_forward_seg(kg_net* net, void* d_dec_workspace, void* d_seg_workspace
 int kg_conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R,
                    int S, int stride, int pad, int relu, const float* d_res, int mode, float* d_y, void* stream);
 
+/* The three second-layer head convs of one scale (KGnet.py:161-209: 7x7, Cin -> 5 (sigmoid) / 10 / 40) through the
+ * row-GEMM + shift-add tcgen05 kernel, on an fp32 NCHW device input with 3*Cin channels (head h reads channels
+ * [h*Cin, (h+1)*Cin)); h_w[h] = host [Cout_h, Cin, 7, 7], d_y[h] = device [N, Cout_h, H, W].  Unit-test entry. */
+int kg_heads_l2_nchw(const float* d_x, int N, int Cin, int H, int W, const float* const* h_w, const float* const* h_bias,
+                     float* const* d_y, void* stream);
+
 /* Work census of the current forward_dec plan: out[0]/out[1] = algorithmic FLOPs (2*MACs, real channel counts, one
  * pass) of the tensor-core / CUDA-core convs, out[2]/out[3] = their launch counts, out[4..7] = tensor-core FLOPs
  * of the backbone, decoder, first-layer heads, second-layer heads.  n >= 8. */

@@ -18,7 +18,7 @@ STAMP = os.path.join(LIB_DIR, "libkgnet_b200.stamp")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "--threads", "0"]
 # per-file extra flags: the decode path reproduces the reference's fp64 operation order, so no FMA contraction
-PER_FILE = {"decode.cu": ["-fmad=false"]}
+PER_FILE = {"decode.cu": ["-fmad=false"], "tc_shift.cu": ["--expt-relaxed-constexpr"]}
 
 
 def sources():

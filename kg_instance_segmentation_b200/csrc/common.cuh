@@ -57,7 +57,7 @@ struct Arena {
 
 // ---- optional per-stage device timing (kg_timing_enable / kg_timing_collect) ---------------------
 // Stage ids: 0 vote, 1 blur+peak, 2 sort+group+boxes, 3 nms, 8.. network stages (see net.cu).
-constexpr int KG_MAX_STAGES = 64;
+constexpr int KG_MAX_STAGES = 256;
 bool timing_enabled();
 void stage_begin(int id, cudaStream_t s);
 void stage_end(int id, cudaStream_t s);

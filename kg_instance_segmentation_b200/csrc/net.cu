@@ -3,6 +3,7 @@
 // net_kernels.cu (CUDA cores) and tc_conv.cu (tcgen05 tensor cores).
 #include "net.cuh"
 #include "tc_conv.cuh"
+#include "tc_shift.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -34,7 +35,7 @@ struct Tensor {
   int H = 0, W = 0, C = 0;
 };
 
-enum OpType { OP_CONV, OP_BILINEAR, OP_MAXPOOL, OP_EXPORT };
+enum OpType { OP_CONV, OP_BILINEAR, OP_MAXPOOL, OP_EXPORT, OP_HEADS2 };
 
 struct Op {
   OpType type = OP_CONV;
@@ -50,7 +51,8 @@ struct Op {
   int Hout = 0, Wout = 0;
   int stage = ST_BACKBONE;
   int tc_passes = 0;                             // 0: CUDA-core kernel; 1 or 3: tensor-core kernel passes
-  int tc_index = -1;                             // index into Plan::tc_ops
+  int tc_index = -1;                             // index into Plan::tc_ops (OP_CONV) / Plan::shift_ops (OP_HEADS2)
+  int head_scale = -1;                           // OP_HEADS2: the three second-layer head convs of this scale in one launch
 };
 
 struct Plan {
@@ -62,6 +64,7 @@ struct Plan {
   ConvProb* d_conv_probs = nullptr;
   ResizeProb* d_resize_probs = nullptr;
   std::vector<TcConvOp> tc_ops;
+  std::vector<TcShiftOp> shift_ops;
   const void* tc_workspace = nullptr;            // workspace base the tensor maps were encoded for
   size_t bytes = 0;
   int feat_ids[5] = {-1, -1, -1, -1, -1};
@@ -353,6 +356,14 @@ static int build_plan(Net* net, int N, int H, int W, int precision) {
     const int C = kHeadC[s];
     int h1 = b.conv("heads_l1_c" + std::to_string(s), cats[s], -1, 1, 3, true, ST_HEAD1, -1, -1, false, 0, false, 0, 0, true,
                     !fast_heads);
+    const int outs[3] = {kHeadOut[0], kHeadOut[1], kHeadOut[2]};
+    if (fast_heads && tc_shift_supported(T(h1).H, T(h1).W, 7, 7, 3, C, 3, outs)) {
+      // the three second-layer head convs of this scale as ONE row-GEMM + shift-add launch (tc_shift.cu)
+      Op op; op.type = OP_HEADS2; op.in0 = h1; op.head_scale = s; op.stage = ST_HEAD2; op.C0 = C;
+      op.Hout = T(h1).H; op.Wout = T(h1).W; op.tc_passes = 1;
+      p->ops.push_back(op);
+      continue;
+    }
     for (int h = 0; h < 3; ++h) {
       const std::string nme = std::string(kHeadNames[h]) + "_c" + std::to_string(s) + ".2";
       b.conv(nme, h1, -1, 1, 3, false, ST_HEAD2, -1, 3 * s + h, h == 0, h * C, false, 0, 0, false);
@@ -399,7 +410,22 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
   if (p->tc_workspace != ws) {
     // (re-)encode the TMA descriptors of every tensor-core op for this workspace base
     p->tc_ops.clear();
+    p->shift_ops.clear();
     for (auto& op : p->ops) {
+      if (op.type == OP_HEADS2) {
+        const Tensor& t0 = p->tensors[op.in0];
+        TcShiftOp t{};
+        t.N = p->N; t.H = t0.H; t.W = t0.W; t.R = 7; t.S = 7; t.pad = 3; t.Cin = op.C0; t.in_hi = P.hi(t0); t.in_C = t0.C; t.n_groups = 3;
+        for (int h = 0; h < 3; ++h) {
+          const ConvW& w = net->convs.at(std::string(kHeadNames[h]) + "_c" + std::to_string(op.head_scale) + ".2");
+          t.g[h].h_w = w.h_w.data(); t.g[h].d_bias = w.d_b; t.g[h].n_out = w.Cout; t.g[h].in_coff = h * op.C0; t.g[h].sigmoid = h == 0;
+        }
+        if (getenv("KG_TC_DEBUG")) fprintf(stderr, "[op %d heads_l2_c%d] ", (int)(&op - p->ops.data()), op.head_scale);
+        KG_TRY(tc_shift_prepare(&t));
+        op.tc_index = (int)p->shift_ops.size();
+        p->shift_ops.push_back(t);
+        continue;
+      }
       if (op.type != OP_CONV || op.tc_passes == 0) continue;
       const Tensor& t0 = p->tensors[op.in0];
       TcConvOp t{};
@@ -412,18 +438,23 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
       if (op.out >= 0) { const Tensor& to = p->tensors[op.out]; t.out_hi = P.hi(to); t.out_lo = op.out_single ? nullptr : P.lo(to); }
       if (op.res >= 0) { const Tensor& tr = p->tensors[op.res]; t.res_hi = P.hi(tr); t.res_lo = P.lo(tr); }
       t.relu = op.relu; t.sigmoid = op.sigmoid;
+      if (getenv("KG_TC_DEBUG")) fprintf(stderr, "[op %d %s] ", (int)(&op - p->ops.data()), op.w->name.c_str());
       KG_TRY(tc_conv_prepare(&t));
       op.tc_index = (int)p->tc_ops.size();
       p->tc_ops.push_back(t);
     }
     p->tc_workspace = ws;
   }
+  // KG_TIMING_PER_OP=1 (diagnostics): every op of the plan gets its own timing slot 64 + index instead of its stage
+  static const bool per_op = getenv("KG_TIMING_PER_OP") != nullptr;
+  int op_index = -1;
   for (const Op& op : p->ops) {
+    ++op_index;
     if (op.type == OP_EXPORT && !want_feats) continue;
-    StageScope ts(op.stage, stream);
+    StageScope ts(per_op && 64 + op_index < KG_MAX_STAGES ? 64 + op_index : op.stage, stream);
     switch (op.type) {
       case OP_CONV: {
-        if (op.tc_passes == 0) ts.restage(ST_STEM);   // stage 8 collects every CUDA-core conv, 9..12 are tensor-core only
+        if (op.tc_passes == 0 && !per_op) ts.restage(ST_STEM);   // stage 8 collects every CUDA-core conv, 9..12 are tensor-core only
         float* out32 = op.out32_ext >= 0 ? ext[op.out32_ext] : nullptr;
         if (op.tc_passes > 0) {
           KG_TRY(tc_conv_launch(&p->tc_ops[op.tc_index], out32, stream));
@@ -452,6 +483,12 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
         a.out32 = out32;
         a.probs = p->d_conv_probs + op.prob_off;
         KG_TRY(launch_conv_ffma(a, op.nprob, op.max_pix, stream));
+        ++launches;
+        break;
+      }
+      case OP_HEADS2: {
+        float* outs[3] = {ext[3 * op.head_scale], ext[3 * op.head_scale + 1], ext[3 * op.head_scale + 2]};
+        KG_TRY(tc_shift_launch(&p->shift_ops[op.tc_index], outs, stream));
         ++launches;
         break;
       }
@@ -856,7 +893,10 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
   const char* dp = (const char*)net->d_seg_probs;
   int launches = 0;
   StageScope ts(ST_SEG, stream);
-  const int passes = (p->precision == 1 && getenv("KG_SEG_3PASS") == nullptr) ? 1 : 3;
+  // precision "fast": single-pass fp16 only at atlas level 0 (where the time goes); the deep, small levels (K up to 9216)
+  // run split-fp16 3-pass, which keeps the mask error of the 10-layer branch within tolerance at negligible cost.
+  const char* sp1 = getenv("KG_SEG_1PASS_LEVELS");
+  const int one_pass_levels = p->precision == 1 ? (sp1 ? atoi(sp1) : 1) : 0;   // levels [0, one_pass_levels) are single-pass
   size_t mask_total = 0;
   for (int l = 0; l < 5; ++l) mask_total += align_up((size_t)sp.lv[l].HA * sp.lv[l].WA, 256);
   KG_CUDA_CHECK(cudaMemsetAsync(masks, 0, mask_total, stream));
@@ -872,6 +912,7 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
   }
   auto conv = [&](const std::string& wname, const SegPlan::Level& L, size_t in0, int C0, size_t in1, int C1, size_t out, int Cout_t,
                   float* out32, bool relu, bool sig) -> int {
+    const int passes = (&L - &sp.lv[0]) < one_pass_levels ? 1 : 3;
     const ConvW& w = net->convs.at(wname);
     TcConvOp t{};
     t.w = &w.tc; t.bias = w.d_b; t.N = 1; t.H = L.HA; t.W = L.WA; t.R = w.R; t.S = w.S; t.pad = w.R / 2;
@@ -973,6 +1014,39 @@ static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const flo
   return rc;
 }
 
+// Unit-test entry of the row-GEMM + shift-add head kernel (tc_shift.cu): the three second-layer head convs of one scale
+// (7x7, Cin -> 5 / 10 / 40; KGnet.py:161-209) on an fp32 NCHW input with 3*Cin channels (head h reads channels [h*Cin, (h+1)*Cin)).
+static int heads_l2_nchw(const float* d_x, int N, int Cin, int H, int W, const float* const* h_w, const float* const* h_bias,
+                         float* const* d_y, cudaStream_t stream) {
+  KG_REQUIRE(d_x && h_w && h_bias && d_y && N > 0 && Cin > 0, "kg_heads_l2_nchw: bad arguments");
+  const int outs[3] = {kHeadOut[0], kHeadOut[1], kHeadOut[2]};
+  if (!tc_shift_supported(H, W, 7, 7, 3, Cin, 3, outs)) { set_error("kg_heads_l2_nchw: shape not supported by the shift-add kernel"); return KG_ERR_INVALID; }
+  Net tmp;
+  const size_t in_e = (size_t)N * H * W * 3 * Cin;
+  __half* xh = nullptr;
+  int rc = KG_OK;
+  do {
+    if (cudaMalloc(&xh, in_e * 2)) { rc = KG_ERR_CUDA; break; }
+    if ((rc = launch_import_nchw(d_x, xh, nullptr, N, H * W, 3 * Cin, stream)) != KG_OK) break;
+    TcShiftOp t{};
+    t.N = N; t.H = H; t.W = W; t.R = 7; t.S = 7; t.pad = 3; t.Cin = Cin; t.in_hi = xh; t.in_C = 3 * Cin; t.n_groups = 3;
+    for (int h = 0; h < 3; ++h) {
+      const std::string nme = "h" + std::to_string(h);
+      if ((rc = set_conv(&tmp, nme.c_str(), h_w[h], kHeadOut[h], Cin, 7, 7, h_bias[h], nullptr, nullptr, nullptr, nullptr, 0.0)) != KG_OK) break;
+      ConvW& w = tmp.convs.at(nme);
+      if ((rc = upload_conv(w)) != KG_OK) break;
+      t.g[h].h_w = w.h_w.data(); t.g[h].d_bias = w.d_b; t.g[h].n_out = kHeadOut[h]; t.g[h].in_coff = h * Cin; t.g[h].sigmoid = h == 0;
+    }
+    if (rc != KG_OK) break;
+    if ((rc = tc_shift_prepare(&t)) != KG_OK) break;
+    if ((rc = tc_shift_launch(&t, d_y, stream)) != KG_OK) break;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("kg_heads_l2_nchw: %s", cudaGetErrorString(cudaGetLastError())); rc = KG_ERR_CUDA; }
+  } while (0);
+  if (rc == KG_ERR_CUDA && cudaPeekAtLastError() != cudaSuccess) set_error("kg_heads_l2_nchw: CUDA error %s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(xh);
+  return rc;
+}
+
 }  // namespace kg
 
 using namespace kg;
@@ -1052,6 +1126,11 @@ int kg_conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* 
   return conv2d_nchw(d_x, N, Cin, H, W, h_w, h_bias, Cout, R, S, stride, pad, relu, d_res, mode, d_y, (cudaStream_t)stream);
 }
 
+int kg_heads_l2_nchw(const float* d_x, int N, int Cin, int H, int W, const float* const* h_w, const float* const* h_bias, float* const* d_y,
+                     void* stream) {
+  return heads_l2_nchw(d_x, N, Cin, H, W, h_w, h_bias, d_y, (cudaStream_t)stream);
+}
+
 /* out[0] = algorithmic FLOPs (2*MACs, real channel counts, one pass) of the tensor-core convs of the current plan,
  * out[1] = same for the CUDA-core convs, out[2] / out[3] = their launch counts, out[4..7] = tensor-core FLOPs by
  * stage (backbone, decoder, head layer 1, head layer 2). */
@@ -1060,6 +1139,11 @@ int kg_net_plan_info(kg_net* h, double* out, int n) {
   KG_REQUIRE(net && net->plan && out && n >= 8, "kg_net_plan_info: no plan (run forward_dec first)");
   for (int i = 0; i < n; ++i) out[i] = 0.0;
   for (const Op& op : net->plan->ops) {
+    if (op.type == OP_HEADS2) {
+      const double f = 2.0 * net->plan->N * op.Hout * op.Wout * (double)(kHeadOut[0] + kHeadOut[1] + kHeadOut[2]) * op.C0 * 49;
+      out[0] += f; out[2] += 1; out[4 + ST_HEAD2 - ST_BACKBONE] += f;
+      continue;
+    }
     if (op.type != OP_CONV) continue;
     const double f = 2.0 * net->plan->N * op.Hout * op.Wout * (double)op.w->Cout * (op.C0 + op.C1) * op.w->R * op.w->S;
     if (op.tc_passes > 0) { out[0] += f; out[2] += 1; if (op.stage >= ST_BACKBONE && op.stage <= ST_HEAD2) out[4 + op.stage - ST_BACKBONE] += f; }

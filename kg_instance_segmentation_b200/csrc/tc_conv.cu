@@ -16,6 +16,7 @@
 //   roles          warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue (one TMEM lane quadrant each);
 //                  smem full/empty mbarrier ring between producer and MMA, one tmem_full barrier to the epilogue.
 #include "tc_conv.cuh"
+#include "tc_ptx.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -51,94 +52,13 @@ struct TcParams {
   int KS;                           // independent accumulator chains per pixel tile (partials are summed in the epilogue):
                                     // back-to-back MMAs into ONE accumulator serialise on its latency when N is small
   int strip;                        // 1: A slot = (BW + S - 1)-pixel strip shared by the S taps of a filter row
+  int wg;                           // weight tap group: taps per W slot (1, or S: the S taps of a filter row arrive in ONE TMA box
+                                    // behind ONE barrier round trip -- narrow-N layers are bound by those round trips)
   unsigned a_tile_bytes, a_tx_bytes;   // smem bytes reserved per A tile (1024-aligned) / bytes TMA delivers per A tile
   int base_offset_mode;
   int relu, sigmoid;
   unsigned tmem_cols;
 };
-
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major; canonical value 1)
-  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                  // descriptor version
-  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
-  return d;
-}
-// A-operand descriptor whose start address may sit s rows (s * 128 B) inside a 1024-byte swizzle atom (strip mode):
-// the descriptor's base-offset field carries (start >> 7) & 7 so that the hardware applies the same XOR pattern TMA used.
-__device__ __forceinline__ uint64_t umma_desc_a(uint32_t saddr, int base_offset_mode) {
-  uint64_t d = umma_desc(saddr);
-  if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
-  return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ---- the kernel ---------------------------------------------------------------------------------
 // Two independent smem rings: the A ring holds activation tiles, the W ring holds weight tiles.  In "strip" mode
@@ -154,7 +74,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const uint32_t a_tile = p.a_tile_bytes;                             // one plane of one pixel tile (or strip)
   const uint32_t a_slot = (uint32_t)(MT * NPL) * a_tile;
   const uint32_t w_tile = (uint32_t)p.BN * 128u;
-  const uint32_t w_slot = (uint32_t)NPL * w_tile;
+  const uint32_t w_plane = (uint32_t)p.wg * w_tile;                   // one plane of one W slot: wg taps back to back
+  const uint32_t w_slot = (uint32_t)NPL * w_plane;
   const uint32_t a_ring = smem0, w_ring = smem0 + (uint32_t)p.NA * a_slot;
   const uint32_t bars = w_ring + (uint32_t)p.NW * w_slot;
   auto a_full = [&](int s) { return bars + 8u * s; };
@@ -228,15 +149,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               __syncwarp();
               if (++ai == p.NA) { ai = 0; aph ^= 1u; }
             }
-            mbar_wait(w_empty(wi), wph ^ 1u);
-            if (leader) {
-              mbar_expect_tx(w_full(wi), w_slot);
-              const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
+            if (p.wg == 1 || s == 0) {
+              mbar_wait(w_empty(wi), wph ^ 1u);
+              if (leader) {
+                mbar_expect_tx(w_full(wi), w_slot);
+                const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
 #pragma unroll
-              for (int pl = 0; pl < NPL; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_tile, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
+                for (int pl = 0; pl < NPL; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_plane, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
+              }
+              __syncwarp();
+              if (++wi == p.NW) { wi = 0; wph ^= 1u; }
             }
-            __syncwarp();
-            if (++wi == p.NW) { wi = 0; wph ^= 1u; }
           }
         }
       }   // work loop
@@ -263,17 +186,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         for (int ch = 0; ch < chunks; ++ch)
           for (int s = 0; s < p.S; ++s) {
             if (!p.strip || s == 0) mbar_wait(a_full(ai), aph);
-            mbar_wait(w_full(wi), wph);
+            if (p.wg == 1 || s == 0) mbar_wait(w_full(wi), wph);
             tc_fence_after();
             const uint32_t abase = a_ring + (uint32_t)ai * a_slot + (p.strip ? (uint32_t)s * 128u : 0u);
-            const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
+            const uint32_t wbase = w_ring + (uint32_t)wi * w_slot + (p.wg > 1 ? (uint32_t)s * w_tile : 0u);
+            const bool w_last = p.wg == 1 || s == p.S - 1;
             uint64_t adesc[MT][NPL], bdesc[NPL];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
               for (int pl = 0; pl < NPL; ++pl) adesc[mt][pl] = umma_desc(abase + (uint32_t)(mt * NPL + pl) * a_tile);
 #pragma unroll
-            for (int pl = 0; pl < NPL; ++pl) bdesc[pl] = umma_desc(wbase + (uint32_t)pl * w_tile);
+            for (int pl = 0; pl < NPL; ++pl) bdesc[pl] = umma_desc(wbase + (uint32_t)pl * w_plane);
             if (leader) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
@@ -289,11 +213,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 ++cnt;
               }
             }
-            umma_commit(w_empty(wi));           // frees the weight slot once these MMAs have read it
+            if (w_last) umma_commit(w_empty(wi));     // frees the weight slot once these MMAs have read it
             if (!p.strip || s == p.S - 1) umma_commit(a_empty(ai));
             }
             __syncwarp();
-            if (++wi == p.NW) { wi = 0; wph ^= 1u; }
+            if (w_last) { if (++wi == p.NW) { wi = 0; wph ^= 1u; } }
             if (!p.strip || s == p.S - 1) {
               if (++ai == p.NA) { ai = 0; aph ^= 1u; }
             }
@@ -459,6 +383,8 @@ static void tc_init() {
 bool tc_available() { tc_init(); return g_tc_state == 1; }
 bool tc_stride2_enabled() { const char* v = getenv("KG_TC_STRIDE2"); return !(v && v[0] == '0'); }
 const char* tc_status() { tc_init(); return g_tc_msg; }
+void* tc_encode_tiled_fn() { tc_init(); return g_tc_state == 1 ? (void*)g_encode : nullptr; }
+int tc_num_sms() { tc_init(); return g_num_sms; }
 bool tc_layer_supported(int cin, int cout, int R, int S) { return cin % TC_BK == 0 && cout >= 1 && R >= 1 && S >= 1 && R * S <= 64; }
 
 void tc_free_weights(TcWeights& w) {
@@ -510,10 +436,10 @@ static int encode_act_map(CUtensorMap* m, const __half* base, int C, int W, int 
   return KG_OK;
 }
 
-static int encode_w_map(CUtensorMap* m, const __half* base, int cin, int cout_pad, int taps, int BN) {
+static int encode_w_map(CUtensorMap* m, const __half* base, int cin, int cout_pad, int taps, int BN, int wg) {
   cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, (cuuint64_t)taps};
   cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout_pad * cin * 2};
-  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, (cuuint32_t)wg};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -567,14 +493,25 @@ int tc_conv_prepare(TcConvOp* op) {
   p.a_tx_bytes = (unsigned)(strip ? strip_px * 128 : TC_A_TILE);
   p.a_tile_bytes = (unsigned)align_up(p.a_tx_bytes, 1024);
   const size_t budget = TC_MAX_SMEM - 2048;
+  // weight tap group: all S taps of a filter row in one W slot when that slot stays small (narrow-N layers)
+  p.wg = 1;
+  if (op->S > 1 && (size_t)op->S * p.NPL * p.BN * 128 <= (size_t)env_int("KG_TC_WG_MAXKB", 48) * 1024 && env_int("KG_TC_WG", 1) != 0) p.wg = op->S;
   auto fit = [&](int mtv, int* na, int* nw) {
-    const size_t a_slot = (size_t)mtv * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.NPL * p.BN * 128;
-    if (strip) {
-      *na = 2;
-      if (2 * a_slot + 2 * w_slot > budget) return false;
-      *nw = (int)((budget - 2 * a_slot) / w_slot);
+    const size_t a_slot = (size_t)mtv * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.wg * p.NPL * p.BN * 128;
+    if (strip || p.wg > 1) {
+      // A slots and W slots are consumed at different rates (one A strip per filter row / one W group per filter row)
+      *na = strip ? 2 : 4;
+      if ((size_t)*na * a_slot + 2 * w_slot > budget) { *na = 2; if (2 * a_slot + 2 * w_slot > budget) return false; }
+      *nw = (int)((budget - (size_t)*na * a_slot) / w_slot);
       if (*nw > 8) *nw = 8;
-      if (*nw >= 6 && 3 * a_slot + 4 * w_slot <= budget) { *na = 3; *nw = (int)((budget - 3 * a_slot) / w_slot); if (*nw > 8) *nw = 8; }
+      const int na_more = strip ? 3 : 8;
+      if (*nw >= (p.wg > 1 ? 3 : 6)) {
+        // spend spare room on more A slots while keeping >= 3 (grouped) / 4 W slots
+        const int keep_w = p.wg > 1 ? 3 : 4;
+        int na2 = (int)((budget - (size_t)keep_w * w_slot) / a_slot);
+        if (na2 > na_more) na2 = na_more;
+        if (na2 > *na) { *na = na2; *nw = (int)((budget - (size_t)*na * a_slot) / w_slot); if (*nw > 8) *nw = 8; }
+      }
       return *nw >= 2;
     }
     int st = (int)(budget / (a_slot + w_slot));
@@ -584,8 +521,9 @@ int tc_conv_prepare(TcConvOp* op) {
   };
   int na = 0, nw = 0;
   if (!fit(p.MT, &na, &nw) && p.MT == 2) { p.MT = 1; }
+  if (!fit(p.MT, &na, &nw) && p.wg > 1) { p.wg = 1; }
   if (!fit(p.MT, &na, &nw)) {
-    const size_t a_slot = (size_t)p.MT * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.NPL * p.BN * 128;
+    const size_t a_slot = (size_t)p.MT * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.wg * p.NPL * p.BN * 128;
     KG_REQUIRE(a_slot + w_slot <= budget, "tc_conv_prepare: tile does not fit in shared memory");
     na = nw = 1;
   }
@@ -594,14 +532,15 @@ int tc_conv_prepare(TcConvOp* op) {
   p.NA = na; p.NW = nw;
   {
     int ks = 512 / (p.acc_stages * p.MT * p.BN);
-    const int want = p.BN <= 64 ? 4 / p.MT : (p.BN <= 128 ? 2 : 1);     // target ~4 independent chains when N is small
+    int want = p.BN <= 64 ? 4 / p.MT : (p.BN <= 128 ? 2 : 1);           // target ~4 independent chains when N is small
+    if (p.BN <= 64) want = env_int("KG_TC_KSWANT", want);
     if (ks > want) ks = want;
     const int ks_env = env_int("KG_TC_KS", 0);
     if (ks_env > 0 && ks_env < ks) ks = ks_env;
     if (ks < 1) ks = 1;
     const int total_mmas = op->R * op->S * (p.chunks0 + p.chunks1) * 4 * p.passes;
     while (ks > 1 && total_mmas < ks) --ks;                               // every chain must receive at least one MMA
-    if (ks == 3) ks = 2;                                                  // power of two (chain = counter & (KS - 1))
+    while (ks & (ks - 1)) --ks;                                           // power of two (chain = counter & (KS - 1))
     p.KS = ks;
   }
   unsigned cols = 32;
@@ -619,14 +558,18 @@ int tc_conv_prepare(TcConvOp* op) {
     KG_TRY(encode_act_map(&p.a_map[1][0], op->in1_hi, op->in1_C, op->W, op->H, op->N, box_w, p.BH));
     if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[1][1], op->in1_lo, op->in1_C, op->W, op->H, op->N, box_w, p.BH));
   }
-  KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.BN));
-  if (p.NPL == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN));
+  KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
+  if (p.NPL == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
   const int persist = env_int("KG_TC_CTAS", g_num_sms);
   op->grid_x = (unsigned)std::min(p.num_work, std::max(1, persist));
   op->grid_y = 1;
-  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024);
+  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.wg * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024);
   KG_REQUIRE(op->smem_bytes <= (unsigned)TC_MAX_SMEM, "tc_conv_prepare: smem %u > %d", op->smem_bytes, TC_MAX_SMEM);
   op->params = sp;
+  if (env_int("KG_TC_DEBUG", 0))
+    fprintf(stderr, "[tc] N%d %dx%d C%d+%d->%d k%dx%d s%d passes%d | BN%d BW%d BH%d MT%d KS%d acc%d strip%d wg%d NA%d NW%d work%d grid%u smem%u tmem%u\n",
+            op->N, op->H, op->W, op->C0, op->C1, op->Cout, op->R, op->S, op->stride, op->passes, p.BN, p.BW, p.BH, p.MT, p.KS, p.acc_stages,
+            p.strip, p.wg, p.NA, p.NW, p.num_work, op->grid_x, op->smem_bytes, p.tmem_cols);
   return KG_OK;
 }
 

@@ -45,6 +45,8 @@ const char* tc_status();
 bool tc_layer_supported(int cin, int cout, int R, int S);
 int tc_pack_weights(const float* w_tap_cin_cout, int cin, int cout, int R, int S, TcWeights* out);
 void tc_free_weights(TcWeights& w);
+void* tc_encode_tiled_fn();   // cuTensorMapEncodeTiled entry point (null when the tensor-core path is unavailable)
+int tc_num_sms();
 int tc_conv_prepare(TcConvOp* op);
 int tc_conv_launch(const TcConvOp* op, float* out32, cudaStream_t stream);
 

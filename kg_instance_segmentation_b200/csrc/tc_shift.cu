@@ -1,0 +1,417 @@
+// "Row-GEMM + shift-add" convolution on the sm_100a tensor cores, for convs with FEW output channels: the second-layer
+// 7x7 head convs of KGnet (KGnet.py:161-209, Cout = 5 / 10 / 40 per head, three heads per scale fused in one launch).
+//
+// Why: with the plain implicit GEMM (tc_conv.cu) such a layer issues one M=128 x N=16 x K=16 tcgen05.mma per filter tap
+// and k-step.  Each of those reads its 4 KiB A slab from shared memory, which costs ~64-96 cycles however small N is,
+// so a 7x7 conv re-reads every activation 49 times and runs at < 10 % of the tensor pipe (measured: 13 ms for the three
+// c0 heads).  Here the S horizontal taps are folded into N instead:
+//
+//     Z[p, (s, co)] = sum_{r, c} X[y + r - pad, p, c] * Wt[r][s][c][co]         (one GEMM, N = S * Cout, K = R * Cin)
+//     out[y, x, co] = sum_s Z[x + s - pad, (s, co)]                              (shift-add, done in the epilogue)
+//
+// so every activation tile is read by the tensor core once per filter ROW (7x instead of 49x) and every MMA has
+// N = 64..160.  The accumulator Z of a 128-pixel tile lives in TMEM (<= 512 fp32 columns: all three heads at once).
+// The epilogue warps pull Z tap by tap out of TMEM and add it, shifted by (pad - s) pixels, into an fp32 output row
+// buffer in shared memory; tiles of one image row are walked left to right by the same CTA, so the 2*pad pixels that
+// straddle a tile edge are simply carried in that buffer (ring-indexed) to the next tile.  Finished pixels get
+// 1/scale, bias, (sigmoid) and go to the fp32 NCHW head outputs.
+//
+//   roles   warp 0: TMA producer (A tile 128 px x 64 ch + the unit's weight slab per slot), warp 1: MMA issuer,
+//           warps 2-5: epilogue.  One smem ring of NS uniform slots, full/empty mbarriers; single TMEM accumulator set
+//           (tmem_full / tmem_empty hand-off: the MMAs of tile i+1 start as soon as tile i's Z has been read).
+#include "tc_shift.cuh"
+#include "tc_conv.cuh"
+#include "tc_ptx.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+namespace kg {
+
+constexpr int SH_THREADS = 192;
+constexpr int SH_MAX_UNITS = 6, SH_MAX_TAPS = 8, SH_MAX_CHUNKS = 16;
+constexpr int SH_BK = 64;
+constexpr int SH_A_TILE = 128 * SH_BK * 2;   // 16 KiB
+constexpr int SH_MAX_N = 160;                // rows of one weight slab (N of one MMA)
+constexpr int SH_MAX_SMEM = 227 * 1024;
+
+struct ShGroup { const float* bias; float* out32; int in_coff; float inv_scale; int sigmoid; };
+struct ShParams {
+  CUtensorMap a_map;
+  CUtensorMap w_map[SH_MAX_UNITS];
+  ShGroup grp[SH_MAX_GROUPS];
+  int N, H, W, pad, kchunks;
+  int BW, BH, tiles_x, rows_y, num_work;
+  int row_mode, RB;
+  int NS;
+  unsigned slot_bytes, tmem_cols;
+};
+
+// Compile-time geometry of one fused launch: up to three convs with O0 / O1 / O2 output channels, TAPS x TAPS filters.
+// A conv's S taps sit side by side along N with a stride of align8(n_out) columns; a "unit" is a run of taps that fits one
+// MMA (N <= SH_MAX_N); TMEM columns == rows of the packed weight tensor, allocated unit after unit.
+template <int O0, int O1, int O2, int TAPS>
+struct ShCfg {
+  static constexpr int NG = (O0 > 0) + (O1 > 0) + (O2 > 0);
+  static constexpr int n_out(int g) { return g == 0 ? O0 : (g == 1 ? O1 : O2); }
+  static constexpr int stride(int g) { return (n_out(g) + 7) / 8 * 8; }
+  static constexpr int per(int g) { return SH_MAX_N / stride(g) < TAPS ? SH_MAX_N / stride(g) : TAPS; }   // taps per unit
+  static constexpr int units_of(int g) { return (TAPS + per(g) - 1) / per(g); }
+  static constexpr int unit_taps(int g, int k) { return TAPS - k * per(g) < per(g) ? TAPS - k * per(g) : per(g); }
+  static constexpr int unit_n(int g, int k) { return (unit_taps(g, k) * stride(g) + 15) / 16 * 16; }
+  static constexpr int gcols(int g) { int c = 0; for (int k = 0; k < units_of(g); ++k) c += unit_n(g, k); return c; }
+  static constexpr int col0(int g) { int c = 0; for (int i = 0; i < g; ++i) c += gcols(i); return c; }
+  static constexpr int bufcol(int g) { int c = 0; for (int i = 0; i < g; ++i) c += n_out(i); return c; }
+  static constexpr int nchunks(int g) { return (n_out(g) + 7) / 8; }                     // 8-column TMEM loads per tap
+  static constexpr int chunk0(int g) { int c = 0; for (int i = 0; i < g; ++i) c += nchunks(i); return c; }
+  static constexpr int NU = (O0 > 0 ? units_of(0) : 0) + (O1 > 0 ? units_of(1) : 0) + (O2 > 0 ? units_of(2) : 0);
+  static constexpr int COLS = col0(NG);
+  static constexpr int NOUT = bufcol(NG);
+  static constexpr int RS = NOUT | 1;         // odd row stride of the output buffer: conflict-free across pixels
+  // unit u -> (group, index inside the group)
+  static constexpr int u_group(int u) { int g = 0; while (u >= units_of(g)) { u -= units_of(g); ++g; } return g; }
+  static constexpr int u_index(int u) { int g = 0; while (u >= units_of(g)) { u -= units_of(g); ++g; } return u; }
+  static constexpr int u_n(int u) { return unit_n(u_group(u), u_index(u)); }
+  static constexpr int u_col(int u) { int c = col0(u_group(u)); for (int k = 0; k < u_index(u); ++k) c += unit_n(u_group(u), k); return c; }
+  static constexpr bool u_share(int u) { return u_index(u) == 1; }                      // 2nd unit of a conv reuses the 1st one's A tile
+  static constexpr bool u_keep(int u) { return u_index(u) == 0 && units_of(u_group(u)) > 1; }
+  // the accumulator column of (group, tap) must be linear in the tap for the epilogue: every non-final unit is unpadded
+  static constexpr bool linear() {
+    for (int g = 0; g < NG; ++g)
+      for (int k = 0; k + 1 < units_of(g); ++k)
+        if (unit_n(g, k) != unit_taps(g, k) * stride(g)) return false;
+    return true;
+  }
+  static_assert(COLS <= 512 && NU <= SH_MAX_UNITS && TAPS <= SH_MAX_TAPS, "configuration does not fit TMEM / the unit table");
+};
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N) -- the geometry functions of ShCfg are then evaluated
+// by the compiler (constexpr locals), never at run time
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int O0, int O1, int O2, int TAPS>
+__global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_constant__ ShParams p) {
+  using Cfg = ShCfg<O0, O1, O2, TAPS>;
+  static_assert(Cfg::linear(), "tap columns must be linear");
+  constexpr int NU = Cfg::NU, NG = Cfg::NG, RS = Cfg::RS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t smem0 = (smem_base + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = smem0;
+  const uint32_t bars = ring + (uint32_t)p.NS * p.slot_bytes;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (p.NS + s); };
+  const uint32_t tmem_full = bars + 16u * p.NS, tmem_empty = tmem_full + 8u, tmem_slot = tmem_full + 16u;
+  float* buf = reinterpret_cast<float*>(smem_raw + (smem0 - smem_base) + (size_t)p.NS * p.slot_bytes + 16u * p.NS + 64u);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.a_map);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) prefetch_tmap(&p.w_map[u]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.NS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(tmem_full, 1); mbar_init(tmem_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2)
+    for (int e = threadIdx.x - 64; e < p.RB * RS; e += 128) buf[e] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    const bool leader = elect_one();
+    int slot = 0; uint32_t ph = 0;
+    for (int work = blockIdx.x; work < p.num_work; work += gridDim.x) {
+      const int n = work / p.rows_y, y0 = (work - n * p.rows_y) * p.BH;
+      for (int tx = 0; tx < p.tiles_x; ++tx)
+        for (int r = 0; r < TAPS; ++r)
+          for (int ch = 0; ch < p.kchunks; ++ch) {
+            static_for<0, NU>([&](auto U) __attribute__((always_inline)) {
+              constexpr int u = decltype(U)::value;
+              constexpr int g = Cfg::u_group(u), wrow = Cfg::u_col(u);
+              constexpr bool share = Cfg::u_share(u);
+              constexpr uint32_t tx_bytes = (share ? 0u : (uint32_t)SH_A_TILE) + (uint32_t)Cfg::u_n(u) * 128u;
+              mbar_wait(empty(slot), ph ^ 1u);
+              if (leader) {
+                const uint32_t base = ring + (uint32_t)slot * p.slot_bytes;
+                mbar_expect_tx(full(slot), tx_bytes);
+                if (!share) tma_load_4d(base, &p.a_map, p.grp[g].in_coff + ch * SH_BK, tx * p.BW, y0 + r - p.pad, n, full(slot));
+                tma_load_3d(base + SH_A_TILE, &p.w_map[u], ch * SH_BK, wrow, r, full(slot));
+              }
+              __syncwarp();
+              if (++slot == p.NS) { slot = 0; ph ^= 1u; }
+            });
+          }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const bool leader = elect_one();
+    int slot = 0; uint32_t ph = 0;
+    uint32_t tile_it = 0;
+    for (int work = blockIdx.x; work < p.num_work; work += gridDim.x)
+      for (int tx = 0; tx < p.tiles_x; ++tx, ++tile_it) {
+        mbar_wait(tmem_empty, (tile_it & 1u) ^ 1u);        // the epilogue has read the previous tile's Z
+        tc_fence_after();
+        for (int r = 0; r < TAPS; ++r)
+          for (int ch = 0; ch < p.kchunks; ++ch) {
+            const uint32_t accum0 = (r | ch) != 0 ? 1u : 0u;
+            static_for<0, NU>([&](auto U) __attribute__((always_inline)) {
+              constexpr int u = decltype(U)::value;
+              constexpr bool share = Cfg::u_share(u), keep = Cfg::u_keep(u);
+              constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(Cfg::u_n(u) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32, K-major, M = 128
+              constexpr uint32_t dcol = (uint32_t)Cfg::u_col(u);
+              mbar_wait(full(slot), ph);
+              tc_fence_after();
+              const uint32_t sbase = ring + (uint32_t)slot * p.slot_bytes;
+              const int pslot = slot == 0 ? p.NS - 1 : slot - 1;
+              const uint32_t abase = share ? ring + (uint32_t)pslot * p.slot_bytes : sbase;
+              const uint64_t adesc = umma_desc(abase), bdesc = umma_desc(sbase + SH_A_TILE);
+              if (leader) {
+#pragma unroll
+                for (int k = 0; k < SH_BK / 16; ++k) umma_f16(tmem_base + dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? accum0 : 1u);
+                if (share) umma_commit(empty(pslot));        // the shared A tile's slot is released with this unit
+                if (!keep) umma_commit(empty(slot));
+              }
+              __syncwarp();
+              if (++slot == p.NS) { slot = 0; ph ^= 1u; }
+            });
+          }
+        if (leader) umma_commit(tmem_full);
+        __syncwarp();
+      }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31; thread t <-> tile position t =====
+    const int quad = warp & 3;
+    const int t = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int tj = p.row_mode ? 0 : t / p.BW, txx = p.row_mode ? t : t - tj * p.BW;
+    const long long cs = (long long)p.H * p.W;
+    uint32_t tile_it = 0;
+    int off = 0;                                           // ring offset of logical buffer row 0
+    for (int work = blockIdx.x; work < p.num_work; work += gridDim.x) {
+      const int n = work / p.rows_y, y0 = (work - n * p.rows_y) * p.BH;
+      for (int tx = 0; tx < p.tiles_x; ++tx, ++tile_it) {
+        mbar_wait(tmem_full, tile_it & 1u);
+        tc_fence_after();
+        // ---- shift-add: tap s of position q goes to output pixel q - s + pad (everything below is compile-time unrolled) ----
+        static_for<0, TAPS>([&](auto Sx) __attribute__((always_inline)) {
+          constexpr int s = decltype(Sx)::value;
+          int L; bool valid = true;
+          if (p.row_mode) { L = t - s + 2 * p.pad; }
+          else { const int x2 = txx - s + p.pad; valid = x2 >= 0 && x2 < p.BW; L = tj * p.BW + x2; }
+          int phys = L + off; if (phys >= p.RB) phys -= p.RB;
+          float* row = buf + (valid ? phys : 0) * RS;
+          // conv by conv: TMEM loads -> wait -> all smem loads -> adds -> stores (bounded register footprint)
+          static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
+            constexpr int g = decltype(Gx)::value;
+            constexpr int no = Cfg::n_out(g), b0 = Cfg::bufcol(g);
+            uint32_t raw[Cfg::nchunks(g)][8];
+            {
+              static_for<0, Cfg::nchunks(g)>([&](auto Cx) __attribute__((always_inline)) {
+                constexpr int c = decltype(Cx)::value;
+                constexpr uint32_t col = (uint32_t)(Cfg::col0(g) + Cfg::stride(g) * s + 8 * c);
+                tmem_ld8_nowait(lane_addr + col, raw[c]);
+              });
+            }
+            tmem_ld_wait();
+            if (s == TAPS - 1 && g == NG - 1) {              // Z fully read: hand the accumulators back to the MMA issuer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
+            }
+            if (valid) {
+              float cur[no];
+#pragma unroll
+              for (int e = 0; e < no; ++e) cur[e] = row[b0 + e];        // all loads first: the smem latency is paid once
+#pragma unroll
+              for (int e = 0; e < no; ++e) row[b0 + e] = cur[e] + __uint_as_float(raw[e / 8][e % 8]);
+            }
+          });
+          epi_bar();
+        });
+        // ---- emit the finished pixels (and clear their buffer rows) ----
+        const bool last = tx == p.tiles_x - 1;
+        const int nL = p.row_mode ? (last ? p.RB : 128) : 128;
+        for (int L = t; L < nL; L += 128) {
+          int phys = L + off; if (phys >= p.RB) phys -= p.RB;
+          float* row = buf + phys * RS;
+          int y, x; bool inside;
+          if (p.row_mode) { y = y0; x = tx * 128 + L - p.pad; inside = x >= 0 && x < p.W; }
+          else { const int jj = L / p.BW; y = y0 + jj; x = L - jj * p.BW; inside = y < p.H; }
+          static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
+            constexpr int g = decltype(Gx)::value;
+            constexpr int no = Cfg::n_out(g), b0 = Cfg::bufcol(g);
+            float v[no];
+#pragma unroll
+            for (int e = 0; e < no; ++e) v[e] = row[b0 + e];
+#pragma unroll
+            for (int e = 0; e < no; ++e) row[b0 + e] = 0.f;
+            if (inside) {
+              const ShGroup& G = p.grp[g];
+              float* dst = G.out32 + ((long long)n * no * p.H + y) * p.W + x;
+#pragma unroll
+              for (int co = 0; co < no; ++co) {
+                float o = v[co] * G.inv_scale + __ldg(G.bias + co);
+                if (G.sigmoid) o = 1.f / (1.f + expf(-o));
+                *dst = o;
+                dst += cs;
+              }
+            }
+          });
+        }
+        if (p.row_mode) { off += 128; if (off >= p.RB) off -= p.RB; }
+        epi_bar();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// the instantiated configurations: KGnet's second-layer heads (kp 5, short offsets 10, mid offsets 40; 7x7)
+using HeadsCfg = ShCfg<5, 10, 40, 7>;
+
+bool tc_shift_supported(int H, int W, int R, int S, int pad, int Cin, int n_groups, const int* n_out) {
+  if (!tc_available()) return false;
+  const char* off = getenv("KG_TC_SHIFT");
+  if (off && off[0] == '0') return false;
+  if (H < 1 || R != S || 2 * pad != S - 1 || Cin % SH_BK != 0) return false;
+  if (!((W >= 128 && W % 128 == 0) || (W >= 8 && W < 128 && is_pow2(W)))) return false;
+  return S == 7 && n_groups == 3 && n_out[0] == 5 && n_out[1] == 10 && n_out[2] == 40;
+}
+
+template <class Cfg>
+static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
+  std::shared_ptr<ShParams> sp(new ShParams());
+  ShParams& p = *sp;
+  memset(&p, 0, sizeof(p));
+  p.N = op->N; p.H = op->H; p.W = op->W; p.pad = op->pad; p.kchunks = op->Cin / SH_BK;
+  p.row_mode = op->W >= 128 ? 1 : 0;
+  p.BW = p.row_mode ? 128 : op->W; p.BH = 128 / p.BW;
+  p.tiles_x = p.row_mode ? op->W / 128 : 1;
+  p.rows_y = ceil_div(op->H, p.BH);
+  p.num_work = op->N * p.rows_y;
+  p.RB = p.row_mode ? 128 + 2 * op->pad : 128;
+  const int rows = Cfg::COLS, S = op->S, R = op->R;
+  unsigned tc = 32;
+  while (tc < (unsigned)Cfg::COLS) tc *= 2;
+  p.tmem_cols = tc;
+  // packed weights [R][rows][Cin] fp16: row of (conv g, tap s, channel co) = col0(g) + s * stride(g) + co; each conv is scaled
+  // by a power of two so that small weights stay in fp16's normal range (undone by inv_scale in the epilogue)
+  std::vector<__half> hw((size_t)R * rows * op->Cin, __float2half_rn(0.f));
+  for (int g = 0; g < Cfg::NG; ++g) {
+    const TcShiftGroup& G = op->g[g];
+    KG_REQUIRE(G.h_w && G.d_bias && G.n_out == Cfg::n_out(g), "tc_shift_prepare: conv %d: null weights / bias or unexpected Cout", g);
+    float mx = 0.f;
+    const size_t nw = (size_t)R * S * op->Cin * G.n_out;
+    for (size_t i = 0; i < nw; ++i) mx = fmaxf(mx, fabsf(G.h_w[i]));
+    int e = 0;
+    if (mx > 0.f && std::isfinite(mx)) { int ex; frexpf(mx, &ex); e = 10 - ex; }
+    e = std::max(-40, std::min(40, e));
+    const float scale = ldexpf(1.f, e);
+    ShGroup& D = p.grp[g];
+    D.bias = G.d_bias; D.in_coff = G.in_coff; D.sigmoid = G.sigmoid ? 1 : 0; D.inv_scale = ldexpf(1.f, -e);
+    for (int r = 0; r < R; ++r)
+      for (int t = 0; t < S; ++t)
+        for (int ci = 0; ci < op->Cin; ++ci)
+          for (int co = 0; co < G.n_out; ++co)
+            hw[((size_t)r * rows + Cfg::col0(g) + t * Cfg::stride(g) + co) * op->Cin + ci] =
+                __float2half_rn(G.h_w[(((size_t)r * S + t) * op->Cin + ci) * G.n_out + co] * scale);
+  }
+  __half* d_w = nullptr;
+  KG_CUDA_CHECK(cudaMalloc(&d_w, hw.size() * sizeof(__half)));
+  op->d_weights = std::shared_ptr<void>(d_w, [](void* q) { cudaFree(q); });
+  KG_CUDA_CHECK(cudaMemcpy(d_w, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)op->in_C, (cuuint64_t)op->W, (cuuint64_t)op->H, (cuuint64_t)op->N};
+    cuuint64_t strides[3] = {(cuuint64_t)op->in_C * 2, (cuuint64_t)op->W * op->in_C * 2, (cuuint64_t)op->H * op->W * op->in_C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)SH_BK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&p.a_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)op->in_hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc_shift_prepare: cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return KG_ERR_CUDA; }
+  }
+  int maxN = 0;
+  for (int u = 0; u < Cfg::NU; ++u) {
+    maxN = std::max(maxN, Cfg::u_n(u));
+    cuuint64_t dims[3] = {(cuuint64_t)op->Cin, (cuuint64_t)rows, (cuuint64_t)R};
+    cuuint64_t strides[2] = {(cuuint64_t)op->Cin * 2, (cuuint64_t)rows * op->Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)SH_BK, (cuuint32_t)Cfg::u_n(u), 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&p.w_map[u], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)d_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tc_shift_prepare: cuTensorMapEncodeTiled(weights, unit %d) failed: %d", u, (int)r); return KG_ERR_CUDA; }
+  }
+  p.slot_bytes = (unsigned)(SH_A_TILE + align_up((size_t)maxN * 128, 1024));
+  const size_t buf_bytes = (size_t)p.RB * Cfg::RS * sizeof(float);
+  const size_t fixed = 1024 + 16 * 16 + 64 + buf_bytes + 64;
+  int ns = (int)((SH_MAX_SMEM - fixed) / p.slot_bytes);
+  if (ns > 8) ns = 8;
+  KG_REQUIRE(ns >= 2, "tc_shift_prepare: tile does not fit in shared memory");
+  p.NS = ns;
+  op->smem_bytes = (unsigned)(1024 + (size_t)ns * p.slot_bytes + 16 * ns + 64 + buf_bytes + 64);
+  op->grid = (unsigned)std::min(p.num_work, tc_num_sms());
+  op->params = sp;
+  if (getenv("KG_TC_DEBUG"))
+    fprintf(stderr, "[tc_shift] N%d %dx%d Cin%d k%dx%d | units%d cols%d BW%d BH%d tiles_x%d work%d NS%d slot%u RB%d RS%d smem%u tmem%u\n",
+            op->N, op->H, op->W, op->Cin, R, S, Cfg::NU, Cfg::COLS, p.BW, p.BH, p.tiles_x, p.num_work, p.NS, p.slot_bytes, p.RB, Cfg::RS,
+            op->smem_bytes, p.tmem_cols);
+  return KG_OK;
+}
+
+int tc_shift_prepare(TcShiftOp* op) {
+  KG_REQUIRE(op != nullptr, "tc_shift_prepare: null op");
+  int n_out[SH_MAX_GROUPS] = {0, 0, 0};
+  for (int g = 0; g < op->n_groups && g < SH_MAX_GROUPS; ++g) n_out[g] = op->g[g].n_out;
+  KG_REQUIRE(tc_shift_supported(op->H, op->W, op->R, op->S, op->pad, op->Cin, op->n_groups, n_out), "tc_shift_prepare: unsupported shape");
+  EncodeTiledFn encode = (EncodeTiledFn)tc_encode_tiled_fn();
+  KG_REQUIRE(encode != nullptr, "tc_shift_prepare: cuTensorMapEncodeTiled unavailable");
+  static bool attr_set = false;
+  if (!attr_set) {
+    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<5, 10, 40, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
+    attr_set = true;
+  }
+  return shift_prepare_t<HeadsCfg>(op, encode);
+}
+
+int tc_shift_launch(const TcShiftOp* op, float* const* out32, cudaStream_t stream) {
+  KG_REQUIRE(op && op->params && out32, "tc_shift_launch: op not prepared");
+  ShParams p = *reinterpret_cast<const ShParams*>(op->params.get());
+  for (int g = 0; g < op->n_groups; ++g) {
+    KG_REQUIRE(out32[g] != nullptr, "tc_shift_launch: output %d is null", g);
+    p.grp[g].out32 = out32[g];
+  }
+  tc_shift_kernel<5, 10, 40, 7><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+}  // namespace kg

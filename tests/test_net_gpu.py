@@ -116,6 +116,42 @@ def test_conv_tensor_core_path(case, mode):
     assert err <= tol, f"max err {err} > {tol}"
 
 
+HEADS_L2_CASES = [  # (N, Cin, H, W): second-layer head convs through the row-GEMM + shift-add kernel (tc_shift.cu)
+    (1, 64, 9, 512),     # row mode, 4 tiles per row: carries across tile edges
+    (2, 64, 5, 256),     # row mode, 2 tiles per row, 2 images
+    (1, 256, 6, 128),    # row mode, one tile per row, 4 K chunks
+    (2, 128, 10, 64),    # two image rows per tile
+    (1, 64, 7, 32),      # four rows per tile, H not a multiple of the tile height
+    (1, 64, 16, 16),
+    (3, 64, 8, 8),       # tile taller than the image
+    (1, 512, 4, 64),     # c3 class: 8 K chunks
+]
+
+
+@pytest.mark.parametrize("case", HEADS_L2_CASES)
+def test_heads_l2_shift_kernel(case):
+    from kg_instance_segmentation_b200 import _cabi
+    L = _cabi.lib()
+    N, Cin, H, W = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, 3 * Cin, H, W, generator=g)
+    ws = [torch.randn(co, Cin, 7, 7, generator=g) * (2.0 / (Cin * 49)) ** 0.5 for co in (5, 10, 40)]
+    bs = [torch.randn(co, generator=g) * 0.1 for co in (5, 10, 40)]
+    ref = [F.conv2d(x[:, h * Cin:(h + 1) * Cin], ws[h], bs[h], padding=3) for h in range(3)]
+    ref[0] = torch.sigmoid(ref[0])
+    xd = x.cuda().contiguous()
+    ys = [torch.full((N, co, H, W), float("nan"), device="cuda") for co in (5, 10, 40)]
+    wp = (C.c_void_p * 3)(*[w.data_ptr() for w in ws]); bp = (C.c_void_p * 3)(*[b.data_ptr() for b in bs])
+    yp = (C.c_void_p * 3)(*[y.data_ptr() for y in ys])
+    _cabi.check(L.kg_heads_l2_nchw(xd.data_ptr(), N, Cin, H, W, wp, bp, yp, None))
+    for h in range(3):
+        got = ys[h].cpu()
+        assert not torch.isnan(got).any(), f"head {h}: unwritten outputs"
+        scale = float(ref[h].abs().max())
+        err = float((got - ref[h]).abs().max())
+        assert err <= 3e-3 * scale + 1e-5, f"head {h}: max err {err} (scale {scale})"
+
+
 def _model(precision):
     from kg_instance_segmentation_b200 import KGnet
     sd = O.make_state_dict(seed=0)

@@ -14,7 +14,7 @@ SKIP=${SKIP:-$((3*L))}
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $L --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1
 if [ "${FULL:-1}" = "1" ]; then
-  timeout 900 ncu --set full --clock-control none -s $SKIP -c $L -f -o gpurun_out/${tag}_step \
+  timeout 700 ncu --set full --clock-control none -s $SKIP -c $L -f -o gpurun_out/${tag}_step \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
   ncu -i gpurun_out/${tag}_step.ncu-rep --page raw --csv > gpurun_out/${tag}_step_raw.csv 2>/dev/null
   sz=$(stat -c %s gpurun_out/${tag}_step.ncu-rep)
