@@ -29,12 +29,14 @@ namespace kg {
 constexpr int TC_BM = 128;          // rows (pixels) per accumulator tile
 constexpr int TC_BK = 64;           // channels per K step (one 128-byte swizzle row)
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KiB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (two warps per TMEM lane quadrant)
 constexpr int TC_MAX_SMEM = 227 * 1024;
 
 struct TcParams {
   CUtensorMap a_map[2][2];          // [source][plane hi/lo]
   CUtensorMap w_map[2];             // [plane hi/lo]
+  CUtensorMap o_map[2];             // NHWC output planes (TMA-store epilogue), boxes of 64 channels x 32 pixels
+  int o_tma, o_bw;                  // o_tma: outputs leave through smem staging + TMA stores; o_bw: box width in pixels (32 / o_bw rows)
   const float* bias;
   __half* out_hi; __half* out_lo;
   float* out32;
@@ -76,7 +78,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const uint32_t w_tile = (uint32_t)p.BN * 128u;
   const uint32_t w_plane = (uint32_t)p.wg * w_tile;                   // one plane of one W slot: wg taps back to back
   const uint32_t w_slot = (uint32_t)NPL * w_plane;
-  const uint32_t a_ring = smem0, w_ring = smem0 + (uint32_t)p.NA * a_slot;
+  const uint32_t stage0 = smem0;                                      // output staging: 4 epilogue warps x (hi 4 KiB + lo 4 KiB)
+  const uint32_t a_ring = smem0 + (p.o_tma ? 65536u : 0u), w_ring = a_ring + (uint32_t)p.NA * a_slot;
   const uint32_t bars = w_ring + (uint32_t)p.NW * w_slot;
   auto a_full = [&](int s) { return bars + 8u * s; };
   auto a_empty = [&](int s) { return bars + 8u * (p.NA + s); };
@@ -91,11 +94,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     prefetch_tmap(&p.a_map[0][0]); prefetch_tmap(&p.w_map[0]);
     if (NPL == 2) { prefetch_tmap(&p.a_map[0][1]); prefetch_tmap(&p.w_map[1]); }
     if (p.chunks1 > 0) { prefetch_tmap(&p.a_map[1][0]); if (NPL == 2) prefetch_tmap(&p.a_map[1][1]); }
+    if (p.o_tma) { prefetch_tmap(&p.o_map[0]); if (p.out_lo != nullptr) prefetch_tmap(&p.o_map[1]); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }   // 4 epilogue warps release a buffer
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 8); }   // 8 epilogue warps release a buffer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -227,10 +231,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       }   // work loop
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4; the two warps of a quadrant take alternate 16-column chunks
+    // (the epilogue is instruction-bound: bias / residual / ReLU / split-fp16 conversion of 128 x BN values per tile) =====
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int cgran = p.o_tma ? 6 : 4;                               // log2 of the column granule one warp owns (64 with TMA staging)
     const int row = quad * 32 + lane;
     const int HW = p.H * p.W;
+    const uint32_t stg = stage0 + (uint32_t)(warp - 2) * 8192u;      // this warp's staging: 32 pixels x 128 B, hi then lo
+    const uint32_t stg_row = stg + (uint32_t)lane * 128u;
     int it = 0;
     for (int work = blockIdx.x; work < p.num_work; work += gridDim.x, ++it) {
     const int m_first = (work / p.n_tiles) * MT;
@@ -250,6 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const long long pix = (long long)n * HW + (long long)oy * p.W + ox;
       const bool keep = valid && (p.mask == nullptr || p.mask[pix] != 0);
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        if (((c0 >> cgran) & 1) != half) continue;
         uint32_t raw[16];
         float v[16];
         tmem_ld16(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.KS * p.BN + c0), raw);
@@ -261,16 +271,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(raw[j]);
         }
         const int co0 = n0 + c0;
-        if (!valid || co0 >= p.Cout) continue;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= p.inv_scale;
+        if ((!valid && !p.o_tma) || co0 >= p.Cout) continue;
         if (co0 + 16 <= p.Cout) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            v[j] = fmaf(v[j], p.inv_scale, b.x); v[j + 1] = fmaf(v[j + 1], p.inv_scale, b.y);
+            v[j + 2] = fmaf(v[j + 2], p.inv_scale, b.z); v[j + 3] = fmaf(v[j + 3], p.inv_scale, b.w);
           }
-          if (p.res_hi != nullptr) {
+          if (p.res_hi != nullptr && valid) {
             const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.Cout + co0);
             const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.Cout + co0);
 #pragma unroll
@@ -289,7 +298,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           for (int j = 0; j < 16; ++j) {
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
             if (p.sigmoid) v[j] = 1.f / (1.f + expf(-v[j]));
-            if (!keep) v[j] = 0.f;
+          }
+          if (p.mask != nullptr && !keep) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
           if (p.out_hi != nullptr) {
             uint4 hi4[2], lo4[2];
@@ -303,14 +315,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               hh[e] = h;
               ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
             }
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0);
-            oh[0] = hi4[0]; oh[1] = hi4[1];
-            if (p.out_lo != nullptr) {
-              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + co0);
-              ol[0] = lo4[0]; ol[1] = lo4[1];
+            if (p.o_tma) {
+              // staging rows are 128 B (64 channels) with the 128-byte swizzle of the store's tensor map: 16-byte chunk j of
+              // row r sits at chunk (j ^ (r & 7)); a 64-channel group is complete after four 16-channel pieces
+              const int piece = (c0 >> 4) & 3;
+              if (piece == 0) {                               // the previous group's TMA store must have read the staging
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+              }
+              const uint32_t sw = (uint32_t)(lane & 7);
+              const uint32_t a0 = stg_row + ((((uint32_t)(2 * piece)) ^ sw) << 4), a1 = stg_row + ((((uint32_t)(2 * piece + 1)) ^ sw) << 4);
+              st_shared_v4(a0, hi4[0]); st_shared_v4(a1, hi4[1]);
+              if (p.out_lo != nullptr) { st_shared_v4(a0 + 4096u, lo4[0]); st_shared_v4(a1 + 4096u, lo4[1]); }
+              if (piece == 3 || c0 + 16 >= p.BN) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  const int r0 = quad * 32;
+                  const int ly = r0 / p.BW, lx = r0 - ly * p.BW;
+                  const int gx = tx * p.BW + lx, gy = ty * p.BH + ly;
+                  if (gx < p.W && gy < p.H) {
+                    tma_store_4d(&p.o_map[0], stg, co0 & ~63, gx, gy, n);
+                    if (p.out_lo != nullptr) tma_store_4d(&p.o_map[1], stg + 4096u, co0 & ~63, gx, gy, n);
+                  }
+                  bulk_commit();
+                }
+              }
+            } else {
+              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0);
+              oh[0] = hi4[0]; oh[1] = hi4[1];
+              if (p.out_lo != nullptr) {
+                uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + co0);
+                ol[0] = lo4[0]; ol[1] = lo4[1];
+              }
             }
           }
-          if (p.out32 != nullptr) {
+          if (p.out32 != nullptr && valid) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) p.out32[((long long)n * p.Cout + co0 + j) * HW + (long long)oy * p.W + ox] = v[j];
           }
@@ -319,8 +359,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = co0 + j;
-            if (co < p.Cout) {
-              float x = v[j] + __ldg(p.bias + co);
+            if (co < p.Cout && valid) {
+              float x = fmaf(v[j], p.inv_scale, __ldg(p.bias + co));
               if (p.relu) x = fmaxf(x, 0.f);
               if (p.sigmoid) x = 1.f / (1.f + expf(-x));
               if (!keep) x = 0.f;
@@ -335,6 +375,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
     }   // work loop
+    if (p.o_tma && lane == 0) bulk_wait_all();              // every TMA store of this warp has landed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -492,7 +533,11 @@ int tc_conv_prepare(TcConvOp* op) {
   const int strip_px = strip ? TC_BM + op->S - 1 : TC_BM;
   p.a_tx_bytes = (unsigned)(strip ? strip_px * 128 : TC_A_TILE);
   p.a_tile_bytes = (unsigned)align_up(p.a_tx_bytes, 1024);
-  const size_t budget = TC_MAX_SMEM - 2048;
+  // TMA-store epilogue (opt-in, KG_TC_OTMA=1): NHWC outputs go through a 64 KiB smem staging area and leave as full 128-byte rows (a lane-per-pixel
+  // direct store writes 32 B per lane at a Cout * 2 B stride: 32 L2 requests per instruction, which bounds wide-N layers)
+  p.o_tma = (op->out_hi != nullptr && op->Cout % 64 == 0 && p.BN % 64 == 0 && env_int("KG_TC_OTMA", 0) != 0) ? 1 : 0;
+  p.o_bw = p.BW < 32 ? p.BW : 32;
+  const size_t budget = TC_MAX_SMEM - 2048 - (p.o_tma ? 65536 : 0);
   // weight tap group: all S taps of a filter row in one W slot when that slot stays small (narrow-N layers)
   p.wg = 1;
   if (op->S > 1 && (size_t)op->S * p.NPL * p.BN * 128 <= (size_t)env_int("KG_TC_WG_MAXKB", 48) * 1024 && env_int("KG_TC_WG", 1) != 0) p.wg = op->S;
@@ -560,16 +605,20 @@ int tc_conv_prepare(TcConvOp* op) {
   }
   KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
   if (p.NPL == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
+  if (p.o_tma) {
+    KG_TRY(encode_act_map(&p.o_map[0], op->out_hi, op->Cout, op->W, op->H, op->N, p.o_bw, 32 / p.o_bw));
+    if (op->out_lo != nullptr) KG_TRY(encode_act_map(&p.o_map[1], op->out_lo, op->Cout, op->W, op->H, op->N, p.o_bw, 32 / p.o_bw));
+  }
   const int persist = env_int("KG_TC_CTAS", g_num_sms);
   op->grid_x = (unsigned)std::min(p.num_work, std::max(1, persist));
   op->grid_y = 1;
-  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.wg * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024);
+  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.wg * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024 + (p.o_tma ? 65536 : 0));
   KG_REQUIRE(op->smem_bytes <= (unsigned)TC_MAX_SMEM, "tc_conv_prepare: smem %u > %d", op->smem_bytes, TC_MAX_SMEM);
   op->params = sp;
   if (env_int("KG_TC_DEBUG", 0))
-    fprintf(stderr, "[tc] N%d %dx%d C%d+%d->%d k%dx%d s%d passes%d | BN%d BW%d BH%d MT%d KS%d acc%d strip%d wg%d NA%d NW%d work%d grid%u smem%u tmem%u\n",
+    fprintf(stderr, "[tc] N%d %dx%d C%d+%d->%d k%dx%d s%d passes%d | BN%d BW%d BH%d MT%d KS%d acc%d strip%d wg%d otma%d NA%d NW%d work%d grid%u smem%u tmem%u\n",
             op->N, op->H, op->W, op->C0, op->C1, op->Cout, op->R, op->S, op->stride, op->passes, p.BN, p.BW, p.BH, p.MT, p.KS, p.acc_stages,
-            p.strip, p.wg, p.NA, p.NW, p.num_work, op->grid_x, op->smem_bytes, p.tmem_cols);
+            p.strip, p.wg, p.o_tma, p.NA, p.NW, p.num_work, op->grid_x, op->smem_bytes, p.tmem_cols);
   return KG_OK;
 }
 

@@ -192,9 +192,40 @@ def test_forward_seg_matches_golden(precision):
             ref = g[f"ref_mask{i}_{j}"]
             got = seg[0][i][j].cpu().numpy()
             assert got.shape == ref.shape
-            # masks: CUDA-core path 2e-3; "fast" runs the mask branch in single-pass fp16 (10 layers deep): 6e-3
-            assert np.abs(got - ref).max() <= (2e-3 if precision == "reference" else 6e-3), (i, j, np.abs(got - ref).max())
+            # masks: CUDA-core path 2e-3.  "fast" runs atlas level 0 of the mask branch in single-pass fp16; the golden
+            # weights are raw Kaiming init, whose mask logits reach |z| ~ 50, so a 1e-3 relative logit error shows up as
+            # ~1e-2 on the sigmoid: 2e-2 here, and the thresholded mask (test.py:149, seg_thresh 0.5) must agree wherever
+            # the reference is not within that margin of the threshold.  The calibrated-logit case is tested below at 3e-3.
+            tol = 2e-3 if precision == "reference" else 2e-2
+            assert np.abs(got - ref).max() <= tol, (i, j, np.abs(got - ref).max())
+            sure = np.abs(ref - 0.5) > tol
+            assert np.array_equal((got >= 0.5)[sure], (ref >= 0.5)[sure])
             assert np.array_equal(seg[1][i][j].numpy(), g[f"ref_det{i}_{j}"])
+
+
+def test_forward_seg_fast_calibrated_logits():
+    """Mask branch in precision "fast" against the oracle with O(1) mask logits (seg_head.2 scaled like the calibrated
+    keypoint heads): 3e-3 on the sigmoid output."""
+    from kg_instance_segmentation_b200 import KGnet
+    sd = O.make_state_dict(seed=0)
+    sd["seg_head.2.weight"] = sd["seg_head.2.weight"] * 0.05
+    m = KGnet.resnet50(pretrained=False, precision="fast")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    torch.manual_seed(7)
+    x = torch.rand(2, 3, 64, 64) - 0.5
+    ref = O.forward_dec(sd, x)
+    boxes = [np.array([[3., 2., 60., 58., 0.9], [20., 10., 40., 44., 0.6]]), np.array([[8., 8., 30., 30., 0.7]])]
+    rseg = O.forward_seg(sd, ref[4], boxes)
+    out = m.forward_dec(x.cuda())
+    seg = m.forward_seg(out[4], boxes)
+    worst = 0.0
+    for i in range(2):
+        assert len(seg[0][i]) == len(rseg[0][i])
+        for a, b in zip(seg[0][i], rseg[0][i]):
+            assert a.shape == b.shape
+            worst = max(worst, float((a.cpu() - b).abs().max()))
+    assert worst <= 3e-3, worst
 
 
 def test_forward_seg_on_external_features_and_empty_boxes():
