@@ -900,26 +900,30 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
   size_t mask_total = 0;
   for (int l = 0; l < 5; ++l) mask_total += align_up((size_t)sp.lv[l].HA * sp.lv[l].WA, 256);
   KG_CUDA_CHECK(cudaMemsetAsync(masks, 0, mask_total, stream));
+  // single-pass levels keep only the hi plane of every atlas tensor (their convs never read lo): half the HBM traffic
+  auto lo_of = [&](int l) -> __half* { return l < one_pass_levels ? nullptr : s_lo; };
   // crops -> P_l, validity masks
   for (int l = 0; l < 5; ++l) {
     auto& L = sp.lv[l];
     if (L.crop.empty()) continue;
     const Tensor& f = p->tensors[p->feat_ids[l]];
-    KG_TRY(launch_bilinear(P.hi(f), P.lo(f), f.C, s_hi, s_lo, f.C, f.C, reinterpret_cast<const ResizeProb*>(dp + o_crop[l]), (int)L.crop.size(),
-                           L.pix_crop, stream));
+    KG_TRY(launch_bilinear(P.hi(f), lo_of(l) ? P.lo(f) : nullptr, f.C, s_hi, lo_of(l), f.C, f.C, reinterpret_cast<const ResizeProb*>(dp + o_crop[l]),
+                           (int)L.crop.size(), L.pix_crop, stream));
     KG_TRY(launch_fill_rects(masks + L.mask, reinterpret_cast<const RectProb*>(dp + o_rect[l]), (int)L.rects.size(), stream));
     launches += 2;
   }
   auto conv = [&](const std::string& wname, const SegPlan::Level& L, size_t in0, int C0, size_t in1, int C1, size_t out, int Cout_t,
                   float* out32, bool relu, bool sig) -> int {
-    const int passes = (&L - &sp.lv[0]) < one_pass_levels ? 1 : 3;
+    const int lvl = (int)(&L - &sp.lv[0]);
+    const int passes = lvl < one_pass_levels ? 1 : 3;
     const ConvW& w = net->convs.at(wname);
     TcConvOp t{};
     t.w = &w.tc; t.bias = w.d_b; t.N = 1; t.H = L.HA; t.W = L.WA; t.R = w.R; t.S = w.S; t.pad = w.R / 2;
     t.C0 = C0; t.C1 = C1; t.Cout = w.Cout; t.passes = passes;
-    t.in0_hi = s_hi + in0; t.in0_lo = s_lo + in0; t.in0_C = C0;
-    if (C1 > 0) { t.in1_hi = s_hi + in1; t.in1_lo = s_lo + in1; t.in1_C = C1; }
-    if (out32 == nullptr) { t.out_hi = s_hi + out; t.out_lo = s_lo + out; }
+    __half* lo = lo_of(lvl);
+    t.in0_hi = s_hi + in0; t.in0_lo = lo ? lo + in0 : nullptr; t.in0_C = C0;
+    if (C1 > 0) { t.in1_hi = s_hi + in1; t.in1_lo = lo ? lo + in1 : nullptr; t.in1_C = C1; }
+    if (out32 == nullptr) { t.out_hi = s_hi + out; t.out_lo = lo ? lo + out : nullptr; }
     (void)Cout_t;
     t.relu = relu; t.sigmoid = sig; t.mask = masks + L.mask;
     KG_TRY(tc_conv_prepare(&t));
@@ -929,11 +933,12 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
   for (int l = 3; l >= 0; --l) {
     auto& L = sp.lv[l];
     if (L.HA == 0) continue;
+    __half* lo = lo_of(l);
     if (!L.up.empty()) {
       const size_t ubytes = (size_t)L.HA * L.WA * kSegUpIn[l] * sizeof(__half);
       KG_CUDA_CHECK(cudaMemsetAsync(s_hi + L.U, 0, ubytes, stream));
-      KG_CUDA_CHECK(cudaMemsetAsync(s_lo + L.U, 0, ubytes, stream));
-      KG_TRY(launch_bilinear(s_hi, s_lo, kSegUpIn[l], s_hi, s_lo, kSegUpIn[l], kSegUpIn[l], reinterpret_cast<const ResizeProb*>(dp + o_up[l]),
+      if (lo) KG_CUDA_CHECK(cudaMemsetAsync(lo + L.U, 0, ubytes, stream));
+      KG_TRY(launch_bilinear(s_hi, lo_of(l + 1), kSegUpIn[l], s_hi, lo, kSegUpIn[l], kSegUpIn[l], reinterpret_cast<const ResizeProb*>(dp + o_up[l]),
                              (int)L.up.size(), L.pix_up, stream));
       ++launches;
       const std::string pre = "skip_combine." + std::to_string(l);
@@ -943,10 +948,10 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
     if (L.up.empty()) {   // no conv wrote C_l: clear it so that the gaps read by the next 3x3 conv are zeros
       const size_t cbytes = (size_t)L.HA * L.WA * kSegOut[l] * sizeof(__half);
       KG_CUDA_CHECK(cudaMemsetAsync(s_hi + L.Cc, 0, cbytes, stream));
-      KG_CUDA_CHECK(cudaMemsetAsync(s_lo + L.Cc, 0, cbytes, stream));
+      if (lo) KG_CUDA_CHECK(cudaMemsetAsync(lo + L.Cc, 0, cbytes, stream));
     }
     if (!L.deepest.empty()) {
-      KG_TRY(launch_bilinear(s_hi, s_lo, kFeatC[l], s_hi, s_lo, kSegOut[l], kFeatC[l], reinterpret_cast<const ResizeProb*>(dp + o_deep[l]),
+      KG_TRY(launch_bilinear(s_hi, lo, kFeatC[l], s_hi, lo, kSegOut[l], kFeatC[l], reinterpret_cast<const ResizeProb*>(dp + o_deep[l]),
                              (int)L.deepest.size(), L.pix_deepest, stream));
       ++launches;
     }

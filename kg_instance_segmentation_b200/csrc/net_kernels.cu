@@ -137,59 +137,77 @@ int launch_conv_ffma(const ConvArgs& a, int nprob, int max_pix, cudaStream_t s) 
 // Stem convolutions on the raw image (KGnet.py:139-141 c0_conv.0: 3->64 3x3/s1, KGnet.py:131-133 conv1+bn1: 3->64
 // 7x7/s2), fp32 NCHW in, split-fp16 NHWC out, ReLU fused.  Cin = 3 makes these HBM-bound on the output write, so one
 // thread owns one output pixel and all 64 output channels (128 B contiguous per plane); weights are broadcast from smem.
-template <int K, int STRIDE>
+// PX horizontally adjacent output pixels per thread: every weight float4 fetched from smem feeds 4 * PX FFMAs (the
+// one-pixel version issued one LDS.128 per 4 FFMAs and was bound by that), and the PX pixels share their input columns.
+template <int K, int STRIDE, int PX>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __half* __restrict__ out_hi,
                                                         __half* __restrict__ out_lo, int N, int H, int W, int Ho, int Wo) {
   __shared__ __align__(16) float sw[K * K * 3 * 64];
   for (int e = threadIdx.x; e < K * K * 3 * 64; e += 128) sw[e] = w[e];
   __syncthreads();
-  const long long total = (long long)N * Ho * Wo;
-  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
-  if (p >= total) return;
-  const int ox = (int)(p % Wo);
-  const int oy = (int)((p / Wo) % Ho);
-  const int n = (int)(p / ((long long)Wo * Ho));
+  const int wq = (Wo + PX - 1) / PX;                    // pixel groups per output row
+  const long long total = (long long)N * Ho * wq;
+  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (g >= total) return;
+  const int ox0 = (int)(g % wq) * PX;
+  const int oy = (int)((g / wq) % Ho);
+  const int n = (int)(g / ((long long)wq * Ho));
   constexpr int PAD = K / 2;
-  float acc[64];
+  constexpr int NIN = K + STRIDE * (PX - 1);            // input columns the PX pixels touch in one filter row
+  float acc[PX][64];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) acc[j] = __ldg(bias + j);
+  for (int q = 0; q < PX; ++q)
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[q][j] = __ldg(bias + j);
   const float* xn = x + (long long)n * 3 * H * W;
+  const int ix0 = ox0 * STRIDE - PAD;
   for (int r = 0; r < K; ++r) {
     const int iy = oy * STRIDE - PAD + r;
     if (iy < 0 || iy >= H) continue;
-    for (int s = 0; s < K; ++s) {
-      const int ix = ox * STRIDE - PAD + s;
-      if (ix < 0 || ix >= W) continue;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v = __ldg(xn + ((long long)c * H + iy) * W + ix);
+    for (int c = 0; c < 3; ++c) {
+      float in[NIN];
+      const float* row = xn + ((long long)c * H + iy) * W;
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) { const int ix = ix0 + i; in[i] = (ix >= 0 && ix < W) ? __ldg(row + ix) : 0.f; }
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
         const float4* wr = reinterpret_cast<const float4*>(&sw[((r * K + s) * 3 + c) * 64]);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 w4 = wr[j];
-          acc[4 * j] = fmaf(v, w4.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+#pragma unroll
+          for (int q = 0; q < PX; ++q) {
+            const float v = in[s + q * STRIDE];
+            acc[q][4 * j] = fmaf(v, w4.x, acc[q][4 * j]); acc[q][4 * j + 1] = fmaf(v, w4.y, acc[q][4 * j + 1]);
+            acc[q][4 * j + 2] = fmaf(v, w4.z, acc[q][4 * j + 2]); acc[q][4 * j + 3] = fmaf(v, w4.w, acc[q][4 * j + 3]);
+          }
         }
       }
     }
   }
-  uint4* oh = reinterpret_cast<uint4*>(out_hi + p * 64);
-  uint4* ol = reinterpret_cast<uint4*>(out_lo + p * 64);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    uint4 h4, l4;
-    __half2* hh = reinterpret_cast<__half2*>(&h4);
-    __half2* ll = reinterpret_cast<__half2*>(&l4);
+  for (int q = 0; q < PX; ++q) {
+    if (ox0 + q >= Wo) break;
+    const long long p = ((long long)n * Ho + oy) * Wo + ox0 + q;
+    uint4* oh = reinterpret_cast<uint4*>(out_hi + p * 64);
+    uint4* ol = reinterpret_cast<uint4*>(out_lo + p * 64);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = fminf(fmaxf(acc[q * 8 + 2 * e], 0.f), 65504.f), b = fminf(fmaxf(acc[q * 8 + 2 * e + 1], 0.f), 65504.f);
-      const __half2 h = __floats2half2_rn(a, b);
-      const float2 hf = __half22float2(h);
-      hh[e] = h;
-      ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+    for (int k = 0; k < 8; ++k) {
+      uint4 h4, l4;
+      __half2* hh = reinterpret_cast<__half2*>(&h4);
+      __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = fminf(fmaxf(acc[q][k * 8 + 2 * e], 0.f), 65504.f), b = fminf(fmaxf(acc[q][k * 8 + 2 * e + 1], 0.f), 65504.f);
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        hh[e] = h;
+        ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+      }
+      oh[k] = h4; ol[k] = l4;
     }
-    oh[q] = h4; ol[q] = l4;
   }
 }
 
@@ -197,10 +215,11 @@ int launch_stem_conv(const float* x, const float* w, const float* bias, __half* 
                      int stride, cudaStream_t s) {
   const int pad = K / 2;
   const int Ho = (H + 2 * pad - K) / stride + 1, Wo = (W + 2 * pad - K) / stride + 1;
-  const long long total = (long long)N * Ho * Wo;
+  constexpr int PX = 2;
+  const long long total = (long long)N * Ho * ((Wo + PX - 1) / PX);
   const unsigned grid = (unsigned)((total + 127) / 128);
-  if (K == 3 && stride == 1) stem_conv_kernel<3, 1><<<grid, 128, 0, s>>>(x, w, bias, out_hi, out_lo, N, H, W, Ho, Wo);
-  else if (K == 7 && stride == 2) stem_conv_kernel<7, 2><<<grid, 128, 0, s>>>(x, w, bias, out_hi, out_lo, N, H, W, Ho, Wo);
+  if (K == 3 && stride == 1) stem_conv_kernel<3, 1, PX><<<grid, 128, 0, s>>>(x, w, bias, out_hi, out_lo, N, H, W, Ho, Wo);
+  else if (K == 7 && stride == 2) stem_conv_kernel<7, 2, PX><<<grid, 128, 0, s>>>(x, w, bias, out_hi, out_lo, N, H, W, Ho, Wo);
   else { set_error("stem conv: unsupported k=%d stride=%d", K, stride); return KG_ERR_INVALID; }
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;
