@@ -28,6 +28,7 @@ struct ConvW {
   float* d_w = nullptr;
   float* d_b = nullptr;
   TcWeights tc;             // fp16 hi/lo [tap][cout_pad][cin] (tensor-core path)
+  mutable TcShiftPacked shift1, shift3;   // weights packed for the row-GEMM + shift-add kernel (1 / 3 passes), built on first use
 };
 
 struct Tensor {
@@ -52,6 +53,7 @@ struct Op {
   int stage = ST_BACKBONE;
   int tc_passes = 0;                             // 0: CUDA-core kernel; 1 or 3: tensor-core kernel passes
   int tc_index = -1;                             // index into Plan::tc_ops (OP_CONV) / Plan::shift_ops (OP_HEADS2)
+  bool use_shift = false;                        // OP_CONV through the row-GEMM + shift-add kernel (64-channel 3x3 convs)
   int head_scale = -1;                           // OP_HEADS2: the three second-layer head convs of this scale in one launch
 };
 
@@ -357,7 +359,7 @@ static int build_plan(Net* net, int N, int H, int W, int precision) {
     int h1 = b.conv("heads_l1_c" + std::to_string(s), cats[s], -1, 1, 3, true, ST_HEAD1, -1, -1, false, 0, false, 0, 0, true,
                     !fast_heads);
     const int outs[3] = {kHeadOut[0], kHeadOut[1], kHeadOut[2]};
-    if (fast_heads && tc_shift_supported(T(h1).H, T(h1).W, 7, 7, 3, C, 3, outs)) {
+    if (fast_heads && tc_shift_supported(T(h1).H, T(h1).W, 7, 7, 3, C, 3, outs, false)) {
       // the three second-layer head convs of this scale as ONE row-GEMM + shift-add launch (tc_shift.cu)
       Op op; op.type = OP_HEADS2; op.in0 = h1; op.head_scale = s; op.stage = ST_HEAD2; op.C0 = C;
       op.Hout = T(h1).H; op.Wout = T(h1).W; op.tc_passes = 1;
@@ -397,6 +399,22 @@ static int ensure_plan(Net* net, int N, int H, int W, int precision) {
   return build_plan(net, N, H, W, precision);
 }
 
+// One 3x3 conv with 64 (NHWC out) or 1 (fp32 out) output channels as a row-GEMM + shift-add launch, or false if unsupported.
+static bool shift_conv_ok(const ConvW* w, int H, int W, int stride, int pad, int Cin_total, int C1, bool nhwc_out, bool has_res) {
+  if (stride != 1 || C1 != 0 || has_res || w->R != 3 || w->S != 3 || pad != 1) return false;
+  const int no[1] = {w->Cout};
+  return tc_shift_supported(H, W, 3, 3, 1, Cin_total, 1, no, nhwc_out);
+}
+
+static int shift_conv_fill(TcShiftOp* t, const ConvW* w, int N, int H, int W, int Cin, int passes) {
+  t->N = N; t->H = H; t->W = W; t->R = 3; t->S = 3; t->pad = 1; t->Cin = Cin; t->passes = passes; t->n_groups = 1;
+  t->g[0].h_w = w->h_w.data(); t->g[0].d_bias = w->d_b; t->g[0].n_out = w->Cout; t->g[0].in_coff = 0;
+  TcShiftPacked& pk = passes == 3 ? w->shift3 : w->shift1;
+  if (!pk.valid()) KG_TRY(tc_shift_pack(t, &pk));
+  t->packed = pk;
+  return KG_OK;
+}
+
 struct Ptrs {
   char* ws;
   __half* hi(const Tensor& t) const { return reinterpret_cast<__half*>(ws + t.off_hi); }
@@ -428,6 +446,21 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
       }
       if (op.type != OP_CONV || op.tc_passes == 0) continue;
       const Tensor& t0 = p->tensors[op.in0];
+      op.use_shift = false;
+      if (op.out >= 0 && op.out32_ext < 0 && !op.sigmoid && op.in0_coff == 0 && t0.C == op.C0 &&
+          shift_conv_ok(op.w, op.Hout, op.Wout, op.stride, op.pad, op.C0, op.C1, true, op.res >= 0) && op.w->Cout == 64) {
+        TcShiftOp t{};
+        t.in_hi = P.hi(t0); t.in_lo = op.in_single ? nullptr : P.lo(t0); t.in_C = t0.C;
+        const Tensor& to = p->tensors[op.out];
+        t.out_hi = P.hi(to); t.out_lo = op.out_single ? nullptr : P.lo(to); t.relu = op.relu;
+        if (getenv("KG_TC_DEBUG")) fprintf(stderr, "[op %d %s] ", (int)(&op - p->ops.data()), op.w->name.c_str());
+        KG_TRY(shift_conv_fill(&t, op.w, p->N, op.Hout, op.Wout, op.C0, op.tc_passes));
+        KG_TRY(tc_shift_prepare(&t));
+        op.use_shift = true;
+        op.tc_index = (int)p->shift_ops.size();
+        p->shift_ops.push_back(t);
+        continue;
+      }
       TcConvOp t{};
       t.w = &op.w->tc; t.bias = op.w->d_b;
       t.N = p->N; t.H = op.Hout; t.W = op.Wout; t.R = op.w->R; t.S = op.w->S; t.pad = op.pad;
@@ -456,6 +489,11 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
       case OP_CONV: {
         if (op.tc_passes == 0 && !per_op) ts.restage(ST_STEM);   // stage 8 collects every CUDA-core conv, 9..12 are tensor-core only
         float* out32 = op.out32_ext >= 0 ? ext[op.out32_ext] : nullptr;
+        if (op.tc_passes > 0 && op.use_shift) {
+          KG_TRY(tc_shift_launch(&p->shift_ops[op.tc_index], nullptr, stream));
+          ++launches;
+          break;
+        }
         if (op.tc_passes > 0) {
           KG_TRY(tc_conv_launch(&p->tc_ops[op.tc_index], out32, stream));
           ++launches;
@@ -917,10 +955,22 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
     const int lvl = (int)(&L - &sp.lv[0]);
     const int passes = lvl < one_pass_levels ? 1 : 3;
     const ConvW& w = net->convs.at(wname);
+    __half* lo = lo_of(lvl);
+    if (shift_conv_ok(&w, L.HA, L.WA, 1, w.R / 2, C0, C1, out32 == nullptr, false) && (w.Cout == 64 || w.Cout == 1)) {
+      TcShiftOp t{};
+      t.in_hi = s_hi + in0; t.in_lo = lo ? lo + in0 : nullptr; t.in_C = C0;
+      if (out32 == nullptr) { t.out_hi = s_hi + out; t.out_lo = lo ? lo + out : nullptr; t.mask = masks + L.mask; }
+      t.relu = relu; t.g[0].sigmoid = sig;
+      KG_TRY(shift_conv_fill(&t, &w, 1, L.HA, L.WA, C0, passes));
+      t.g[0].sigmoid = sig;
+      KG_TRY(tc_shift_prepare(&t));
+      ++launches;
+      float* outs[1] = {out32};
+      return tc_shift_launch(&t, outs, stream);
+    }
     TcConvOp t{};
     t.w = &w.tc; t.bias = w.d_b; t.N = 1; t.H = L.HA; t.W = L.WA; t.R = w.R; t.S = w.S; t.pad = w.R / 2;
     t.C0 = C0; t.C1 = C1; t.Cout = w.Cout; t.passes = passes;
-    __half* lo = lo_of(lvl);
     t.in0_hi = s_hi + in0; t.in0_lo = lo ? lo + in0 : nullptr; t.in0_C = C0;
     if (C1 > 0) { t.in1_hi = s_hi + in1; t.in1_lo = lo ? lo + in1 : nullptr; t.in1_C = C1; }
     if (out32 == nullptr) { t.out_hi = s_hi + out; t.out_lo = lo ? lo + out : nullptr; }
@@ -967,7 +1017,8 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
 static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R, int S,
                        int stride, int pad, int relu, const float* d_res, int mode, float* d_y, cudaStream_t stream) {
   KG_REQUIRE(d_x && h_w && d_y && N > 0 && Cin > 0 && Cout > 0, "kg_conv2d_nchw: bad arguments");
-  KG_REQUIRE(mode == 0 || mode == 1 || mode == 3, "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 or 3 (tensor-core passes)");
+  KG_REQUIRE(mode == 0 || mode == 1 || mode == 3 || mode == 11 || mode == 13,
+             "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 / 3 (tensor-core passes) or 11 / 13 (row-GEMM + shift-add kernel, 1 / 3 passes)");
   Net tmp;
   KG_TRY(set_conv(&tmp, "c", h_w, Cout, Cin, R, S, h_bias, nullptr, nullptr, nullptr, nullptr, 0.0));
   ConvW& w = tmp.convs.at("c");
@@ -999,6 +1050,22 @@ static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const flo
       a.stride = stride; a.pad = pad; a.out_hi = yh; a.out_lo = yl; a.out_ps = Cout; a.res_hi = rh; a.res_lo = rl; a.res_ps = Cout;
       a.relu = relu; a.probs = d_probs;
       if ((rc = launch_conv_ffma(a, N, Ho * Wo, stream)) != KG_OK) break;
+    } else if (mode >= 10) {
+      const bool nhwc = Cout != 1;
+      if (d_res != nullptr || !shift_conv_ok(&w, Ho, Wo, stride, pad, Cin, 0, nhwc, false)) {
+        set_error("kg_conv2d_nchw: shape not supported by the shift-add kernel"); rc = KG_ERR_INVALID; break;
+      }
+      TcShiftOp t{};
+      t.in_hi = xh; t.in_lo = xl; t.in_C = Cin; t.relu = relu != 0;
+      if (nhwc) { t.out_hi = yh; t.out_lo = yl; }
+      if ((rc = shift_conv_fill(&t, &w, N, Ho, Wo, Cin, mode - 10)) != KG_OK) break;
+      if ((rc = tc_shift_prepare(&t)) != KG_OK) break;
+      float* outs[1] = {d_y};
+      if ((rc = tc_shift_launch(&t, outs, stream)) != KG_OK) break;
+      if (!nhwc) {
+        if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("kg_conv2d_nchw: %s", cudaGetErrorString(cudaGetLastError())); rc = KG_ERR_CUDA; }
+        break;
+      }
     } else {
       if ((stride != 1 && stride != 2) || !tc_layer_supported(Cin, Cout, R, S) || Cout % 16 != 0 || 2 * pad != R - 1 || R != S) {
         set_error("kg_conv2d_nchw: shape not supported by the tensor-core path"); rc = KG_ERR_INVALID; break;
@@ -1025,7 +1092,7 @@ static int heads_l2_nchw(const float* d_x, int N, int Cin, int H, int W, const f
                          float* const* d_y, cudaStream_t stream) {
   KG_REQUIRE(d_x && h_w && h_bias && d_y && N > 0 && Cin > 0, "kg_heads_l2_nchw: bad arguments");
   const int outs[3] = {kHeadOut[0], kHeadOut[1], kHeadOut[2]};
-  if (!tc_shift_supported(H, W, 7, 7, 3, Cin, 3, outs)) { set_error("kg_heads_l2_nchw: shape not supported by the shift-add kernel"); return KG_ERR_INVALID; }
+  if (!tc_shift_supported(H, W, 7, 7, 3, Cin, 3, outs, false)) { set_error("kg_heads_l2_nchw: shape not supported by the shift-add kernel"); return KG_ERR_INVALID; }
   Net tmp;
   const size_t in_e = (size_t)N * H * W * 3 * Cin;
   __half* xh = nullptr;

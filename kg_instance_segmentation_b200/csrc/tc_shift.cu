@@ -34,19 +34,22 @@ constexpr int SH_THREADS = 192;
 constexpr int SH_MAX_UNITS = 6, SH_MAX_TAPS = 8, SH_MAX_CHUNKS = 16;
 constexpr int SH_BK = 64;
 constexpr int SH_A_TILE = 128 * SH_BK * 2;   // 16 KiB
-constexpr int SH_MAX_N = 160;                // rows of one weight slab (N of one MMA)
+constexpr int SH_MAX_N = 192;                // rows of one weight slab (N of one MMA)
 constexpr int SH_MAX_SMEM = 227 * 1024;
 
 struct ShGroup { const float* bias; float* out32; int in_coff; float inv_scale; int sigmoid; };
 struct ShParams {
-  CUtensorMap a_map;
-  CUtensorMap w_map[SH_MAX_UNITS];
+  CUtensorMap a_map[2];                       // activation planes (hi, lo)
+  CUtensorMap w_map[SH_MAX_UNITS][2];         // weight slab of each unit, planes (hi, lo)
   ShGroup grp[SH_MAX_GROUPS];
+  __half* out_hi; __half* out_lo;             // NHWC output mode (conv 0)
+  const uint8_t* mask;
+  int relu;
   int N, H, W, pad, kchunks;
   int BW, BH, tiles_x, rows_y, num_work;
   int row_mode, RB;
   int NS;
-  unsigned slot_bytes, tmem_cols;
+  unsigned slot_bytes, w_slab, tmem_cols;     // w_slab: bytes reserved per weight plane inside a slot
 };
 
 // Compile-time geometry of one fused launch: up to three convs with O0 / O1 / O2 output channels, TAPS x TAPS filters.
@@ -96,11 +99,15 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int O0, int O1, int O2, int TAPS>
+// OUTMODE 0: fp32 NCHW per conv (+sigmoid); OUTMODE 1: conv 0 -> split-fp16 NHWC (+ReLU, +mask)
+template <int O0, int O1, int O2, int TAPS, int PASSES, int OUTMODE>
 __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_constant__ ShParams p) {
   using Cfg = ShCfg<O0, O1, O2, TAPS>;
   static_assert(Cfg::linear(), "tap columns must be linear");
-  constexpr int NU = Cfg::NU, NG = Cfg::NG, RS = Cfg::RS;
+  static_assert(OUTMODE == 0 || (Cfg::NG == 1 && O0 % 8 == 0), "NHWC output: one conv, Cout a multiple of 8");
+  constexpr int NU = Cfg::NU, NG = Cfg::NG, RS = Cfg::RS, COLS = Cfg::COLS;
+  constexpr int NPL = PASSES == 3 ? 2 : 1;
+  constexpr int ACC = 2 * COLS <= 512 ? 2 : 1;               // TMEM accumulator sets (2: epilogue of tile i overlaps the MMAs of tile i+1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t smem0 = (smem_base + 1023u) & ~1023u;
@@ -109,17 +116,24 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
   const uint32_t bars = ring + (uint32_t)p.NS * p.slot_bytes;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (p.NS + s); };
-  const uint32_t tmem_full = bars + 16u * p.NS, tmem_empty = tmem_full + 8u, tmem_slot = tmem_full + 16u;
+  const uint32_t tbar = bars + 16u * p.NS;
+  auto tmem_full = [&](int a) { return tbar + 8u * a; };
+  auto tmem_empty = [&](int a) { return tbar + 16u + 8u * a; };
+  const uint32_t tmem_slot = tbar + 32u;
   float* buf = reinterpret_cast<float*>(smem_raw + (smem0 - smem_base) + (size_t)p.NS * p.slot_bytes + 16u * p.NS + 64u);
+  const uint32_t w_off = (uint32_t)NPL * SH_A_TILE;          // weight planes follow the activation planes inside a slot
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&p.a_map);
 #pragma unroll
-    for (int u = 0; u < NU; ++u) prefetch_tmap(&p.w_map[u]);
+    for (int pl = 0; pl < NPL; ++pl) {
+      prefetch_tmap(&p.a_map[pl]);
+#pragma unroll
+      for (int u = 0; u < NU; ++u) prefetch_tmap(&p.w_map[u][pl]);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.NS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(tmem_full, 1); mbar_init(tmem_empty, 4);
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -147,13 +161,16 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               constexpr int u = decltype(U)::value;
               constexpr int g = Cfg::u_group(u), wrow = Cfg::u_col(u);
               constexpr bool share = Cfg::u_share(u);
-              constexpr uint32_t tx_bytes = (share ? 0u : (uint32_t)SH_A_TILE) + (uint32_t)Cfg::u_n(u) * 128u;
+              constexpr uint32_t tx_bytes = (uint32_t)NPL * ((share ? 0u : (uint32_t)SH_A_TILE) + (uint32_t)Cfg::u_n(u) * 128u);
               mbar_wait(empty(slot), ph ^ 1u);
               if (leader) {
                 const uint32_t base = ring + (uint32_t)slot * p.slot_bytes;
                 mbar_expect_tx(full(slot), tx_bytes);
-                if (!share) tma_load_4d(base, &p.a_map, p.grp[g].in_coff + ch * SH_BK, tx * p.BW, y0 + r - p.pad, n, full(slot));
-                tma_load_3d(base + SH_A_TILE, &p.w_map[u], ch * SH_BK, wrow, r, full(slot));
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                  if (!share) tma_load_4d(base + (uint32_t)pl * SH_A_TILE, &p.a_map[pl], p.grp[g].in_coff + ch * SH_BK, tx * p.BW, y0 + r - p.pad, n, full(slot));
+                  tma_load_3d(base + w_off + (uint32_t)pl * p.w_slab, &p.w_map[u][pl], ch * SH_BK, wrow, r, full(slot));
+                }
               }
               __syncwarp();
               if (++slot == p.NS) { slot = 0; ph ^= 1u; }
@@ -167,8 +184,11 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
     uint32_t tile_it = 0;
     for (int work = blockIdx.x; work < p.num_work; work += gridDim.x)
       for (int tx = 0; tx < p.tiles_x; ++tx, ++tile_it) {
-        mbar_wait(tmem_empty, (tile_it & 1u) ^ 1u);        // the epilogue has read the previous tile's Z
+        const uint32_t acc = ACC == 2 ? (tile_it & 1u) : 0u;
+        const uint32_t acc_phase = ACC == 2 ? ((tile_it >> 1) & 1u) : (tile_it & 1u);
+        mbar_wait(tmem_empty(acc), acc_phase ^ 1u);          // the epilogue has read this accumulator set
         tc_fence_after();
+        const uint32_t dbase = tmem_base + acc * (uint32_t)COLS;
         for (int r = 0; r < TAPS; ++r)
           for (int ch = 0; ch < p.kchunks; ++ch) {
             const uint32_t accum0 = (r | ch) != 0 ? 1u : 0u;
@@ -182,10 +202,21 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               const uint32_t sbase = ring + (uint32_t)slot * p.slot_bytes;
               const int pslot = slot == 0 ? p.NS - 1 : slot - 1;
               const uint32_t abase = share ? ring + (uint32_t)pslot * p.slot_bytes : sbase;
-              const uint64_t adesc = umma_desc(abase), bdesc = umma_desc(sbase + SH_A_TILE);
+              uint64_t adesc[NPL], bdesc[NPL];
+#pragma unroll
+              for (int pl = 0; pl < NPL; ++pl) {
+                adesc[pl] = umma_desc(abase + (uint32_t)pl * SH_A_TILE);
+                bdesc[pl] = umma_desc(sbase + w_off + (uint32_t)pl * p.w_slab);
+              }
               if (leader) {
 #pragma unroll
-                for (int k = 0; k < SH_BK / 16; ++k) umma_f16(tmem_base + dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k == 0 ? accum0 : 1u);
+                for (int k = 0; k < SH_BK / 16; ++k)
+#pragma unroll
+                  for (int ps = 0; ps < PASSES; ++ps) {
+                    constexpr int kAPl[3] = {0, 1, 0}, kWPl[3] = {0, 0, 1};     // hi*hi, lo*hi, hi*lo
+                    umma_f16(dbase + dcol, adesc[kAPl[ps] % NPL] + (uint64_t)(2 * k), bdesc[kWPl[ps] % NPL] + (uint64_t)(2 * k), idesc,
+                             (k | ps) == 0 ? accum0 : 1u);
+                  }
                 if (share) umma_commit(empty(pslot));        // the shared A tile's slot is released with this unit
                 if (!keep) umma_commit(empty(slot));
               }
@@ -193,14 +224,13 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               if (++slot == p.NS) { slot = 0; ph ^= 1u; }
             });
           }
-        if (leader) umma_commit(tmem_full);
+        if (leader) umma_commit(tmem_full(acc));
         __syncwarp();
       }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31; thread t <-> tile position t =====
     const int quad = warp & 3;
     const int t = quad * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int tj = p.row_mode ? 0 : t / p.BW, txx = p.row_mode ? t : t - tj * p.BW;
     const long long cs = (long long)p.H * p.W;
     uint32_t tile_it = 0;
@@ -208,8 +238,11 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
     for (int work = blockIdx.x; work < p.num_work; work += gridDim.x) {
       const int n = work / p.rows_y, y0 = (work - n * p.rows_y) * p.BH;
       for (int tx = 0; tx < p.tiles_x; ++tx, ++tile_it) {
-        mbar_wait(tmem_full, tile_it & 1u);
+        const uint32_t acc = ACC == 2 ? (tile_it & 1u) : 0u;
+        const uint32_t acc_phase = ACC == 2 ? ((tile_it >> 1) & 1u) : (tile_it & 1u);
+        mbar_wait(tmem_full(acc), acc_phase);
         tc_fence_after();
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)COLS;
         // ---- shift-add: tap s of position q goes to output pixel q - s + pad (everything below is compile-time unrolled) ----
         static_for<0, TAPS>([&](auto Sx) __attribute__((always_inline)) {
           constexpr int s = decltype(Sx)::value;
@@ -218,31 +251,34 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
           else { const int x2 = txx - s + p.pad; valid = x2 >= 0 && x2 < p.BW; L = tj * p.BW + x2; }
           int phys = L + off; if (phys >= p.RB) phys -= p.RB;
           float* row = buf + (valid ? phys : 0) * RS;
-          // conv by conv: TMEM loads -> wait -> all smem loads -> adds -> stores (bounded register footprint)
+          // conv by conv, at most 32 columns at a time: TMEM loads -> wait -> smem loads -> adds -> stores
           static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
             constexpr int g = decltype(Gx)::value;
             constexpr int no = Cfg::n_out(g), b0 = Cfg::bufcol(g);
-            uint32_t raw[Cfg::nchunks(g)][8];
-            {
-              static_for<0, Cfg::nchunks(g)>([&](auto Cx) __attribute__((always_inline)) {
+            constexpr int NB = (no + 31) / 32;               // batches of up to 32 channels
+            static_for<0, NB>([&](auto Bx) __attribute__((always_inline)) {
+              constexpr int bb = decltype(Bx)::value;
+              constexpr int c_lo = bb * 32, c_n = no - c_lo < 32 ? no - c_lo : 32, nch = (c_n + 7) / 8;
+              uint32_t raw[nch][8];
+              static_for<0, nch>([&](auto Cx) __attribute__((always_inline)) {
                 constexpr int c = decltype(Cx)::value;
-                constexpr uint32_t col = (uint32_t)(Cfg::col0(g) + Cfg::stride(g) * s + 8 * c);
+                constexpr uint32_t col = (uint32_t)(Cfg::col0(g) + Cfg::stride(g) * s + c_lo + 8 * c);
                 tmem_ld8_nowait(lane_addr + col, raw[c]);
               });
-            }
-            tmem_ld_wait();
-            if (s == TAPS - 1 && g == NG - 1) {              // Z fully read: hand the accumulators back to the MMA issuer
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
-            }
-            if (valid) {
-              float cur[no];
+              tmem_ld_wait();
+              if (s == TAPS - 1 && g == NG - 1 && bb == NB - 1) {   // Z fully read: hand the accumulators back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
+              }
+              if (valid) {
+                float cur[c_n];
 #pragma unroll
-              for (int e = 0; e < no; ++e) cur[e] = row[b0 + e];        // all loads first: the smem latency is paid once
+                for (int e = 0; e < c_n; ++e) cur[e] = row[b0 + c_lo + e];        // all loads first: the smem latency is paid once
 #pragma unroll
-              for (int e = 0; e < no; ++e) row[b0 + e] = cur[e] + __uint_as_float(raw[e / 8][e % 8]);
-            }
+                for (int e = 0; e < c_n; ++e) row[b0 + c_lo + e] = cur[e] + __uint_as_float(raw[e / 8][e % 8]);
+              }
+            });
           });
           epi_bar();
         });
@@ -255,26 +291,61 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
           int y, x; bool inside;
           if (p.row_mode) { y = y0; x = tx * 128 + L - p.pad; inside = x >= 0 && x < p.W; }
           else { const int jj = L / p.BW; y = y0 + jj; x = L - jj * p.BW; inside = y < p.H; }
-          static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
-            constexpr int g = decltype(Gx)::value;
-            constexpr int no = Cfg::n_out(g), b0 = Cfg::bufcol(g);
-            float v[no];
+          if (OUTMODE == 0) {
+            static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
+              constexpr int g = decltype(Gx)::value;
+              constexpr int no = Cfg::n_out(g), b0 = Cfg::bufcol(g);
+              float v[no];
 #pragma unroll
-            for (int e = 0; e < no; ++e) v[e] = row[b0 + e];
+              for (int e = 0; e < no; ++e) v[e] = row[b0 + e];
 #pragma unroll
-            for (int e = 0; e < no; ++e) row[b0 + e] = 0.f;
-            if (inside) {
-              const ShGroup& G = p.grp[g];
-              float* dst = G.out32 + ((long long)n * no * p.H + y) * p.W + x;
+              for (int e = 0; e < no; ++e) row[b0 + e] = 0.f;
+              if (inside) {
+                const ShGroup& G = p.grp[g];
+                float* dst = G.out32 + ((long long)n * no * p.H + y) * p.W + x;
 #pragma unroll
-              for (int co = 0; co < no; ++co) {
-                float o = v[co] * G.inv_scale + __ldg(G.bias + co);
-                if (G.sigmoid) o = 1.f / (1.f + expf(-o));
-                *dst = o;
-                dst += cs;
+                for (int co = 0; co < no; ++co) {
+                  float o = fmaf(v[co], G.inv_scale, __ldg(G.bias + co));
+                  if (G.sigmoid) o = 1.f / (1.f + expf(-o));
+                  *dst = o;
+                  dst += cs;
+                }
               }
-            }
-          });
+            });
+          } else {
+            constexpr int no = Cfg::n_out(0);
+            const long long pix = ((long long)n * p.H + y) * p.W + x;
+            const bool keep = inside && (p.mask == nullptr || p.mask[pix] != 0);
+            const ShGroup& G = p.grp[0];
+            static_for<0, no / 8>([&](auto Cx) __attribute__((always_inline)) {
+              constexpr int c0 = decltype(Cx)::value * 8;
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = row[c0 + e];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) row[c0 + e] = 0.f;
+              if (inside) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(G.bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(G.bias + c0 + 4));
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint4 h4, l4;
+                __half2* hh = reinterpret_cast<__half2*>(&h4);
+                __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float a = fmaf(v[2 * e], G.inv_scale, bb[2 * e]), b = fmaf(v[2 * e + 1], G.inv_scale, bb[2 * e + 1]);
+                  if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                  if (!keep) { a = 0.f; b = 0.f; }
+                  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+                  const __half2 h = __floats2half2_rn(a, b);
+                  const float2 hf = __half22float2(h);
+                  hh[e] = h;
+                  ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+                }
+                *reinterpret_cast<uint4*>(p.out_hi + pix * no + c0) = h4;
+                if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * no + c0) = l4;
+              }
+            });
+          }
         }
         if (p.row_mode) { off += 128; if (off >= p.RB) off -= p.RB; }
         epi_bar();
@@ -296,40 +367,42 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// the instantiated configurations: KGnet's second-layer heads (kp 5, short offsets 10, mid offsets 40; 7x7)
-using HeadsCfg = ShCfg<5, 10, 40, 7>;
+// the instantiated configurations
+using HeadsCfg = ShCfg<5, 10, 40, 7>;   // KGnet's second-layer heads: kp 5 (sigmoid), short offsets 10, mid offsets 40; 7x7
+using C64Cfg = ShCfg<64, 0, 0, 3>;      // one 3x3 conv with 64 output channels (c0_conv.2, c1/c2_up_conv, layer1 conv2, mask branch)
+using C1Cfg = ShCfg<1, 0, 0, 3>;        // seg_head.2: 3x3, one output channel
+enum ShKernel { SHK_NONE = -1, SHK_HEADS = 0, SHK_C64, SHK_C1 };
 
-bool tc_shift_supported(int H, int W, int R, int S, int pad, int Cin, int n_groups, const int* n_out) {
+static ShKernel pick_kernel(int R, int S, int n_groups, const int* n_out, bool nhwc_out) {
+  if (R != S) return SHK_NONE;
+  if (S == 7 && n_groups == 3 && n_out[0] == 5 && n_out[1] == 10 && n_out[2] == 40 && !nhwc_out) return SHK_HEADS;
+  if (S == 3 && n_groups == 1 && n_out[0] == 64 && nhwc_out) return SHK_C64;
+  if (S == 3 && n_groups == 1 && n_out[0] == 1 && !nhwc_out) return SHK_C1;
+  return SHK_NONE;
+}
+
+bool tc_shift_supported(int H, int W, int R, int S, int pad, int Cin, int n_groups, const int* n_out, bool nhwc_out) {
   if (!tc_available()) return false;
   const char* off = getenv("KG_TC_SHIFT");
   if (off && off[0] == '0') return false;
-  if (H < 1 || R != S || 2 * pad != S - 1 || Cin % SH_BK != 0) return false;
+  if (H < 1 || 2 * pad != S - 1 || Cin % SH_BK != 0 || n_groups < 1 || n_groups > SH_MAX_GROUPS) return false;
   if (!((W >= 128 && W % 128 == 0) || (W >= 8 && W < 128 && is_pow2(W)))) return false;
-  return S == 7 && n_groups == 3 && n_out[0] == 5 && n_out[1] == 10 && n_out[2] == 40;
+  const ShKernel k = pick_kernel(R, S, n_groups, n_out, nhwc_out);
+  if (k == SHK_C64 || k == SHK_C1) { const char* c = getenv("KG_TC_SHIFT_CONV"); if (c && c[0] == '0') return false; }
+  return k != SHK_NONE;
 }
 
 template <class Cfg>
-static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
-  std::shared_ptr<ShParams> sp(new ShParams());
-  ShParams& p = *sp;
-  memset(&p, 0, sizeof(p));
-  p.N = op->N; p.H = op->H; p.W = op->W; p.pad = op->pad; p.kchunks = op->Cin / SH_BK;
-  p.row_mode = op->W >= 128 ? 1 : 0;
-  p.BW = p.row_mode ? 128 : op->W; p.BH = 128 / p.BW;
-  p.tiles_x = p.row_mode ? op->W / 128 : 1;
-  p.rows_y = ceil_div(op->H, p.BH);
-  p.num_work = op->N * p.rows_y;
-  p.RB = p.row_mode ? 128 + 2 * op->pad : 128;
+static int shift_pack_t(const TcShiftOp* op, TcShiftPacked* out) {
   const int rows = Cfg::COLS, S = op->S, R = op->R;
-  unsigned tc = 32;
-  while (tc < (unsigned)Cfg::COLS) tc *= 2;
-  p.tmem_cols = tc;
-  // packed weights [R][rows][Cin] fp16: row of (conv g, tap s, channel co) = col0(g) + s * stride(g) + co; each conv is scaled
-  // by a power of two so that small weights stay in fp16's normal range (undone by inv_scale in the epilogue)
-  std::vector<__half> hw((size_t)R * rows * op->Cin, __float2half_rn(0.f));
+  const size_t ne = (size_t)R * rows * op->Cin;
+  std::vector<__half> hi(ne, __float2half_rn(0.f)), lo;
+  if (op->passes == 3) lo.assign(ne, __float2half_rn(0.f));
+  // row of (conv g, tap s, channel co) = col0(g) + s * stride(g) + co; each conv is scaled by a power of two so that small
+  // weights stay in fp16's normal range (undone by inv_scale in the epilogue)
   for (int g = 0; g < Cfg::NG; ++g) {
     const TcShiftGroup& G = op->g[g];
-    KG_REQUIRE(G.h_w && G.d_bias && G.n_out == Cfg::n_out(g), "tc_shift_prepare: conv %d: null weights / bias or unexpected Cout", g);
+    KG_REQUIRE(G.h_w && G.n_out == Cfg::n_out(g), "tc_shift_pack: conv %d: null weights or unexpected Cout", g);
     float mx = 0.f;
     const size_t nw = (size_t)R * S * op->Cin * G.n_out;
     for (size_t i = 0; i < nw; ++i) mx = fmaxf(mx, fabsf(G.h_w[i]));
@@ -337,40 +410,84 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
     if (mx > 0.f && std::isfinite(mx)) { int ex; frexpf(mx, &ex); e = 10 - ex; }
     e = std::max(-40, std::min(40, e));
     const float scale = ldexpf(1.f, e);
-    ShGroup& D = p.grp[g];
-    D.bias = G.d_bias; D.in_coff = G.in_coff; D.sigmoid = G.sigmoid ? 1 : 0; D.inv_scale = ldexpf(1.f, -e);
+    out->inv_scale[g] = ldexpf(1.f, -e);
     for (int r = 0; r < R; ++r)
       for (int t = 0; t < S; ++t)
         for (int ci = 0; ci < op->Cin; ++ci)
-          for (int co = 0; co < G.n_out; ++co)
-            hw[((size_t)r * rows + Cfg::col0(g) + t * Cfg::stride(g) + co) * op->Cin + ci] =
-                __float2half_rn(G.h_w[(((size_t)r * S + t) * op->Cin + ci) * G.n_out + co] * scale);
+          for (int co = 0; co < G.n_out; ++co) {
+            const float v = G.h_w[(((size_t)r * S + t) * op->Cin + ci) * G.n_out + co] * scale;
+            const size_t o = ((size_t)r * rows + Cfg::col0(g) + t * Cfg::stride(g) + co) * op->Cin + ci;
+            const __half h = __float2half_rn(v);
+            hi[o] = h;
+            if (op->passes == 3) lo[o] = __float2half_rn(v - __half2float(h));
+          }
   }
-  __half* d_w = nullptr;
-  KG_CUDA_CHECK(cudaMalloc(&d_w, hw.size() * sizeof(__half)));
-  op->d_weights = std::shared_ptr<void>(d_w, [](void* q) { cudaFree(q); });
-  KG_CUDA_CHECK(cudaMemcpy(d_w, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice));
-  {
+  __half* d = nullptr;
+  KG_CUDA_CHECK(cudaMalloc(&d, ne * sizeof(__half)));
+  out->d_hi = std::shared_ptr<void>(d, [](void* q) { cudaFree(q); });
+  KG_CUDA_CHECK(cudaMemcpy(d, hi.data(), ne * sizeof(__half), cudaMemcpyHostToDevice));
+  if (op->passes == 3) {
+    KG_CUDA_CHECK(cudaMalloc(&d, ne * sizeof(__half)));
+    out->d_lo = std::shared_ptr<void>(d, [](void* q) { cudaFree(q); });
+    KG_CUDA_CHECK(cudaMemcpy(d, lo.data(), ne * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  out->passes = op->passes;
+  return KG_OK;
+}
+
+template <class Cfg>
+static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
+  std::shared_ptr<ShParams> sp(new ShParams());
+  ShParams& p = *sp;
+  memset(&p, 0, sizeof(p));
+  const int NPL = op->passes == 3 ? 2 : 1;
+  p.N = op->N; p.H = op->H; p.W = op->W; p.pad = op->pad; p.kchunks = op->Cin / SH_BK;
+  p.row_mode = op->W >= 128 ? 1 : 0;
+  p.BW = p.row_mode ? 128 : op->W; p.BH = 128 / p.BW;
+  p.tiles_x = p.row_mode ? op->W / 128 : 1;
+  p.rows_y = ceil_div(op->H, p.BH);
+  p.num_work = op->N * p.rows_y;
+  p.RB = p.row_mode ? 128 + 2 * op->pad : 128;
+  p.out_hi = op->out_hi; p.out_lo = op->out_lo; p.mask = op->mask; p.relu = op->relu ? 1 : 0;
+  const int rows = Cfg::COLS, R = op->R;
+  const int acc_sets = 2 * Cfg::COLS <= 512 ? 2 : 1;
+  unsigned tc = 32;
+  while (tc < (unsigned)(acc_sets * Cfg::COLS)) tc *= 2;
+  p.tmem_cols = tc;
+  if (!op->packed.valid() || op->packed.passes != op->passes) KG_TRY(shift_pack_t<Cfg>(op, &op->packed));
+  for (int g = 0; g < Cfg::NG; ++g) {
+    const TcShiftGroup& G = op->g[g];
+    KG_REQUIRE(G.d_bias && G.n_out == Cfg::n_out(g), "tc_shift_prepare: conv %d: null bias or unexpected Cout", g);
+    ShGroup& D = p.grp[g];
+    D.bias = G.d_bias; D.in_coff = G.in_coff; D.sigmoid = G.sigmoid ? 1 : 0; D.inv_scale = op->packed.inv_scale[g];
+  }
+  for (int pl = 0; pl < NPL; ++pl) {
+    const __half* base = pl == 0 ? op->in_hi : op->in_lo;
+    KG_REQUIRE(base != nullptr, "tc_shift_prepare: input plane %d is null", pl);
     cuuint64_t dims[4] = {(cuuint64_t)op->in_C, (cuuint64_t)op->W, (cuuint64_t)op->H, (cuuint64_t)op->N};
     cuuint64_t strides[3] = {(cuuint64_t)op->in_C * 2, (cuuint64_t)op->W * op->in_C * 2, (cuuint64_t)op->H * op->W * op->in_C * 2};
     cuuint32_t box[4] = {(cuuint32_t)SH_BK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = encode(&p.a_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)op->in_hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(&p.a_map[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tc_shift_prepare: cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return KG_ERR_CUDA; }
   }
   int maxN = 0;
   for (int u = 0; u < Cfg::NU; ++u) {
     maxN = std::max(maxN, Cfg::u_n(u));
-    cuuint64_t dims[3] = {(cuuint64_t)op->Cin, (cuuint64_t)rows, (cuuint64_t)R};
-    cuuint64_t strides[2] = {(cuuint64_t)op->Cin * 2, (cuuint64_t)rows * op->Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)SH_BK, (cuuint32_t)Cfg::u_n(u), 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode(&p.w_map[u], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)d_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("tc_shift_prepare: cuTensorMapEncodeTiled(weights, unit %d) failed: %d", u, (int)r); return KG_ERR_CUDA; }
+    for (int pl = 0; pl < NPL; ++pl) {
+      void* base = pl == 0 ? op->packed.d_hi.get() : op->packed.d_lo.get();
+      cuuint64_t dims[3] = {(cuuint64_t)op->Cin, (cuuint64_t)rows, (cuuint64_t)R};
+      cuuint64_t strides[2] = {(cuuint64_t)op->Cin * 2, (cuuint64_t)rows * op->Cin * 2};
+      cuuint32_t box[3] = {(cuuint32_t)SH_BK, (cuuint32_t)Cfg::u_n(u), 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = encode(&p.w_map[u][pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("tc_shift_prepare: cuTensorMapEncodeTiled(weights, unit %d) failed: %d", u, (int)r); return KG_ERR_CUDA; }
+    }
   }
-  p.slot_bytes = (unsigned)(SH_A_TILE + align_up((size_t)maxN * 128, 1024));
+  p.w_slab = (unsigned)align_up((size_t)maxN * 128, 1024);
+  p.slot_bytes = (unsigned)NPL * (SH_A_TILE + p.w_slab);
   const size_t buf_bytes = (size_t)p.RB * Cfg::RS * sizeof(float);
   const size_t fixed = 1024 + 16 * 16 + 64 + buf_bytes + 64;
   int ns = (int)((SH_MAX_SMEM - fixed) / p.slot_bytes);
@@ -381,35 +498,76 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   op->grid = (unsigned)std::min(p.num_work, tc_num_sms());
   op->params = sp;
   if (getenv("KG_TC_DEBUG"))
-    fprintf(stderr, "[tc_shift] N%d %dx%d Cin%d k%dx%d | units%d cols%d BW%d BH%d tiles_x%d work%d NS%d slot%u RB%d RS%d smem%u tmem%u\n",
-            op->N, op->H, op->W, op->Cin, R, S, Cfg::NU, Cfg::COLS, p.BW, p.BH, p.tiles_x, p.num_work, p.NS, p.slot_bytes, p.RB, Cfg::RS,
-            op->smem_bytes, p.tmem_cols);
+    fprintf(stderr, "[tc_shift] N%d %dx%d Cin%d k%dx%d passes%d | units%d cols%d acc%d BW%d BH%d tiles_x%d work%d NS%d slot%u RB%d RS%d smem%u tmem%u\n",
+            op->N, op->H, op->W, op->Cin, R, op->S, op->passes, Cfg::NU, Cfg::COLS, acc_sets, p.BW, p.BH, p.tiles_x, p.num_work, p.NS, p.slot_bytes, p.RB,
+            Cfg::RS, op->smem_bytes, p.tmem_cols);
   return KG_OK;
+}
+
+static ShKernel kernel_of(const TcShiftOp* op) {
+  int n_out[SH_MAX_GROUPS] = {0, 0, 0};
+  for (int g = 0; g < op->n_groups && g < SH_MAX_GROUPS; ++g) n_out[g] = op->g[g].n_out;
+  if (!tc_shift_supported(op->H, op->W, op->R, op->S, op->pad, op->Cin, op->n_groups, n_out, op->out_hi != nullptr)) return SHK_NONE;
+  return pick_kernel(op->R, op->S, op->n_groups, n_out, op->out_hi != nullptr);
+}
+
+int tc_shift_pack(const TcShiftOp* op, TcShiftPacked* out) {
+  KG_REQUIRE(op && out, "tc_shift_pack: null argument");
+  switch (kernel_of(op)) {
+    case SHK_HEADS: return shift_pack_t<HeadsCfg>(op, out);
+    case SHK_C64: return shift_pack_t<C64Cfg>(op, out);
+    case SHK_C1: return shift_pack_t<C1Cfg>(op, out);
+    default: set_error("tc_shift_pack: unsupported shape"); return KG_ERR_INVALID;
+  }
 }
 
 int tc_shift_prepare(TcShiftOp* op) {
   KG_REQUIRE(op != nullptr, "tc_shift_prepare: null op");
-  int n_out[SH_MAX_GROUPS] = {0, 0, 0};
-  for (int g = 0; g < op->n_groups && g < SH_MAX_GROUPS; ++g) n_out[g] = op->g[g].n_out;
-  KG_REQUIRE(tc_shift_supported(op->H, op->W, op->R, op->S, op->pad, op->Cin, op->n_groups, n_out), "tc_shift_prepare: unsupported shape");
+  KG_REQUIRE(op->passes == 1 || op->passes == 3, "tc_shift_prepare: passes=%d", op->passes);
+  const ShKernel k = kernel_of(op);
+  KG_REQUIRE(k != SHK_NONE, "tc_shift_prepare: unsupported shape");
+  KG_REQUIRE(k != SHK_HEADS || op->passes == 1, "tc_shift_prepare: the fused head kernel is single-pass only");
   EncodeTiledFn encode = (EncodeTiledFn)tc_encode_tiled_fn();
   KG_REQUIRE(encode != nullptr, "tc_shift_prepare: cuTensorMapEncodeTiled unavailable");
   static bool attr_set = false;
   if (!attr_set) {
-    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<5, 10, 40, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
+    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<5, 10, 40, 7, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
+    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<64, 0, 0, 3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
+    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<64, 0, 0, 3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
+    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<1, 0, 0, 3, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
+    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<1, 0, 0, 3, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
     attr_set = true;
   }
-  return shift_prepare_t<HeadsCfg>(op, encode);
+  switch (k) {
+    case SHK_HEADS: return shift_prepare_t<HeadsCfg>(op, encode);
+    case SHK_C64: return shift_prepare_t<C64Cfg>(op, encode);
+    default: return shift_prepare_t<C1Cfg>(op, encode);
+  }
 }
 
 int tc_shift_launch(const TcShiftOp* op, float* const* out32, cudaStream_t stream) {
-  KG_REQUIRE(op && op->params && out32, "tc_shift_launch: op not prepared");
+  KG_REQUIRE(op && op->params, "tc_shift_launch: op not prepared");
   ShParams p = *reinterpret_cast<const ShParams*>(op->params.get());
-  for (int g = 0; g < op->n_groups; ++g) {
-    KG_REQUIRE(out32[g] != nullptr, "tc_shift_launch: output %d is null", g);
-    p.grp[g].out32 = out32[g];
+  const bool nhwc = op->out_hi != nullptr;
+  if (!nhwc) {
+    KG_REQUIRE(out32 != nullptr, "tc_shift_launch: null outputs");
+    for (int g = 0; g < op->n_groups; ++g) {
+      KG_REQUIRE(out32[g] != nullptr, "tc_shift_launch: output %d is null", g);
+      p.grp[g].out32 = out32[g];
+    }
   }
-  tc_shift_kernel<5, 10, 40, 7><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
+  switch (kernel_of(op)) {
+    case SHK_HEADS: tc_shift_kernel<5, 10, 40, 7, 1, 0><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p); break;
+    case SHK_C64:
+      if (op->passes == 3) tc_shift_kernel<64, 0, 0, 3, 3, 1><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
+      else tc_shift_kernel<64, 0, 0, 3, 1, 1><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
+      break;
+    case SHK_C1:
+      if (op->passes == 3) tc_shift_kernel<1, 0, 0, 3, 3, 0><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
+      else tc_shift_kernel<1, 0, 0, 3, 1, 0><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
+      break;
+    default: set_error("tc_shift_launch: unsupported shape"); return KG_ERR_INVALID;
+  }
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;
 }

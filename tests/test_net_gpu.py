@@ -152,6 +152,29 @@ def test_heads_l2_shift_kernel(case):
         assert err <= 3e-3 * scale + 1e-5, f"head {h}: max err {err} (scale {scale})"
 
 
+SHIFT_CONV_CASES = [  # (N, Cin, H, W, Cout): 3x3 convs through the row-GEMM + shift-add kernel (tc_shift.cu)
+    (1, 64, 7, 512, 64),     # c1_up_conv / c0_conv.2 class, 4 tiles per row
+    (2, 256, 5, 256, 64),    # c2_up_conv class: 4 K chunks, 2 tiles per row
+    (2, 64, 9, 128, 64),     # layer1 conv2 class
+    (1, 64, 12, 64, 64),     # two rows per tile
+    (3, 64, 8, 8, 64),
+    (1, 64, 6, 256, 1),      # seg_head.2: one output channel, fp32 output
+    (1, 64, 10, 32, 1),
+]
+
+
+@pytest.mark.parametrize("case", SHIFT_CONV_CASES)
+@pytest.mark.parametrize("mode", [13, 11])
+def test_conv_shift_kernel(case, mode):
+    N, Cin, H, W, Cout = case
+    x, w, b, pad, r, y = _case(6, N, Cin, H, W, Cout, 3, 1, Cout != 1, False)
+    got = _conv(x, w, b, 1, pad, Cout != 1, None, mode)
+    scale = float(y.abs().max())
+    tol = (2e-4 if mode == 13 else 3e-3) * scale + 1e-5
+    err = float((got - y).abs().max())
+    assert err <= tol, f"max err {err} > {tol}"
+
+
 def _model(precision):
     from kg_instance_segmentation_b200 import KGnet
     sd = O.make_state_dict(seed=0)
