@@ -309,6 +309,10 @@ static void assign_tc(Plan* p, int precision) {
     if (op.C0 % 64 != 0 || (op.C1 % 64) != 0) continue;
     const bool head = op.stage == ST_HEAD1 || op.stage == ST_HEAD2;
     op.tc_passes = (head && precision == 1) ? 1 : 3;
+    // "fast": the three 64-channel 3x3 decoder convs keep split activations but single-plane weights (2 passes).  CPU
+    // emulation (tools/precision_emulate.py, "<group>:w") puts the keypoint-map error at 6-7e-4 with them, 5.8e-4 without.
+    if (precision == 1 && getenv("KG_NO_2PASS") == nullptr &&
+        (w->name == "c0_conv.2" || w->name == "c1_up_conv.0" || w->name == "c2_up_conv.0")) op.tc_passes = 2;
   }
 }
 
@@ -409,7 +413,7 @@ static bool shift_conv_ok(const ConvW* w, int H, int W, int stride, int pad, int
 static int shift_conv_fill(TcShiftOp* t, const ConvW* w, int N, int H, int W, int Cin, int passes) {
   t->N = N; t->H = H; t->W = W; t->R = 3; t->S = 3; t->pad = 1; t->Cin = Cin; t->passes = passes; t->n_groups = 1;
   t->g[0].h_w = w->h_w.data(); t->g[0].d_bias = w->d_b; t->g[0].n_out = w->Cout; t->g[0].in_coff = 0;
-  TcShiftPacked& pk = passes == 3 ? w->shift3 : w->shift1;
+  TcShiftPacked& pk = passes == 3 ? w->shift3 : w->shift1;      // passes 1 and 2 share the hi-only packing
   if (!pk.valid()) KG_TRY(tc_shift_pack(t, &pk));
   t->packed = pk;
   return KG_OK;
@@ -461,6 +465,7 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
         p->shift_ops.push_back(t);
         continue;
       }
+      if (op.tc_passes == 2) op.tc_passes = 3;               // the plain implicit-GEMM kernel has no 2-pass variant
       TcConvOp t{};
       t.w = &op.w->tc; t.bias = op.w->d_b;
       t.N = p->N; t.H = op.Hout; t.W = op.Wout; t.R = op.w->R; t.S = op.w->S; t.pad = op.pad;
@@ -1017,8 +1022,8 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
 static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R, int S,
                        int stride, int pad, int relu, const float* d_res, int mode, float* d_y, cudaStream_t stream) {
   KG_REQUIRE(d_x && h_w && d_y && N > 0 && Cin > 0 && Cout > 0, "kg_conv2d_nchw: bad arguments");
-  KG_REQUIRE(mode == 0 || mode == 1 || mode == 3 || mode == 11 || mode == 13,
-             "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 / 3 (tensor-core passes) or 11 / 13 (row-GEMM + shift-add kernel, 1 / 3 passes)");
+  KG_REQUIRE(mode == 0 || mode == 1 || mode == 3 || mode == 11 || mode == 12 || mode == 13,
+             "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 / 3 (tensor-core passes) or 11 / 12 / 13 (row-GEMM + shift-add kernel, 1 / 2 / 3 passes)");
   Net tmp;
   KG_TRY(set_conv(&tmp, "c", h_w, Cout, Cin, R, S, h_bias, nullptr, nullptr, nullptr, nullptr, 0.0));
   ConvW& w = tmp.convs.at("c");

@@ -50,6 +50,7 @@ struct ShParams {
   int row_mode, RB;
   int NS;
   unsigned slot_bytes, w_slab, tmem_cols;     // w_slab: bytes reserved per weight plane inside a slot
+  unsigned wres_bytes;                        // resident-weights mode: bytes of the weight region in front of the ring
 };
 
 // Compile-time geometry of one fused launch: up to three convs with O0 / O1 / O2 output channels, TAPS x TAPS filters.
@@ -100,48 +101,61 @@ __device__ __forceinline__ void static_for(F&& f) {
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // OUTMODE 0: fp32 NCHW per conv (+sigmoid); OUTMODE 1: conv 0 -> split-fp16 NHWC (+ReLU, +mask)
-template <int O0, int O1, int O2, int TAPS, int PASSES, int OUTMODE>
+// PASSES 1: fp16 x fp16; 2: (hi + lo activations) x hi weights; 3: split-fp16 on both sides (hi*hi + lo*hi + hi*lo).
+// WRES: the whole weight tensor stays resident in shared memory (loaded once per CTA); the ring then carries activations only.
+template <int O0, int O1, int O2, int TAPS, int PASSES, int OUTMODE, bool WRES>
 __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_constant__ ShParams p) {
   using Cfg = ShCfg<O0, O1, O2, TAPS>;
   static_assert(Cfg::linear(), "tap columns must be linear");
   static_assert(OUTMODE == 0 || (Cfg::NG == 1 && O0 % 8 == 0), "NHWC output: one conv, Cout a multiple of 8");
   constexpr int NU = Cfg::NU, NG = Cfg::NG, RS = Cfg::RS, COLS = Cfg::COLS;
-  constexpr int NPL = PASSES == 3 ? 2 : 1;
+  constexpr int NPA = PASSES >= 2 ? 2 : 1;                   // activation planes
+  constexpr int NPW = PASSES == 3 ? 2 : 1;                   // weight planes
+  static_assert(!WRES || NU == 1, "resident weights: single-unit configurations only");
   constexpr int ACC = 2 * COLS <= 512 ? 2 : 1;               // TMEM accumulator sets (2: epilogue of tile i overlaps the MMAs of tile i+1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t smem0 = (smem_base + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ring = smem0;
+  const uint32_t wres = smem0;                               // resident weights: [r][chunk][plane] slabs of w_slab bytes
+  const uint32_t ring = smem0 + (WRES ? p.wres_bytes : 0u);
   const uint32_t bars = ring + (uint32_t)p.NS * p.slot_bytes;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (p.NS + s); };
   const uint32_t tbar = bars + 16u * p.NS;
   auto tmem_full = [&](int a) { return tbar + 8u * a; };
   auto tmem_empty = [&](int a) { return tbar + 16u + 8u * a; };
-  const uint32_t tmem_slot = tbar + 32u;
-  float* buf = reinterpret_cast<float*>(smem_raw + (smem0 - smem_base) + (size_t)p.NS * p.slot_bytes + 16u * p.NS + 64u);
-  const uint32_t w_off = (uint32_t)NPL * SH_A_TILE;          // weight planes follow the activation planes inside a slot
+  const uint32_t wres_bar = tbar + 32u;
+  const uint32_t tmem_slot = tbar + 40u;
+  float* buf = reinterpret_cast<float*>(smem_raw + (smem0 - smem_base) + (WRES ? p.wres_bytes : 0u) + (size_t)p.NS * p.slot_bytes + 16u * p.NS + 64u);
+  const uint32_t w_off = (uint32_t)NPA * SH_A_TILE;          // weight planes follow the activation planes inside a slot
+  float* s_bias = buf + p.RB * RS;                           // biases of all convs (a global load per output pixel stalls the emission)
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
-    for (int pl = 0; pl < NPL; ++pl) {
-      prefetch_tmap(&p.a_map[pl]);
+    for (int pl = 0; pl < NPA; ++pl) prefetch_tmap(&p.a_map[pl]);
+#pragma unroll
+    for (int pl = 0; pl < NPW; ++pl)
 #pragma unroll
       for (int u = 0; u < NU; ++u) prefetch_tmap(&p.w_map[u][pl]);
-    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.NS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
+    mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2)
+  if (warp >= 2) {
     for (int e = threadIdx.x - 64; e < p.RB * RS; e += 128) buf[e] = 0.f;
+    static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
+      constexpr int g = decltype(Gx)::value;
+      for (int e = threadIdx.x - 64; e < Cfg::n_out(g); e += 128) s_bias[Cfg::bufcol(g) + e] = p.grp[g].bias[e];
+    });
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,6 +166,15 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
     // ===== TMA producer =====
     const bool leader = elect_one();
     int slot = 0; uint32_t ph = 0;
+    if (WRES && leader) {                                    // the whole weight tensor, once
+      mbar_expect_tx(wres_bar, (uint32_t)(TAPS * p.kchunks * NPW) * (uint32_t)Cfg::u_n(0) * 128u);
+      for (int r = 0; r < TAPS; ++r)
+        for (int ch = 0; ch < p.kchunks; ++ch)
+#pragma unroll
+          for (int pl = 0; pl < NPW; ++pl)
+            tma_load_3d(wres + (uint32_t)((r * p.kchunks + ch) * NPW + pl) * p.w_slab, &p.w_map[0][pl], ch * SH_BK, 0, r, wres_bar);
+    }
+    __syncwarp();
     for (int work = blockIdx.x; work < p.num_work; work += gridDim.x) {
       const int n = work / p.rows_y, y0 = (work - n * p.rows_y) * p.BH;
       for (int tx = 0; tx < p.tiles_x; ++tx)
@@ -161,15 +184,19 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               constexpr int u = decltype(U)::value;
               constexpr int g = Cfg::u_group(u), wrow = Cfg::u_col(u);
               constexpr bool share = Cfg::u_share(u);
-              constexpr uint32_t tx_bytes = (uint32_t)NPL * ((share ? 0u : (uint32_t)SH_A_TILE) + (uint32_t)Cfg::u_n(u) * 128u);
+              constexpr uint32_t tx_bytes = (uint32_t)NPA * (share ? 0u : (uint32_t)SH_A_TILE) + (WRES ? 0u : (uint32_t)NPW * (uint32_t)Cfg::u_n(u) * 128u);
               mbar_wait(empty(slot), ph ^ 1u);
               if (leader) {
                 const uint32_t base = ring + (uint32_t)slot * p.slot_bytes;
                 mbar_expect_tx(full(slot), tx_bytes);
+                if (!share) {
 #pragma unroll
-                for (int pl = 0; pl < NPL; ++pl) {
-                  if (!share) tma_load_4d(base + (uint32_t)pl * SH_A_TILE, &p.a_map[pl], p.grp[g].in_coff + ch * SH_BK, tx * p.BW, y0 + r - p.pad, n, full(slot));
-                  tma_load_3d(base + w_off + (uint32_t)pl * p.w_slab, &p.w_map[u][pl], ch * SH_BK, wrow, r, full(slot));
+                  for (int pl = 0; pl < NPA; ++pl)
+                    tma_load_4d(base + (uint32_t)pl * SH_A_TILE, &p.a_map[pl], p.grp[g].in_coff + ch * SH_BK, tx * p.BW, y0 + r - p.pad, n, full(slot));
+                }
+                if (!WRES) {
+#pragma unroll
+                  for (int pl = 0; pl < NPW; ++pl) tma_load_3d(base + w_off + (uint32_t)pl * p.w_slab, &p.w_map[u][pl], ch * SH_BK, wrow, r, full(slot));
                 }
               }
               __syncwarp();
@@ -182,6 +209,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
     const bool leader = elect_one();
     int slot = 0; uint32_t ph = 0;
     uint32_t tile_it = 0;
+    if (WRES) { mbar_wait(wres_bar, 0u); tc_fence_after(); }
     for (int work = blockIdx.x; work < p.num_work; work += gridDim.x)
       for (int tx = 0; tx < p.tiles_x; ++tx, ++tile_it) {
         const uint32_t acc = ACC == 2 ? (tile_it & 1u) : 0u;
@@ -202,19 +230,19 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               const uint32_t sbase = ring + (uint32_t)slot * p.slot_bytes;
               const int pslot = slot == 0 ? p.NS - 1 : slot - 1;
               const uint32_t abase = share ? ring + (uint32_t)pslot * p.slot_bytes : sbase;
-              uint64_t adesc[NPL], bdesc[NPL];
+              uint64_t adesc[NPA], bdesc[NPW];
 #pragma unroll
-              for (int pl = 0; pl < NPL; ++pl) {
-                adesc[pl] = umma_desc(abase + (uint32_t)pl * SH_A_TILE);
-                bdesc[pl] = umma_desc(sbase + w_off + (uint32_t)pl * p.w_slab);
-              }
+              for (int pl = 0; pl < NPA; ++pl) adesc[pl] = umma_desc(abase + (uint32_t)pl * SH_A_TILE);
+#pragma unroll
+              for (int pl = 0; pl < NPW; ++pl)
+                bdesc[pl] = umma_desc(WRES ? wres + (uint32_t)((r * p.kchunks + ch) * NPW + pl) * p.w_slab : sbase + w_off + (uint32_t)pl * p.w_slab);
               if (leader) {
 #pragma unroll
                 for (int k = 0; k < SH_BK / 16; ++k)
 #pragma unroll
                   for (int ps = 0; ps < PASSES; ++ps) {
                     constexpr int kAPl[3] = {0, 1, 0}, kWPl[3] = {0, 0, 1};     // hi*hi, lo*hi, hi*lo
-                    umma_f16(dbase + dcol, adesc[kAPl[ps] % NPL] + (uint64_t)(2 * k), bdesc[kWPl[ps] % NPL] + (uint64_t)(2 * k), idesc,
+                    umma_f16(dbase + dcol, adesc[kAPl[ps] % NPA] + (uint64_t)(2 * k), bdesc[kWPl[ps] % NPW] + (uint64_t)(2 * k), idesc,
                              (k | ps) == 0 ? accum0 : 1u);
                   }
                 if (share) umma_commit(empty(pslot));        // the shared A tile's slot is released with this unit
@@ -305,7 +333,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                 float* dst = G.out32 + ((long long)n * no * p.H + y) * p.W + x;
 #pragma unroll
                 for (int co = 0; co < no; ++co) {
-                  float o = fmaf(v[co], G.inv_scale, __ldg(G.bias + co));
+                  float o = fmaf(v[co], G.inv_scale, s_bias[b0 + co]);
                   if (G.sigmoid) o = 1.f / (1.f + expf(-o));
                   *dst = o;
                   dst += cs;
@@ -325,8 +353,9 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
 #pragma unroll
               for (int e = 0; e < 8; ++e) row[c0 + e] = 0.f;
               if (inside) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(G.bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(G.bias + c0 + 4));
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float bb[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bb[e] = s_bias[c0 + e];
                 uint4 h4, l4;
                 __half2* hh = reinterpret_cast<__half2*>(&h4);
                 __half2* ll = reinterpret_cast<__half2*>(&l4);
@@ -440,7 +469,7 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   std::shared_ptr<ShParams> sp(new ShParams());
   ShParams& p = *sp;
   memset(&p, 0, sizeof(p));
-  const int NPL = op->passes == 3 ? 2 : 1;
+  const int NPA = op->passes >= 2 ? 2 : 1, NPW = op->passes == 3 ? 2 : 1;
   p.N = op->N; p.H = op->H; p.W = op->W; p.pad = op->pad; p.kchunks = op->Cin / SH_BK;
   p.row_mode = op->W >= 128 ? 1 : 0;
   p.BW = p.row_mode ? 128 : op->W; p.BH = 128 / p.BW;
@@ -454,14 +483,14 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   unsigned tc = 32;
   while (tc < (unsigned)(acc_sets * Cfg::COLS)) tc *= 2;
   p.tmem_cols = tc;
-  if (!op->packed.valid() || op->packed.passes != op->passes) KG_TRY(shift_pack_t<Cfg>(op, &op->packed));
+  if (!op->packed.valid() || (op->passes == 3 && op->packed.d_lo == nullptr)) KG_TRY(shift_pack_t<Cfg>(op, &op->packed));
   for (int g = 0; g < Cfg::NG; ++g) {
     const TcShiftGroup& G = op->g[g];
     KG_REQUIRE(G.d_bias && G.n_out == Cfg::n_out(g), "tc_shift_prepare: conv %d: null bias or unexpected Cout", g);
     ShGroup& D = p.grp[g];
     D.bias = G.d_bias; D.in_coff = G.in_coff; D.sigmoid = G.sigmoid ? 1 : 0; D.inv_scale = op->packed.inv_scale[g];
   }
-  for (int pl = 0; pl < NPL; ++pl) {
+  for (int pl = 0; pl < NPA; ++pl) {
     const __half* base = pl == 0 ? op->in_hi : op->in_lo;
     KG_REQUIRE(base != nullptr, "tc_shift_prepare: input plane %d is null", pl);
     cuuint64_t dims[4] = {(cuuint64_t)op->in_C, (cuuint64_t)op->W, (cuuint64_t)op->H, (cuuint64_t)op->N};
@@ -475,7 +504,7 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   int maxN = 0;
   for (int u = 0; u < Cfg::NU; ++u) {
     maxN = std::max(maxN, Cfg::u_n(u));
-    for (int pl = 0; pl < NPL; ++pl) {
+    for (int pl = 0; pl < NPW; ++pl) {
       void* base = pl == 0 ? op->packed.d_hi.get() : op->packed.d_lo.get();
       cuuint64_t dims[3] = {(cuuint64_t)op->Cin, (cuuint64_t)rows, (cuuint64_t)R};
       cuuint64_t strides[2] = {(cuuint64_t)op->Cin * 2, (cuuint64_t)rows * op->Cin * 2};
@@ -487,19 +516,24 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
     }
   }
   p.w_slab = (unsigned)align_up((size_t)maxN * 128, 1024);
-  p.slot_bytes = (unsigned)NPL * (SH_A_TILE + p.w_slab);
-  const size_t buf_bytes = (size_t)p.RB * Cfg::RS * sizeof(float);
+  const size_t buf_bytes = ((size_t)p.RB * Cfg::RS + Cfg::NOUT) * sizeof(float);
   const size_t fixed = 1024 + 16 * 16 + 64 + buf_bytes + 64;
-  int ns = (int)((SH_MAX_SMEM - fixed) / p.slot_bytes);
+  // resident weights: the whole [R][chunks][planes] weight tensor stays in smem when it leaves room for >= 3 activation slots
+  const size_t wres_total = (size_t)R * p.kchunks * NPW * p.w_slab;
+  const char* wr = getenv("KG_TC_SHIFT_WRES");
+  op->wres = Cfg::NU == 1 && !(wr && wr[0] == '0') && fixed + wres_total + 3 * (size_t)NPA * SH_A_TILE <= (size_t)SH_MAX_SMEM;
+  p.wres_bytes = op->wres ? (unsigned)wres_total : 0u;
+  p.slot_bytes = (unsigned)(NPA * SH_A_TILE + (op->wres ? 0 : NPW * p.w_slab));
+  int ns = (int)((SH_MAX_SMEM - fixed - p.wres_bytes) / p.slot_bytes);
   if (ns > 8) ns = 8;
   KG_REQUIRE(ns >= 2, "tc_shift_prepare: tile does not fit in shared memory");
   p.NS = ns;
-  op->smem_bytes = (unsigned)(1024 + (size_t)ns * p.slot_bytes + 16 * ns + 64 + buf_bytes + 64);
+  op->smem_bytes = (unsigned)(1024 + p.wres_bytes + (size_t)ns * p.slot_bytes + 16 * ns + 64 + buf_bytes + 64);
   op->grid = (unsigned)std::min(p.num_work, tc_num_sms());
   op->params = sp;
   if (getenv("KG_TC_DEBUG"))
-    fprintf(stderr, "[tc_shift] N%d %dx%d Cin%d k%dx%d passes%d | units%d cols%d acc%d BW%d BH%d tiles_x%d work%d NS%d slot%u RB%d RS%d smem%u tmem%u\n",
-            op->N, op->H, op->W, op->Cin, R, op->S, op->passes, Cfg::NU, Cfg::COLS, acc_sets, p.BW, p.BH, p.tiles_x, p.num_work, p.NS, p.slot_bytes, p.RB,
+    fprintf(stderr, "[tc_shift] N%d %dx%d Cin%d k%dx%d passes%d wres%d | units%d cols%d acc%d BW%d BH%d tiles_x%d work%d NS%d slot%u RB%d RS%d smem%u tmem%u\n",
+            op->N, op->H, op->W, op->Cin, R, op->S, op->passes, (int)op->wres, Cfg::NU, Cfg::COLS, acc_sets, p.BW, p.BH, p.tiles_x, p.num_work, p.NS, p.slot_bytes, p.RB,
             Cfg::RS, op->smem_bytes, p.tmem_cols);
   return KG_OK;
 }
@@ -523,7 +557,7 @@ int tc_shift_pack(const TcShiftOp* op, TcShiftPacked* out) {
 
 int tc_shift_prepare(TcShiftOp* op) {
   KG_REQUIRE(op != nullptr, "tc_shift_prepare: null op");
-  KG_REQUIRE(op->passes == 1 || op->passes == 3, "tc_shift_prepare: passes=%d", op->passes);
+  KG_REQUIRE(op->passes >= 1 && op->passes <= 3, "tc_shift_prepare: passes=%d", op->passes);
   const ShKernel k = kernel_of(op);
   KG_REQUIRE(k != SHK_NONE, "tc_shift_prepare: unsupported shape");
   KG_REQUIRE(k != SHK_HEADS || op->passes == 1, "tc_shift_prepare: the fused head kernel is single-pass only");
@@ -531,11 +565,13 @@ int tc_shift_prepare(TcShiftOp* op) {
   KG_REQUIRE(encode != nullptr, "tc_shift_prepare: cuTensorMapEncodeTiled unavailable");
   static bool attr_set = false;
   if (!attr_set) {
-    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<5, 10, 40, 7, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
-    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<64, 0, 0, 3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
-    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<64, 0, 0, 3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
-    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<1, 0, 0, 3, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
-    KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<1, 0, 0, 3, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM));
+#define KG_SH_ATTR(...) KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM))
+    KG_SH_ATTR(5, 10, 40, 7, 1, 0, false);
+    KG_SH_ATTR(64, 0, 0, 3, 1, 1, false); KG_SH_ATTR(64, 0, 0, 3, 2, 1, false); KG_SH_ATTR(64, 0, 0, 3, 3, 1, false);
+    KG_SH_ATTR(64, 0, 0, 3, 1, 1, true); KG_SH_ATTR(64, 0, 0, 3, 2, 1, true); KG_SH_ATTR(64, 0, 0, 3, 3, 1, true);
+    KG_SH_ATTR(1, 0, 0, 3, 1, 0, false); KG_SH_ATTR(1, 0, 0, 3, 3, 0, false);
+    KG_SH_ATTR(1, 0, 0, 3, 1, 0, true); KG_SH_ATTR(1, 0, 0, 3, 3, 0, true);
+#undef KG_SH_ATTR
     attr_set = true;
   }
   switch (k) {
@@ -556,18 +592,21 @@ int tc_shift_launch(const TcShiftOp* op, float* const* out32, cudaStream_t strea
       p.grp[g].out32 = out32[g];
     }
   }
+#define KG_SH_LAUNCH(...) tc_shift_kernel<__VA_ARGS__><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p)
   switch (kernel_of(op)) {
-    case SHK_HEADS: tc_shift_kernel<5, 10, 40, 7, 1, 0><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p); break;
+    case SHK_HEADS: KG_SH_LAUNCH(5, 10, 40, 7, 1, 0, false); break;
     case SHK_C64:
-      if (op->passes == 3) tc_shift_kernel<64, 0, 0, 3, 3, 1><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
-      else tc_shift_kernel<64, 0, 0, 3, 1, 1><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
+      if (op->wres) { if (op->passes == 3) KG_SH_LAUNCH(64, 0, 0, 3, 3, 1, true); else if (op->passes == 2) KG_SH_LAUNCH(64, 0, 0, 3, 2, 1, true); else KG_SH_LAUNCH(64, 0, 0, 3, 1, 1, true); }
+      else { if (op->passes == 3) KG_SH_LAUNCH(64, 0, 0, 3, 3, 1, false); else if (op->passes == 2) KG_SH_LAUNCH(64, 0, 0, 3, 2, 1, false); else KG_SH_LAUNCH(64, 0, 0, 3, 1, 1, false); }
       break;
     case SHK_C1:
-      if (op->passes == 3) tc_shift_kernel<1, 0, 0, 3, 3, 0><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
-      else tc_shift_kernel<1, 0, 0, 3, 1, 0><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p);
+      KG_REQUIRE(op->passes != 2, "tc_shift_launch: the one-channel kernel has no 2-pass variant");
+      if (op->wres) { if (op->passes == 3) KG_SH_LAUNCH(1, 0, 0, 3, 3, 0, true); else KG_SH_LAUNCH(1, 0, 0, 3, 1, 0, true); }
+      else { if (op->passes == 3) KG_SH_LAUNCH(1, 0, 0, 3, 3, 0, false); else KG_SH_LAUNCH(1, 0, 0, 3, 1, 0, false); }
       break;
     default: set_error("tc_shift_launch: unsupported shape"); return KG_ERR_INVALID;
   }
+#undef KG_SH_LAUNCH
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;
 }

@@ -33,9 +33,9 @@ struct TcShiftPacked {
 struct TcShiftOp {
   int N = 0, H = 0, W = 0, R = 0, S = 0, pad = 0, Cin = 0;   // stride-1 "same" convs: output size == input size
   const __half* in_hi = nullptr;                              // NHWC fp16, pixel stride in_C channels
-  const __half* in_lo = nullptr;                              // second plane (split fp16), needed when passes == 3
+  const __half* in_lo = nullptr;                              // second plane (split fp16), needed when passes >= 2
   int in_C = 0;
-  int passes = 1;                                             // 1: fp16 x fp16; 3: split-fp16 (hi*hi + lo*hi + hi*lo)
+  int passes = 1;                                             // 1: fp16 x fp16; 2: (hi + lo activations) x hi weights; 3: split-fp16 (hi*hi + lo*hi + hi*lo)
   int n_groups = 0;
   TcShiftGroup g[SH_MAX_GROUPS];
   // output: fp32 NCHW per conv (given at launch) unless out_hi is set: then conv 0 writes split-fp16 NHWC (+ReLU)
@@ -47,6 +47,7 @@ struct TcShiftOp {
   // filled by tc_shift_prepare
   std::shared_ptr<void> params;
   unsigned grid = 0, smem_bytes = 0;
+  bool wres = false;                                          // weights resident in shared memory
 };
 
 // configurations with a compiled kernel: the three KGnet heads (5, 10, 40; 7x7; fp32 NCHW out), one 64-channel 3x3 conv

@@ -164,10 +164,12 @@ SHIFT_CONV_CASES = [  # (N, Cin, H, W, Cout): 3x3 convs through the row-GEMM + s
 
 
 @pytest.mark.parametrize("case", SHIFT_CONV_CASES)
-@pytest.mark.parametrize("mode", [13, 11])
+@pytest.mark.parametrize("mode", [13, 12, 11])
 def test_conv_shift_kernel(case, mode):
     N, Cin, H, W, Cout = case
     x, w, b, pad, r, y = _case(6, N, Cin, H, W, Cout, 3, 1, Cout != 1, False)
+    if mode == 12 and Cout == 1:
+        pytest.skip("the one-channel kernel has no 2-pass variant")
     got = _conv(x, w, b, 1, pad, Cout != 1, None, mode)
     scale = float(y.abs().max())
     tol = (2e-4 if mode == 13 else 3e-3) * scale + 1e-5

@@ -11,9 +11,11 @@ def q16(t):
 def run(sd, x, groups, blocks=(3, 4, 6)):
     def conv(xx, name, group, bias=True, stride=1, pad=0):
         w = sd[name + ".weight"]; b = sd.get(name + ".bias") if bias else None
-        if group in groups:
+        if group in groups or (group + ":w") in groups:       # "<group>:w" rounds only the weights (activations stay split-fp16)
             mx = w.abs().max(); sc = 2.0 ** (10 - torch.frexp(mx)[1].item())
-            xx = q16(xx); w = q16(w * sc) / sc
+            if group in groups:
+                xx = q16(xx)
+            w = q16(w * sc) / sc
         return F.conv2d(xx, w, b, stride=stride, padding=pad)
     def bn(xx, p):
         return F.batch_norm(xx, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, 1e-5)
@@ -38,9 +40,9 @@ def run(sd, x, groups, blocks=(3, 4, 6)):
         c3c = F.relu(conv(torch.cat((c4u, c3), 1), "c3_cat_refine.0", "dec_cat"))
         c3u = F.relu(conv(up(c3c, c2), "c3_up_conv.0", "dec_up", pad=1))
         c2c = F.relu(conv(torch.cat((c3u, c2), 1), "c2_cat_refine.0", "dec_cat"))
-        c2u = F.relu(conv(up(c2c, c1), "c2_up_conv.0", "dec_up", pad=1))
+        c2u = F.relu(conv(up(c2c, c1), "c2_up_conv.0", "dec_up" if "c2up:w" not in groups else "c2up", pad=1))
         c1c = F.relu(conv(torch.cat((c2u, c1), 1), "c1_cat_refine.0", "dec_cat"))
-        c1u = F.relu(conv(up(c1c, c0), "c1_up_conv.0", "dec_up", pad=1))
+        c1u = F.relu(conv(up(c1c, c0), "c1_up_conv.0", "dec_up" if "c1up:w" not in groups else "c1up", pad=1))
         c0c = F.relu(conv(torch.cat((c1u, c0), 1), "c0_cat_refine.0", "dec_cat"))
         outs = []
         for s, f in enumerate((c0c, c1c, c2c, c3c)):
@@ -55,7 +57,8 @@ for seed in (0, 1):
     torch.manual_seed(seed)
     x = torch.rand(1, 3, size, size) - 0.5
     ref = run(sd, x, set())
-    for groups in (["head1", "head2"], ["head1", "head2", "dec_up"], ["head1", "head2", "dec_cat"], ["head1", "head2", "dec_up", "dec_cat"],
+    for groups in (["head1", "head2"], ["head1", "head2", "c0b:w", "c1up:w"], ["head1", "head2", "c0b:w", "c1up:w", "c2up:w"],
+                   ["head1", "head2", "c0b:w", "c1up:w", "dec_cat:w"], ["head1", "head2", "dec_up"], ["head1", "head2", "dec_cat"], ["head1", "head2", "dec_up", "dec_cat"],
                    ["head1", "head2", "dec_up", "dec_cat", "c0b"], ["head1", "head2", "backbone"],
                    ["head1", "head2", "dec_up", "dec_cat", "c0b", "backbone"]):
         out = run(sd, x, set(groups))
