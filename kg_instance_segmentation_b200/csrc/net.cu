@@ -4,6 +4,7 @@
 #include "net.cuh"
 #include "tc_conv.cuh"
 #include "tc_shift.cuh"
+#include "tc_stem.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -28,6 +29,7 @@ struct ConvW {
   float* d_w = nullptr;
   float* d_b = nullptr;
   TcWeights tc;             // fp16 hi/lo [tap][cout_pad][cin] (tensor-core path)
+  mutable TcStemWeights stemw;            // swizzled weight image of the tensor-core stem kernel, built on first use
   mutable TcShiftPacked shift1, shift3;   // weights packed for the row-GEMM + shift-add kernel (1 / 3 passes), built on first use
 };
 
@@ -508,6 +510,12 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
         if (op.x_input && w->Cin == 3 && w->Cout == 64 && op.relu && op.out >= 0 && !op.out_single && out32 == nullptr &&
             ((w->R == 3 && op.stride == 1) || (w->R == 7 && op.stride == 2)) && w->R == w->S && op.pad == w->R / 2) {
           const Tensor& to = p->tensors[op.out];
+          if (p->precision != 0 && tc_stem_supported(w->R, op.stride)) {
+            if (!w->stemw.d_img) KG_TRY(tc_stem_pack(w->h_w.data(), w->R, &w->stemw));
+            KG_TRY(tc_stem_launch(d_x, &w->stemw, w->d_b, P.hi(to), P.lo(to), p->N, p->H, p->W, w->R, op.stride, stream));
+            ++launches;
+            break;
+          }
           KG_TRY(launch_stem_conv(d_x, w->d_w, w->d_b, P.hi(to), P.lo(to), p->N, p->H, p->W, w->R, op.stride, stream));
           ++launches;
           break;

@@ -1,0 +1,21 @@
+// Tensor-core kernels for the two convs that read the raw 3-channel image (c0_conv.0, conv1 + bn1).  See tc_stem.cu.
+#pragma once
+#include <cuda_fp16.h>
+
+#include <memory>
+
+#include "common.cuh"
+
+namespace kg {
+
+struct TcStemWeights {
+  std::shared_ptr<void> d_img;   // device: fp16 hi / lo planes in the swizzled shared-memory layout of the kernel
+  int K = 0;
+};
+
+bool tc_stem_supported(int K, int stride);
+int tc_stem_pack(const float* w_tap_cin_cout, int K, TcStemWeights* out);   // weights [tap][3][64] fp32 (BN folded)
+int tc_stem_launch(const float* x, const TcStemWeights* w, const float* bias, __half* out_hi, __half* out_lo, int N, int H, int W, int K,
+                   int stride, cudaStream_t s);
+
+}  // namespace kg

@@ -1,12 +1,15 @@
 #!/bin/bash
 # usage (on the GPU box, via gpurun): tools/gpu_profile.sh <tag>   -> gpurun_out/<tag>_*
-# pytest -m gpu, the default bench line, the ncu launch list of one step and one `--set full` capture of that step.
+# pytest -m gpu, the default bench line, the ncu launch list of one step and one `--set full` capture of the tensor-core
+# launches (tc_conv / tc_shift) of that step.
 tag=${1:-r1}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv,noheader > gpurun_out/${tag}_gpu.txt
-python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/${tag}_pytest.log
+python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/${tag}_pytest.log
+tail -2 gpurun_out/${tag}_pytest.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
-tail -c 600 gpurun_out/${tag}_bench.json
+tail -c 400 gpurun_out/${tag}_bench.json
+python bench.py --workload decode --steps 10 --warmup 3 > gpurun_out/${tag}_bench_decode.json 2>> gpurun_out/${tag}_bench.err
 # launches per step are printed by bench (gpu_launches / steps); warm-up = 3 steps
 L=$(python -c "import json;d=json.load(open('gpurun_out/${tag}_bench.json'));print(d['gpu_launches']//d['steps'])")
 echo "launches/step=$L"
@@ -14,10 +17,19 @@ SKIP=${SKIP:-$((3*L))}
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $L --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1
 if [ "${FULL:-1}" = "1" ]; then
-  timeout 700 ncu --set full --clock-control none -s $SKIP -c $L -f -o gpurun_out/${tag}_step \
+  TC=$(python - <<PY
+import csv
+rows=list(csv.reader(open('gpurun_out/${tag}_launches.csv')))
+hi=[i for i,r in enumerate(rows) if r and r[0]=='ID'][0]
+k=rows[hi].index('Kernel Name')
+print(sum(1 for r in rows[hi+1:] if len(r)>k and ('tc_conv' in r[k] or 'tc_shift' in r[k])))
+PY
+)
+  echo "tensor-core launches/step=$TC"
+  timeout 800 ncu --set full --clock-control none -k regex:'tc_conv|tc_shift' -s $((3*TC)) -c $TC -f -o gpurun_out/${tag}_tc \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
-  ncu -i gpurun_out/${tag}_step.ncu-rep --page raw --csv > gpurun_out/${tag}_step_raw.csv 2>/dev/null
-  sz=$(stat -c %s gpurun_out/${tag}_step.ncu-rep)
-  if [ "$sz" -gt 40000000 ]; then rm -f gpurun_out/${tag}_step.ncu-rep; fi
+  ncu -i gpurun_out/${tag}_tc.ncu-rep --page raw --csv > gpurun_out/${tag}_tc_raw.csv 2>/dev/null
+  sz=$(stat -c %s gpurun_out/${tag}_tc.ncu-rep)
+  if [ "$sz" -gt 40000000 ]; then rm -f gpurun_out/${tag}_tc.ncu-rep; fi
   ls -la gpurun_out/
 fi
