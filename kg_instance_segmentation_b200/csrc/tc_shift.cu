@@ -30,7 +30,7 @@
 
 namespace kg {
 
-constexpr int SH_THREADS = 192;
+constexpr int SH_THREADS = 320;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (two per TMEM lane quadrant)
 constexpr int SH_MAX_UNITS = 6, SH_MAX_TAPS = 8, SH_MAX_CHUNKS = 16;
 constexpr int SH_BK = 64;
 constexpr int SH_A_TILE = 128 * SH_BK * 2;   // 16 KiB
@@ -70,6 +70,13 @@ struct ShCfg {
   static constexpr int bufcol(int g) { int c = 0; for (int i = 0; i < g; ++i) c += n_out(i); return c; }
   static constexpr int nchunks(int g) { return (n_out(g) + 7) / 8; }                     // 8-column TMEM loads per tap
   static constexpr int chunk0(int g) { int c = 0; for (int i = 0; i < g; ++i) c += nchunks(i); return c; }
+  // epilogue work list: batches of up to 16 channels of one conv; batch b is handled by epilogue half (b & 1)
+  static constexpr int nbatch(int g) { return (n_out(g) + 15) / 16; }
+  static constexpr int NBT = (O0 > 0 ? nbatch(0) : 0) + (O1 > 0 ? nbatch(1) : 0) + (O2 > 0 ? nbatch(2) : 0);
+  static constexpr int b_group(int b) { int g = 0; while (b >= nbatch(g)) { b -= nbatch(g); ++g; } return g; }
+  static constexpr int b_lo(int b) { int g = 0; while (b >= nbatch(g)) { b -= nbatch(g); ++g; } return b * 16; }
+  static constexpr int b_n(int b) { return n_out(b_group(b)) - b_lo(b) < 16 ? n_out(b_group(b)) - b_lo(b) : 16; }
+  static constexpr int last_batch_of_half(int h) { int l = -1; for (int b = 0; b < NBT; ++b) if ((b & 1) == h) l = b; return l; }
   static constexpr int NU = (O0 > 0 ? units_of(0) : 0) + (O1 > 0 ? units_of(1) : 0) + (O2 > 0 ? units_of(2) : 0);
   static constexpr int COLS = col0(NG);
   static constexpr int NOUT = bufcol(NG);
@@ -98,7 +105,7 @@ __device__ __forceinline__ void static_for(F&& f) {
   if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // OUTMODE 0: fp32 NCHW per conv (+sigmoid); OUTMODE 1: conv 0 -> split-fp16 NHWC (+ReLU, +mask)
 // PASSES 1: fp16 x fp16; 2: (hi + lo activations) x hi weights; 3: split-fp16 on both sides (hi*hi + lo*hi + hi*lo).
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.NS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 8); }
     mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -150,10 +157,10 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2) {
-    for (int e = threadIdx.x - 64; e < p.RB * RS; e += 128) buf[e] = 0.f;
+    for (int e = threadIdx.x - 64; e < p.RB * RS; e += 256) buf[e] = 0.f;
     static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
       constexpr int g = decltype(Gx)::value;
-      for (int e = threadIdx.x - 64; e < Cfg::n_out(g); e += 128) s_bias[Cfg::bufcol(g) + e] = p.grp[g].bias[e];
+      for (int e = threadIdx.x - 64; e < Cfg::n_out(g); e += 256) s_bias[Cfg::bufcol(g) + e] = p.grp[g].bias[e];
     });
   }
   tc_fence_before();
@@ -256,8 +263,10 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
         __syncwarp();
       }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31; thread t <-> tile position t =====
+    // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 * (w % 4) .. + 31 (thread t <-> tile position t); the two warps of
+    // a quadrant ("halves") take alternate 16-channel batches of the work list =====
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int t = quad * 32 + lane;
     const int tj = p.row_mode ? 0 : t / p.BW, txx = p.row_mode ? t : t - tj * p.BW;
     const long long cs = (long long)p.H * p.W;
@@ -279,14 +288,11 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
           else { const int x2 = txx - s + p.pad; valid = x2 >= 0 && x2 < p.BW; L = tj * p.BW + x2; }
           int phys = L + off; if (phys >= p.RB) phys -= p.RB;
           float* row = buf + (valid ? phys : 0) * RS;
-          // conv by conv, at most 32 columns at a time: TMEM loads -> wait -> smem loads -> adds -> stores
-          static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
-            constexpr int g = decltype(Gx)::value;
-            constexpr int no = Cfg::n_out(g), b0 = Cfg::bufcol(g);
-            constexpr int NB = (no + 31) / 32;               // batches of up to 32 channels
-            static_for<0, NB>([&](auto Bx) __attribute__((always_inline)) {
-              constexpr int bb = decltype(Bx)::value;
-              constexpr int c_lo = bb * 32, c_n = no - c_lo < 32 ? no - c_lo : 32, nch = (c_n + 7) / 8;
+          // batch by batch (<= 16 channels): TMEM loads -> wait -> smem loads -> adds -> stores
+          static_for<0, Cfg::NBT>([&](auto Bx) __attribute__((always_inline)) {
+            constexpr int b = decltype(Bx)::value;
+            constexpr int g = Cfg::b_group(b), c_lo = Cfg::b_lo(b), c_n = Cfg::b_n(b), b0 = Cfg::bufcol(g), nch = (c_n + 7) / 8;
+            if ((b & 1) == half) {
               uint32_t raw[nch][8];
               static_for<0, nch>([&](auto Cx) __attribute__((always_inline)) {
                 constexpr int c = decltype(Cx)::value;
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                 tmem_ld8_nowait(lane_addr + col, raw[c]);
               });
               tmem_ld_wait();
-              if (s == TAPS - 1 && g == NG - 1 && bb == NB - 1) {   // Z fully read: hand the accumulators back to the MMA issuer
+              if (s == TAPS - 1 && b == Cfg::last_batch_of_half(b & 1)) {   // this warp has read all of its columns of Z
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
@@ -306,8 +312,13 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
 #pragma unroll
                 for (int e = 0; e < c_n; ++e) row[b0 + c_lo + e] = cur[e] + __uint_as_float(raw[e / 8][e % 8]);
               }
-            });
+            }
           });
+          if (Cfg::last_batch_of_half(1) < 0 && half == 1 && s == TAPS - 1) {   // a half without work still releases the accumulators
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
+          }
           epi_bar();
         });
         // ---- emit the finished pixels (and clear their buffer rows) ----
@@ -319,62 +330,54 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
           int y, x; bool inside;
           if (p.row_mode) { y = y0; x = tx * 128 + L - p.pad; inside = x >= 0 && x < p.W; }
           else { const int jj = L / p.BW; y = y0 + jj; x = L - jj * p.BW; inside = y < p.H; }
-          if (OUTMODE == 0) {
-            static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
-              constexpr int g = decltype(Gx)::value;
-              constexpr int no = Cfg::n_out(g), b0 = Cfg::bufcol(g);
-              float v[no];
+          const long long pix = ((long long)n * p.H + y) * p.W + x;
+          const bool keep = OUTMODE == 1 && inside && (p.mask == nullptr || p.mask[pix] != 0);
+          static_for<0, Cfg::NBT>([&](auto Bx) __attribute__((always_inline)) {
+            constexpr int b = decltype(Bx)::value;
+            constexpr int g = Cfg::b_group(b), c_lo = Cfg::b_lo(b), c_n = Cfg::b_n(b), b0 = Cfg::bufcol(g), no = Cfg::n_out(g);
+            if ((b & 1) == half) {
+              float v[c_n];
 #pragma unroll
-              for (int e = 0; e < no; ++e) v[e] = row[b0 + e];
+              for (int e = 0; e < c_n; ++e) v[e] = row[b0 + c_lo + e];
 #pragma unroll
-              for (int e = 0; e < no; ++e) row[b0 + e] = 0.f;
+              for (int e = 0; e < c_n; ++e) row[b0 + c_lo + e] = 0.f;
+              const ShGroup& G = p.grp[g];
               if (inside) {
-                const ShGroup& G = p.grp[g];
-                float* dst = G.out32 + ((long long)n * no * p.H + y) * p.W + x;
+                if (OUTMODE == 0) {
+                  float* dst = G.out32 + (((long long)n * no + c_lo) * p.H + y) * p.W + x;
 #pragma unroll
-                for (int co = 0; co < no; ++co) {
-                  float o = fmaf(v[co], G.inv_scale, s_bias[b0 + co]);
-                  if (G.sigmoid) o = 1.f / (1.f + expf(-o));
-                  *dst = o;
-                  dst += cs;
+                  for (int e = 0; e < c_n; ++e) {
+                    float o = fmaf(v[e], G.inv_scale, s_bias[b0 + c_lo + e]);
+                    if (G.sigmoid) o = 1.f / (1.f + expf(-o));
+                    *dst = o;
+                    dst += cs;
+                  }
+                } else {
+                  // split-fp16 NHWC: c_n is a multiple of 8 here
+                  static_for<0, c_n / 8>([&](auto Cx) __attribute__((always_inline)) {
+                    constexpr int c0 = decltype(Cx)::value * 8;
+                    uint4 h4, l4;
+                    __half2* hh = reinterpret_cast<__half2*>(&h4);
+                    __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      float a = fmaf(v[c0 + 2 * e], G.inv_scale, s_bias[b0 + c_lo + c0 + 2 * e]);
+                      float bq = fmaf(v[c0 + 2 * e + 1], G.inv_scale, s_bias[b0 + c_lo + c0 + 2 * e + 1]);
+                      if (p.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
+                      if (!keep) { a = 0.f; bq = 0.f; }
+                      a = fminf(fmaxf(a, -65504.f), 65504.f); bq = fminf(fmaxf(bq, -65504.f), 65504.f);
+                      const __half2 h = __floats2half2_rn(a, bq);
+                      const float2 hf = __half22float2(h);
+                      hh[e] = h;
+                      ll[e] = __floats2half2_rn(a - hf.x, bq - hf.y);
+                    }
+                    *reinterpret_cast<uint4*>(p.out_hi + pix * no + c_lo + c0) = h4;
+                    if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * no + c_lo + c0) = l4;
+                  });
                 }
               }
-            });
-          } else {
-            constexpr int no = Cfg::n_out(0);
-            const long long pix = ((long long)n * p.H + y) * p.W + x;
-            const bool keep = inside && (p.mask == nullptr || p.mask[pix] != 0);
-            const ShGroup& G = p.grp[0];
-            static_for<0, no / 8>([&](auto Cx) __attribute__((always_inline)) {
-              constexpr int c0 = decltype(Cx)::value * 8;
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = row[c0 + e];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) row[c0 + e] = 0.f;
-              if (inside) {
-                float bb[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) bb[e] = s_bias[c0 + e];
-                uint4 h4, l4;
-                __half2* hh = reinterpret_cast<__half2*>(&h4);
-                __half2* ll = reinterpret_cast<__half2*>(&l4);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float a = fmaf(v[2 * e], G.inv_scale, bb[2 * e]), b = fmaf(v[2 * e + 1], G.inv_scale, bb[2 * e + 1]);
-                  if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                  if (!keep) { a = 0.f; b = 0.f; }
-                  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
-                  const __half2 h = __floats2half2_rn(a, b);
-                  const float2 hf = __half22float2(h);
-                  hh[e] = h;
-                  ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
-                }
-                *reinterpret_cast<uint4*>(p.out_hi + pix * no + c0) = h4;
-                if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * no + c0) = l4;
-              }
-            });
-          }
+            }
+          });
         }
         if (p.row_mode) { off += 128; if (off >= p.RB) off -= p.RB; }
         epi_bar();
