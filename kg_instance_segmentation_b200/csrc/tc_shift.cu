@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
   float* buf = reinterpret_cast<float*>(smem_raw + (smem0 - smem_base) + (WRES ? p.wres_bytes : 0u) + (size_t)p.NS * p.slot_bytes + 16u * p.NS + 64u);
   const uint32_t w_off = (uint32_t)NPA * SH_A_TILE;          // weight planes follow the activation planes inside a slot
   float* s_bias = buf + p.RB * RS;                           // biases of all convs (a global load per output pixel stalls the emission)
+  float* s_edge = s_bias + ((Cfg::NOUT + 3) & ~3);           // register-shuffle epilogue: warp / tile edge exchange (832 floats)
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -280,6 +281,100 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
         mbar_wait(tmem_full(acc), acc_phase);
         tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)COLS;
+        if constexpr (OUTMODE == 1 && TAPS == 3 && O0 == 64 && NG == 1) {
+          if (p.row_mode) {
+            // ---- 3x3, 64 channels, whole-row tiles: shift-add in REGISTERS.  out[x] = Z[x-1][tap 0] + Z[x][tap 1] + Z[x+1][tap 2]:
+            // the neighbours' values come by warp shuffle, only warp / tile edges go through shared memory.  (The smem row
+            // buffer of the generic path below competes with the tensor core for the shared-memory pipe: measured 48 % LSU +
+            // 24 % UMMA wavefronts on c0_conv.2.)  The last pixel of a tile waits for the next tile's first pixel ("pend").
+            const bool first = tx == 0, last = tx == p.tiles_x - 1;
+            const uint32_t par = tile_it & 1u;
+            float* e0 = s_edge + par * 256u;                 // tap-0 values of lane 31 of every quadrant, [quad][64], double-buffered
+            const float* e0_prev = s_edge + (par ^ 1u) * 256u;
+            float* e2 = s_edge + 512;                        // tap-2 values of lane 0 of every quadrant
+            float* pend = s_edge + 768;                      // partial sum of the previous tile's last pixel
+            const int cb = half * 32;                        // this warp's 32 channels
+            const ShGroup& G = p.grp[0];
+            auto emit32 = [&](const float* v, long long pix) __attribute__((always_inline)) {
+              const bool keep = p.mask == nullptr || p.mask[pix] != 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 h4, l4;
+                __half2* hh = reinterpret_cast<__half2*>(&h4);
+                __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float a = fmaf(v[8 * k + 2 * e], G.inv_scale, s_bias[cb + 8 * k + 2 * e]);
+                  float bq = fmaf(v[8 * k + 2 * e + 1], G.inv_scale, s_bias[cb + 8 * k + 2 * e + 1]);
+                  if (p.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
+                  if (!keep) { a = 0.f; bq = 0.f; }
+                  a = fminf(fmaxf(a, -65504.f), 65504.f); bq = fminf(fmaxf(bq, -65504.f), 65504.f);
+                  const __half2 h = __floats2half2_rn(a, bq);
+                  const float2 hf = __half22float2(h);
+                  hh[e] = h;
+                  ll[e] = __floats2half2_rn(a - hf.x, bq - hf.y);
+                }
+                *reinterpret_cast<uint4*>(p.out_hi + pix * 64 + cb + 8 * k) = h4;
+                if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * 64 + cb + 8 * k) = l4;
+              }
+            };
+            const long long pix0 = ((long long)n * p.H + y0) * p.W + (long long)tx * 128;
+            float z0[32], z2[32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld8_nowait(lane_addr + (uint32_t)(cb + 8 * c), reinterpret_cast<uint32_t*>(&z0[8 * c]));
+              tmem_ld8_nowait(lane_addr + (uint32_t)(128 + cb + 8 * c), reinterpret_cast<uint32_t*>(&z2[8 * c]));
+            }
+            tmem_ld_wait();
+            if (lane == 31) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) e0[quad * 64 + cb + c] = z0[c];
+            }
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) e2[quad * 64 + cb + c] = z2[c];
+              if (!first && quad == 0) {                     // the previous tile's last pixel is complete now
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = pend[cb + c] + z2[c];
+                emit32(v, pix0 - 1);
+              }
+            }
+            epi_bar();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              z0[c] = __shfl_up_sync(0xffffffffu, z0[c], 1);       // left neighbour's tap 0
+              z2[c] = __shfl_down_sync(0xffffffffu, z2[c], 1);     // right neighbour's tap 2
+            }
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) z0[c] = quad == 0 ? (first ? 0.f : e0_prev[3 * 64 + cb + c]) : e0[(quad - 1) * 64 + cb + c];
+            }
+            if (lane == 31) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) z2[c] = quad == 3 ? 0.f : e2[(quad + 1) * 64 + cb + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t z1[8];
+              tmem_ld8_nowait(lane_addr + (uint32_t)(64 + cb + 8 * c), z1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 8; ++e) z0[8 * c + e] = __uint_as_float(z1[e]) + z0[8 * c + e] + z2[8 * c + e];
+            }
+            tc_fence_before();                               // Z fully read: hand the accumulators back to the MMA issuer
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
+            if (quad == 3 && lane == 31 && !last) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) pend[cb + c] = z0[c];
+            } else {
+              emit32(z0, pix0 + t);
+            }
+            epi_bar();
+            continue;
+          }
+        }
         // ---- shift-add: tap s of position q goes to output pixel q - s + pad (everything below is compile-time unrolled) ----
         static_for<0, TAPS>([&](auto Sx) __attribute__((always_inline)) {
           constexpr int s = decltype(Sx)::value;
@@ -480,6 +575,7 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   p.rows_y = ceil_div(op->H, p.BH);
   p.num_work = op->N * p.rows_y;
   p.RB = p.row_mode ? 128 + 2 * op->pad : 128;
+  if (std::is_same<Cfg, C64Cfg>::value && p.row_mode && op->out_hi != nullptr) p.RB = 0;   // register-shuffle epilogue: no row buffer
   p.out_hi = op->out_hi; p.out_lo = op->out_lo; p.mask = op->mask; p.relu = op->relu ? 1 : 0;
   const int rows = Cfg::COLS, R = op->R;
   const int acc_sets = 2 * Cfg::COLS <= 512 ? 2 : 1;
@@ -519,7 +615,7 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
     }
   }
   p.w_slab = (unsigned)align_up((size_t)maxN * 128, 1024);
-  const size_t buf_bytes = ((size_t)p.RB * Cfg::RS + Cfg::NOUT) * sizeof(float);
+  const size_t buf_bytes = ((size_t)p.RB * Cfg::RS + Cfg::NOUT + 4 + 832) * sizeof(float);
   const size_t fixed = 1024 + 16 * 16 + 64 + buf_bytes + 64;
   // resident weights: the whole [R][chunks][planes] weight tensor stays in smem when it leaves room for >= 3 activation slots
   const size_t wres_total = (size_t)R * p.kchunks * NPW * p.w_slab;
