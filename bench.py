@@ -85,6 +85,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def profiled_traffic(key=None):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/*_traffic.json);
+    None when no capture has been committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    if key is not None:
+        d = d.get(key)
+        if d is None:
+            return None, None
+    return d.get("dram_bytes_per_launch"), os.path.basename(files[-1])
+
+
 def planted_batch(n_distinct=4):
     """Teacher-forced decode load: planted 40-cell scenes, bs 32 built from n_distinct scenes."""
     from kg_instance_segmentation_b200 import synthetic
@@ -177,8 +192,10 @@ def run_decode(args, rank, world, dist):
     pk, pk_kind = peaks()
     dom_ms = float(st_ms[dom]) / args.steps
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic, traffic_src = profiled_traffic("decode" if dom == 1 else ("decode_vote" if dom == 0 else "none"))
     roofline = {"kernel": names[dom], "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "peak_kind": pk_kind + " (burst copy)",
+                "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic, "traffic_source": traffic_src,
+                "peak_kind": pk_kind + " (burst copy)",
                 "algorithmic_bytes_per_launch": alg_bytes // max(1, stage[names[dom]]["launches_per_step"]),
                 "stages": stage}
     out = {
@@ -296,15 +313,17 @@ def run_pipeline(args, rank, world, dist):
         t = float(st_ms[9 + j]) / args.steps
         if t > 0:
             per_class[nme] = {"tflops": round(info[4 + j] / (t * 1e-3) / 1e12, 1), "frac": round(info[4 + j] / (t * 1e-3) / 1e12 / peak_tf, 4)}
-    roofline = {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv, all tensor-core launches of forward_dec)", "bound": "tensor",
-                "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4), "traffic": None,
+    traffic, traffic_src = profiled_traffic()
+    roofline = {"kernel": "tc_conv_kernel + tc_shift_kernel (tcgen05 implicit-GEMM / row-GEMM shift-add convs: all tensor-core launches of forward_dec)",
+                "bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4),
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_kind": pk_kind + " (cuBLAS bf16 sustained; kernel timed inside a long step)",
                 "algorithmic_flops_per_step": info[0], "launches_per_step": tc_launches, "avg_launch_ms": round(tc_ms / max(1, tc_launches), 4),
                 "cuda_core_conv_flops_per_step": info[1], "per_class": per_class, "stages": stages}
     out = {
         "metric": METRIC, "value": round(world * BS * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16 operands (split hi+lo x3 in backbone/decoder, single pass in heads), fp32 accumulate; fp64 decode"
+        "dtype": "fp16 operands (split hi+lo x3 in backbone/decoder, x2 in three 64-channel decoder convs, single pass in heads), fp32 accumulate; fp64 decode"
                  if args.precision == "fast" else args.precision,
         "data": "synthetic (seeded Kaiming weights with calibrated heads; rand-0.5 images; planted 40-cell scenes)",
         "config": {"workload": "bs32/GPU 512x512: forward_dec (ResNet-50 trunk + decoder + 12 heads) -> vote/blur/peak/group/boxes/NMS -> forward_seg"
@@ -399,6 +418,8 @@ def main():
     import torch
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
