@@ -151,155 +151,6 @@ __global__ void __launch_bounds__(256) blur_peak_kernel(const unsigned long long
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 (fast variant, used when the caller does not ask for the dense vote / heat maps): same result as
-// blur_peak_kernel, but the fp64 pipe only touches CANDIDATE pixels.  The reference's operation order costs ~90
-// DADD/DMUL per pixel (no FMA), which bounds the exact kernel at ~7 % of HBM peak.  Here the separable blur first runs
-// in fp32 over the whole tile; a pixel can only be a peak if its fp32 value, inflated by a relative margin far above
-// the fp32 error bound, reaches the threshold and its four fp32 neighbours.  Those few pixels (and their neighbours)
-// are then recomputed in fp64 in exactly the reference order and put through the exact peak test, so the emitted
-// peak set and confidences are bit-identical to the exact kernel.  The error bound needs non-negative votes
-// (sum of non-negative terms: relative fp32 error < 3e-6); a tile that sees a negative accumulator takes the exact
-// path for every pixel.
-constexpr int BF_MAXC = 512;            // candidates kept per tile before the whole tile falls back to "all pixels"
-constexpr float BF_MARGIN = 1.0001f;    // >> 40 * 2^-24
-struct BlurFastSmem {
-  long long q[BI][BI];                  // raw accumulators (reflect-mapped halo)
-  float f[BI][BI];                      // fp32 heat
-  float t[BB][BI];                      // fp32 axis-0 pass
-  float b[BB][BB + 1];                  // fp32 blurred tile (+1 halo)
-  double scratch[8][(2 * GAUSS_R + 3) * (2 * GAUSS_R + 3) + 3 * (2 * GAUSS_R + 3) + 8];   // per warp: 19x19 inputs, 3x19 axis-0 values, 5 results
-  unsigned short cand[BF_MAXC];
-  int ncand;
-};
-
-__device__ __forceinline__ double heat_of(long long q) { return ((double)q * KG_UNFIX) / KG_PI_R2; }
-
-__global__ void __launch_bounds__(256) blur_peak_fast_kernel(const unsigned long long* __restrict__ acc, int H, int W,
-                                                             double peak_thresh, int list_index_base, int n_scales,
-                                                             int max_peaks, double* __restrict__ peak_conf,
-                                                             int* __restrict__ peak_key, int* __restrict__ peak_count,
-                                                             int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char bf_raw[];
-  BlurFastSmem& S = *reinterpret_cast<BlurFastSmem*>(bf_raw);
-  const int plane_id = blockIdx.z;
-  const int n = plane_id / 5, ch = plane_id - n * 5;
-  const int hw = H * W;
-  const unsigned long long* plane = acc + (size_t)plane_id * hw;
-  const int x0 = blockIdx.x * BT, y0 = blockIdx.y * BT;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) S.ncand = 0;
-  int neg = 0;
-  const float kScale = (float)(KG_UNFIX / KG_PI_R2);
-  // interior tiles (halo inside the image) skip the reflect mapping: its two integer modulos per element dominated the load phase
-  const bool interior = y0 >= GAUSS_R + 1 && x0 >= GAUSS_R + 1 && y0 - (GAUSS_R + 1) + BI <= H && x0 - (GAUSS_R + 1) + BI <= W;
-  for (int e = tid; e < BI * BI; e += 256) {
-    const int r = e / BI, c = e - r * BI;
-    int gy = y0 - (GAUSS_R + 1) + r, gx = x0 - (GAUSS_R + 1) + c;
-    if (!interior) { gy = reflect_index(gy, H); gx = reflect_index(gx, W); }
-    const long long q = (long long)__ldg(plane + gy * W + gx);
-    S.q[r][c] = q;
-    S.f[r][c] = __ll2float_rn(q) * kScale;
-    neg |= (q < 0);
-  }
-  const int any_neg = __syncthreads_or(neg);
-  // fp32 blur (any operation order: only used to select candidates)
-  for (int e = tid; e < BB * BI; e += 256) {
-    const int r = e / BI, c = e - r * BI;
-    float t = 0.f;
-#pragma unroll
-    for (int j = -GAUSS_R; j <= GAUSS_R; ++j) t = fmaf(S.f[r + GAUSS_R + j][c], (float)c_gauss[GAUSS_R - (j < 0 ? -j : j)], t);
-    S.t[r][c] = t;
-  }
-  __syncthreads();
-  for (int e = tid; e < BB * BB; e += 256) {
-    const int r = e / BB, c = e - r * BB;
-    float t = 0.f;
-#pragma unroll
-    for (int j = -GAUSS_R; j <= GAUSS_R; ++j) t = fmaf(S.t[r][c + GAUSS_R + j], (float)c_gauss[GAUSS_R - (j < 0 ? -j : j)], t);
-    S.b[r][c] = t;
-  }
-  __syncthreads();
-  // candidate selection
-  const float thr = (float)peak_thresh;
-  for (int e = tid; e < BT * BT; e += 256) {
-    const int r = e / BT, c = e - r * BT;
-    const int gy = y0 + r, gx = x0 + c;
-    if (gy >= H || gx >= W) continue;
-    bool is_c = any_neg != 0;
-    if (!is_c) {
-      const float h = S.b[r + 1][c + 1] * BF_MARGIN;
-      is_c = h > thr;
-      if (gy > 0) is_c = is_c && h >= S.b[r][c + 1];
-      if (gy < H - 1) is_c = is_c && h >= S.b[r + 2][c + 1];
-      if (gx > 0) is_c = is_c && h >= S.b[r + 1][c];
-      if (gx < W - 1) is_c = is_c && h >= S.b[r + 1][c + 2];
-    }
-    if (is_c) {
-      const int slot = atomicAdd(&S.ncand, 1);
-      if (slot < BF_MAXC) S.cand[slot] = (unsigned short)e;
-    }
-  }
-  __syncthreads();
-  const int nc_raw = S.ncand;
-  const bool all = nc_raw > BF_MAXC;                  // list overflow: every pixel of the tile is a candidate
-  const int nc = all ? BT * BT : nc_raw;
-  // exact evaluation, one warp per candidate
-  constexpr int WN = 2 * GAUSS_R + 3;                 // 19: window edge of inputs feeding a pixel and its 4 neighbours
-  double* in = S.scratch[warp];                       // [19][19] exact heat values
-  double* v0 = in + WN * WN;                          // [3][19] axis-0 results for blurred rows r-1, r, r+1
-  double* res = v0 + 3 * WN;                          // h(r,c), up, down, left, right
-  for (int k = warp; k < nc; k += 8) {
-    const int e = all ? k : (int)S.cand[k];
-    const int r = e / BT, c = e - r * BT;
-    const int gy = y0 + r, gx = x0 + c;
-    if (gy >= H || gx >= W) continue;                 // (only reachable in the "all" case; warp-uniform)
-    // inputs: tile rows r .. r+18, cols c .. c+18 of S.q  (blurred (r+1, c+1) is centred on input (r+9, c+9))
-    for (int i = lane; i < WN * WN; i += 32) { const int a = i / WN, b = i - a * WN; in[i] = heat_of(S.q[r + a][c + b]); }
-    __syncwarp();
-    // axis-0 (vertical) pass for blurred rows r, r+1, r+2 (i.e. dy = -1, 0, +1), all 19 columns
-    for (int i = lane; i < 3 * WN; i += 32) {
-      const int dy = i / WN, b = i - dy * WN;
-      const int cc = dy + GAUSS_R;                    // centre row inside the window
-      double t = in[cc * WN + b] * c_gauss[GAUSS_R];
-#pragma unroll
-      for (int j = -GAUSS_R; j < 0; ++j) t += (in[(cc + j) * WN + b] + in[(cc - j) * WN + b]) * c_gauss[j + GAUSS_R];
-      v0[i] = t;
-    }
-    __syncwarp();
-    // axis-1 pass for the five pixels: (dy, dx) = (0,0), (-1,0), (+1,0), (0,-1), (0,+1)
-    if (lane < 5) {
-      const int dy = lane == 1 ? -1 : (lane == 2 ? 1 : 0), dx = lane == 3 ? -1 : (lane == 4 ? 1 : 0);
-      const double* row = v0 + (dy + 1) * WN;
-      const int cc = GAUSS_R + 1 + dx;
-      double t = row[cc] * c_gauss[GAUSS_R];
-#pragma unroll
-      for (int j = -GAUSS_R; j < 0; ++j) t += (row[cc + j] + row[cc - j]) * c_gauss[j + GAUSS_R];
-      res[lane] = t;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const double h = res[0];
-      double m = h;
-      if (gy > 0) m = fmax(m, res[1]);
-      if (gy < H - 1) m = fmax(m, res[2]);
-      if (gx > 0) m = fmax(m, res[3]);
-      if (gx < W - 1) m = fmax(m, res[4]);
-      if (m == h && h > peak_thresh) {
-        const int list = n * n_scales + list_index_base;
-        const int slot = atomicAdd(peak_count + list, 1);
-        if (slot < max_peaks) {
-          peak_conf[(size_t)list * max_peaks + slot] = h;
-          peak_key[(size_t)list * max_peaks + slot] = ch * hw + gy * W + gx;
-        } else {
-          atomicOr(status, 1);
-        }
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // K3: per (image, scale): sort peaks (conf desc, generation order asc == Python's stable
 // list.sort(reverse=True), postprocessing.py:87), greedy grouping (:98-124), refine_skeleton
 // (:150-159) and skeleton_to_box (:164-242).
@@ -687,7 +538,6 @@ int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const 
     KG_REQUIRE(sc[s].d_kp && sc[s].d_short && sc[s].d_mid, "kg_decode: scale %d has a null head pointer", s);
   int launches = 0;
   const int N = cfg->N, S = cfg->n_scales, P = cfg->max_peaks;
-  KG_CUDA_CHECK(cudaFuncSetAttribute(blur_peak_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlurFastSmem)));
   KG_CUDA_CHECK(cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, stream));
   KG_CUDA_CHECK(cudaMemsetAsync(out->d_status, 0, sizeof(int), stream));
   double* peak_conf = out->d_peak_conf ? out->d_peak_conf : w.peak_conf;
@@ -703,13 +553,8 @@ int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const 
     dim3 g2(ceil_div(W, BT), ceil_div(H, BT), N * 5);
     {
       StageScope t(1, stream);
-      if (out->d_vote[s] == nullptr && out->d_heat[s] == nullptr && getenv("KG_BLUR_EXACT") == nullptr) {
-        blur_peak_fast_kernel<<<g2, 256, sizeof(BlurFastSmem), stream>>>(w.acc[s], H, W, cfg->peak_thresh, s, S, P, peak_conf, peak_key,
-                                                                         peak_count, out->d_status);
-      } else {
-        blur_peak_kernel<<<g2, 256, 0, stream>>>(w.acc[s], H, W, cfg->peak_thresh, s, S, P, peak_conf, peak_key, peak_count,
-                                                 out->d_vote[s], out->d_heat[s], out->d_status);
-      }
+      blur_peak_kernel<<<g2, 256, 0, stream>>>(w.acc[s], H, W, cfg->peak_thresh, s, S, P, peak_conf, peak_key, peak_count,
+                                               out->d_vote[s], out->d_heat[s], out->d_status);
     }
     launches += 2;
   }
