@@ -1032,8 +1032,8 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
 static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R, int S,
                        int stride, int pad, int relu, const float* d_res, int mode, float* d_y, cudaStream_t stream) {
   KG_REQUIRE(d_x && h_w && d_y && N > 0 && Cin > 0 && Cout > 0, "kg_conv2d_nchw: bad arguments");
-  KG_REQUIRE(mode == 0 || mode == 1 || mode == 3 || mode == 11 || mode == 12 || mode == 13,
-             "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 / 3 (tensor-core passes) or 11 / 12 / 13 (row-GEMM + shift-add kernel, 1 / 2 / 3 passes)");
+  KG_REQUIRE(mode == 0 || mode == 1 || mode == 3 || mode == 11 || mode == 12 || mode == 13 || mode == 21,
+             "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 / 3 (tensor-core passes) or 11 / 12 / 13 (row-GEMM + shift-add kernel, 1 / 2 / 3 passes) or 21 (single pass, hi-plane output: CTA-pair kernel where eligible)");
   Net tmp;
   KG_TRY(set_conv(&tmp, "c", h_w, Cout, Cin, R, S, h_bias, nullptr, nullptr, nullptr, nullptr, 0.0));
   ConvW& w = tmp.convs.at("c");
@@ -1065,7 +1065,7 @@ static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const flo
       a.stride = stride; a.pad = pad; a.out_hi = yh; a.out_lo = yl; a.out_ps = Cout; a.res_hi = rh; a.res_lo = rl; a.res_ps = Cout;
       a.relu = relu; a.probs = d_probs;
       if ((rc = launch_conv_ffma(a, N, Ho * Wo, stream)) != KG_OK) break;
-    } else if (mode >= 10) {
+    } else if (mode >= 10 && mode < 20) {
       const bool nhwc = Cout != 1;
       if (d_res != nullptr || !shift_conv_ok(&w, Ho, Wo, stride, pad, Cin, 0, nhwc, false)) {
         set_error("kg_conv2d_nchw: shape not supported by the shift-add kernel"); rc = KG_ERR_INVALID; break;
@@ -1089,11 +1089,12 @@ static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const flo
       TcConvOp t{};
       t.w = &w.tc; t.bias = w.d_b; t.N = N; t.H = Ho; t.W = Wo; t.R = R; t.S = S; t.pad = pad; t.C0 = Cin; t.C1 = 0; t.Cout = Cout;
       t.stride = stride; t.Hin = H; t.Win = W;
-      t.passes = mode; t.in0_hi = xh; t.in0_lo = xl; t.in0_C = Cin; t.out_hi = yh; t.out_lo = yl; t.res_hi = rh; t.res_lo = rl; t.relu = relu != 0;
+      t.passes = mode == 21 ? 1 : mode; t.in0_hi = xh; t.in0_lo = xl; t.in0_C = Cin; t.out_hi = yh; t.out_lo = mode == 21 ? nullptr : yl;
+      t.res_hi = rh; t.res_lo = rl; t.relu = relu != 0;
       if ((rc = tc_conv_prepare(&t)) != KG_OK) break;
       if ((rc = tc_conv_launch(&t, nullptr, stream)) != KG_OK) break;
     }
-    if ((rc = launch_export_nchw(yh, yl, d_y, N, Ho * Wo, Cout, stream)) != KG_OK) break;
+    if ((rc = launch_export_nchw(yh, mode == 21 ? nullptr : yl, d_y, N, Ho * Wo, Cout, stream)) != KG_OK) break;
     if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("kg_conv2d_nchw: %s", cudaGetErrorString(cudaGetLastError())); rc = KG_ERR_CUDA; }
   } while (0);
   if (rc == KG_ERR_CUDA && cudaPeekAtLastError() != cudaSuccess) set_error("kg_conv2d_nchw: CUDA error %s", cudaGetErrorString(cudaGetLastError()));

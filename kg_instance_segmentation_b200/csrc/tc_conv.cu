@@ -58,6 +58,7 @@ struct TcParams {
                                     // behind ONE barrier round trip -- narrow-N layers are bound by those round trips)
   unsigned a_tile_bytes, a_tx_bytes;   // smem bytes reserved per A tile (1024-aligned) / bytes TMA delivers per A tile
   int base_offset_mode;
+  int two_cta;                      // CTA-pair kernel: BN is the FULL N of the pair's MMA, each CTA holds BN / 2 weight rows
   int relu, sigmoid;
   unsigned tmem_cols;
 };
@@ -385,6 +386,190 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   }
 }
 
+// ---- CTA-pair variant (cta_group::2) ------------------------------------------------------------------------------
+// First-layer head convs (single pass, ReLU, hi-plane NHWC output, no residual, 7x7 with N = 192 / 256).  In the one-CTA kernel
+// every MMA re-reads A (4 KiB) AND the full weight tile (N x 32 B) from shared memory while TMA refills the weight ring at
+// ~0.55 wavefronts/clk: ~1.4 shared-memory wavefronts per clock are requested where the pipe delivers one (ncu: 54-62 %
+// tensor-pipe active at c0/c1).  Two CTAs of a cluster run ONE M = 256 MMA: each CTA contributes its own 128-pixel A tile and
+// HALF of the weight rows, so per SM the weight reads, the weight TMA fill and the L2 weight traffic all halve.
+//   - both CTAs run a TMA producer (own A tile + own half of W); every load signals the LEADER's (rank 0) full barriers
+//   - only the leader issues tcgen05.mma.cta_group::2; its commits are multicast to the empty / tmem_full barriers of both CTAs
+//   - both CTAs run the epilogue on their own TMEM (rows 0-127 / 128-255 of D); all 16 epilogue warps release the leader's
+//     tmem_empty barrier
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_conv2_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  const uint32_t a_slot = p.a_tile_bytes;
+  const uint32_t w_tile = (uint32_t)(p.BN / 2) * 128u;               // this CTA's half of the weight tile
+  const uint32_t w_slot = w_tile;
+  const uint32_t a_ring = smem0, w_ring = a_ring + (uint32_t)p.NA * a_slot;
+  const uint32_t bars = w_ring + (uint32_t)p.NW * w_slot;
+  auto a_full = [&](int s) { return bars + 8u * s; };
+  auto a_empty = [&](int s) { return bars + 8u * (p.NA + s); };
+  auto w_full = [&](int s) { return bars + 16u * p.NA + 8u * s; };
+  auto w_empty = [&](int s) { return bars + 16u * p.NA + 8u * (p.NW + s); };
+  const uint32_t bar_tmem = bars + 16u * (p.NA + p.NW);
+  auto tmem_full = [&](int a) { return bar_tmem + 8u * a; };
+  auto tmem_empty = [&](int a) { return bar_tmem + 16u + 8u * a; };
+  const uint32_t tmem_slot = bar_tmem + 32u;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&p.a_map[0][0]); prefetch_tmap(&p.w_map[0]); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 16); }   // 8 epilogue warps of each CTA
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                                 // barriers of both CTAs are initialised before any remote signal
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int chunks = p.chunks0;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const uint32_t acc_cols = (uint32_t)p.BN;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own pixel tile, own half of the weight rows; completion -> leader's full barriers =====
+    const bool leader = elect_one();
+    int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
+    for (int work = cluster_id; work < p.num_work; work += n_clusters) {
+      const int m = (work / p.n_tiles) * 2 + (int)rank;
+      const int n0 = (work % p.n_tiles) * p.BN + (int)rank * (p.BN / 2);
+      int tn, ty0, tx0;
+      if (m < p.m_tiles) {
+        const int n = m / tiles_per_img, rem = m - n * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        tn = n; ty0 = ty * p.BH; tx0 = tx * p.BW;
+      } else { tn = p.N; ty0 = 0; tx0 = 0; }                          // out-of-range tile: TMA zero-fills
+      for (int r = 0; r < p.R; ++r)
+        for (int ch = 0; ch < chunks; ++ch) {
+          const int c = p.coff0 + ch * TC_BK;
+          for (int s = 0; s < p.S; ++s) {
+            if (!p.strip || s == 0) {
+              mbar_wait(a_empty(ai), aph ^ 1u);
+              if (leader) {
+                if (is_leader) mbar_expect_tx(a_full(ai), 2u * p.a_tx_bytes);       // both CTAs' tiles land on the leader's barrier
+                tma_load_4d_2sm(a_ring + (uint32_t)ai * a_slot, &p.a_map[0][0], c, tx0 + (p.strip ? 0 : s) - p.pad, ty0 + r - p.pad, tn,
+                                mapa_cluster(a_full(ai), 0));
+              }
+              __syncwarp();
+              if (++ai == p.NA) { ai = 0; aph ^= 1u; }
+            }
+            mbar_wait(w_empty(wi), wph ^ 1u);
+            if (leader) {
+              if (is_leader) mbar_expect_tx(w_full(wi), 2u * w_slot);
+              tma_load_3d_2sm(w_ring + (uint32_t)wi * w_slot, &p.w_map[0], ch * TC_BK, n0, r * p.S + s, mapa_cluster(w_full(wi), 0));
+            }
+            __syncwarp();
+            if (++wi == p.NW) { wi = 0; wph ^= 1u; }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    if (is_leader) {
+      // ===== MMA issuer (leader CTA only): M = 256 over the pair =====
+      const bool leader = elect_one();
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
+      int ai = 0, wi = 0; uint32_t aph = 0, wph = 0;
+      int it = 0;
+      for (int work = cluster_id; work < p.num_work; work += n_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty(acc), acc_phase ^ 1u);                  // both CTAs' epilogues have drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t acc_base = tmem_base + (uint32_t)acc * acc_cols;
+        uint32_t cnt = 0;
+        for (int r = 0; r < p.R; ++r)
+          for (int ch = 0; ch < chunks; ++ch)
+            for (int s = 0; s < p.S; ++s) {
+              if (!p.strip || s == 0) mbar_wait(a_full(ai), aph);
+              mbar_wait(w_full(wi), wph);
+              tc_fence_after();
+              const uint64_t adesc = umma_desc(a_ring + (uint32_t)ai * a_slot + (p.strip ? (uint32_t)s * 128u : 0u));
+              const uint64_t bdesc = umma_desc(w_ring + (uint32_t)wi * w_slot);
+              if (leader) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                  umma_f16_2sm(acc_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, cnt > 0 ? 1u : 0u);
+                  ++cnt;
+                }
+                umma_commit_2sm(w_empty(wi));                         // frees the weight slot in both CTAs
+                if (!p.strip || s == p.S - 1) umma_commit_2sm(a_empty(ai));
+              } else {
+                cnt += TC_BK / 16;
+              }
+              __syncwarp();
+              if (++wi == p.NW) { wi = 0; wph ^= 1u; }
+              if (!p.strip || s == p.S - 1) { if (++ai == p.NA) { ai = 0; aph ^= 1u; } }
+            }
+        if (leader) umma_commit_2sm(tmem_full(acc));
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): warps 2..9, TMEM lane quadrant = warp % 4, alternate 16-column chunks per half =====
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int HW = p.H * p.W;
+    int it = 0;
+    for (int work = cluster_id; work < p.num_work; work += n_clusters, ++it) {
+      const int m = (work / p.n_tiles) * 2 + (int)rank;
+      const int n0 = (work % p.n_tiles) * p.BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tmem_full(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t acc_base = tmem_base + (uint32_t)acc * acc_cols;
+      if (m < p.m_tiles) {
+        const int n = m / tiles_per_img, rem = m - n * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int oy = ty * p.BH + row / p.BW, ox = tx * p.BW + row % p.BW;
+        const bool valid = oy < p.H && ox < p.W;
+        const long long pix = (long long)n * HW + (long long)oy * p.W + ox;
+        for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
+          uint32_t raw[16];
+          tmem_ld16(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, raw);
+          const int co0 = n0 + c0;
+          if (!valid || co0 >= p.Cout) continue;
+          uint4 hi4[2];
+          __half2* hh = reinterpret_cast<__half2*>(hi4);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+            float v0 = fmaf(__uint_as_float(raw[j]), p.inv_scale, b.x), v1 = fmaf(__uint_as_float(raw[j + 1]), p.inv_scale, b.y);
+            float v2 = fmaf(__uint_as_float(raw[j + 2]), p.inv_scale, b.z), v3 = fmaf(__uint_as_float(raw[j + 3]), p.inv_scale, b.w);
+            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+            hh[j / 2] = __floats2half2_rn(fminf(fmaxf(v0, -65504.f), 65504.f), fminf(fmaxf(v1, -65504.f), 65504.f));
+            hh[j / 2 + 1] = __floats2half2_rn(fminf(fmaxf(v2, -65504.f), 65504.f), fminf(fmaxf(v3, -65504.f), 65504.f));
+          }
+          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0);
+          oh[0] = hi4[0]; oh[1] = hi4[1];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(tmem_empty(acc), 0));   // release on the LEADER's barrier
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                                                 // both CTAs are done with TMEM and with each other's barriers
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -414,7 +599,8 @@ static void tc_init() {
   if (cudaFuncSetAttribute(tc_conv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(tc_conv_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(tc_conv_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(tc_conv_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess) {
+      cudaFuncSetAttribute(tc_conv_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess) {
     g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
     return;
   }
@@ -593,11 +779,24 @@ int tc_conv_prepare(TcConvOp* op) {
     while (ks & (ks - 1)) --ks;                                           // power of two (chain = counter & (KS - 1))
     p.KS = ks;
   }
+  // CTA-pair kernel (tc_conv2_kernel): single-pass, hi-plane NHWC output, no residual / mask / second source, N = 192 or 256
+  p.two_cta = (op->passes == 1 && (p.BN == 192 || p.BN == 256) && op->w->cout_pad % p.BN == 0 && op->C1 == 0 && op->stride == 1 &&
+               op->res_hi == nullptr && op->mask == nullptr && op->out_hi != nullptr && op->out_lo == nullptr && !op->sigmoid &&
+               op->Cout % 16 == 0 && p.m_tiles >= 2 && env_int("KG_TC_2CTA", 1) != 0) ? 1 : 0;
+  if (p.two_cta) {
+    p.MT = 1; p.KS = 1; p.acc_stages = 2; p.wg = 1; p.o_tma = 0;
+    const size_t budget2 = TC_MAX_SMEM - 2048;
+    const size_t a_slot = p.a_tile_bytes, w_slot = (size_t)(p.BN / 2) * 128;
+    if (strip) { na = 3; nw = (int)((budget2 - 3 * a_slot) / w_slot); if (nw > 8) nw = 8; }
+    else { int st = (int)(budget2 / (a_slot + w_slot)); if (st > 8) st = 8; na = nw = st; }
+    KG_REQUIRE(na >= 2 && nw >= 2, "tc_conv_prepare: CTA-pair tile does not fit in shared memory");
+    p.NA = na; p.NW = nw;
+  }
   unsigned cols = 32;
   while (cols < (unsigned)(p.acc_stages * p.MT * p.KS * p.BN)) cols *= 2;
   p.tmem_cols = cols;
   p.n_tiles = op->w->cout_pad / p.BN;
-  p.num_work = ceil_div(p.m_tiles, p.MT) * p.n_tiles;
+  p.num_work = ceil_div(p.m_tiles, p.two_cta ? 2 : p.MT) * p.n_tiles;
   p.bias = op->bias; p.inv_scale = op->w->inv_scale;
   p.out_hi = op->out_hi; p.out_lo = op->out_lo; p.res_hi = op->res_hi; p.res_lo = op->res_lo;
   p.relu = op->relu; p.sigmoid = op->sigmoid; p.mask = op->mask;
@@ -608,7 +807,7 @@ int tc_conv_prepare(TcConvOp* op) {
     KG_TRY(encode_act_map(&p.a_map[1][0], op->in1_hi, op->in1_C, op->W, op->H, op->N, box_w, p.BH));
     if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[1][1], op->in1_lo, op->in1_C, op->W, op->H, op->N, box_w, p.BH));
   }
-  KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
+  KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.two_cta ? p.BN / 2 : p.BN, p.wg));
   if (p.NPL == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
   if (p.o_tma) {
     KG_TRY(encode_act_map(&p.o_map[0], op->out_hi, op->Cout, op->W, op->H, op->N, p.o_bw, 32 / p.o_bw));
@@ -616,14 +815,16 @@ int tc_conv_prepare(TcConvOp* op) {
   }
   const int persist = env_int("KG_TC_CTAS", g_num_sms);
   op->grid_x = (unsigned)std::min(p.num_work, std::max(1, persist));
+  if (p.two_cta) op->grid_x = (unsigned)std::min(2 * p.num_work, std::max(2, persist & ~1));   // whole CTA pairs
   op->grid_y = 1;
   op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.wg * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024 + (p.o_tma ? 65536 : 0));
+  if (p.two_cta) op->smem_bytes = (unsigned)((size_t)p.NA * p.a_tile_bytes + (size_t)p.NW * (p.BN / 2) * 128 + 16 * (p.NA + p.NW) + 128 + 1024);
   KG_REQUIRE(op->smem_bytes <= (unsigned)TC_MAX_SMEM, "tc_conv_prepare: smem %u > %d", op->smem_bytes, TC_MAX_SMEM);
   op->params = sp;
   if (env_int("KG_TC_DEBUG", 0))
-    fprintf(stderr, "[tc] N%d %dx%d C%d+%d->%d k%dx%d s%d passes%d | BN%d BW%d BH%d MT%d KS%d acc%d strip%d wg%d otma%d NA%d NW%d work%d grid%u smem%u tmem%u\n",
+    fprintf(stderr, "[tc] N%d %dx%d C%d+%d->%d k%dx%d s%d passes%d | BN%d BW%d BH%d MT%d KS%d acc%d strip%d wg%d otma%d 2cta%d NA%d NW%d work%d grid%u smem%u tmem%u\n",
             op->N, op->H, op->W, op->C0, op->C1, op->Cout, op->R, op->S, op->stride, op->passes, p.BN, p.BW, p.BH, p.MT, p.KS, p.acc_stages,
-            p.strip, p.wg, p.o_tma, p.NA, p.NW, p.num_work, op->grid_x, op->smem_bytes, p.tmem_cols);
+            p.strip, p.wg, p.o_tma, p.two_cta, p.NA, p.NW, p.num_work, op->grid_x, op->smem_bytes, p.tmem_cols);
   return KG_OK;
 }
 
@@ -632,6 +833,12 @@ int tc_conv_launch(const TcConvOp* op, float* out32, cudaStream_t stream) {
   TcParams p = *reinterpret_cast<const TcParams*>(op->params.get());
   p.out32 = out32;
   dim3 grid(op->grid_x, op->grid_y, 1);
+  if (p.two_cta && out32 == nullptr) {
+    tc_conv2_kernel<<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
+    KG_CUDA_CHECK(cudaGetLastError());
+    return KG_OK;
+  }
+  KG_REQUIRE(!p.two_cta, "tc_conv_launch: the CTA-pair kernel has no fp32 NCHW output");
   if (p.MT == 1 && p.passes == 1) tc_conv_kernel<1, 1><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
   else if (p.MT == 2 && p.passes == 1) tc_conv_kernel<2, 1><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
   else if (p.MT == 1 && p.passes == 3) tc_conv_kernel<1, 3><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);

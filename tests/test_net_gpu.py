@@ -177,6 +177,24 @@ def test_conv_shift_kernel(case, mode):
     assert err <= tol, f"max err {err} > {tol}"
 
 
+TWO_CTA_CASES = [  # first-layer head class through the CTA-pair (cta_group::2) kernel: single pass, hi-plane output
+    (2, 64, 6, 256, 192, 7, 1, True, False),    # c0 / c1 class: strip mode, N = 192, 2 tiles per row
+    (1, 64, 5, 128, 192, 7, 1, True, False),    # odd number of pixel tiles: the peer CTA of the last pair idles
+    (1, 256, 4, 128, 768, 7, 1, True, False),   # c2 class: N tile 256 x 3, 4 K chunks
+    (2, 128, 8, 64, 256, 3, 1, True, False),    # two image rows per tile (no strip)
+    (1, 64, 16, 16, 192, 7, 1, True, False),    # small map
+]
+
+
+@pytest.mark.parametrize("case", TWO_CTA_CASES)
+def test_conv_cta_pair_kernel(case):
+    x, w, b, pad, r, y = _case(8, *case)
+    got = _conv(x, w, b, 1, pad, case[7], r, 21)
+    scale = float(y.abs().max())
+    err = float((got - y).abs().max())
+    assert err <= 3e-3 * scale + 1e-5, f"max err {err}"
+
+
 def _model(precision):
     from kg_instance_segmentation_b200 import KGnet
     sd = O.make_state_dict(seed=0)
