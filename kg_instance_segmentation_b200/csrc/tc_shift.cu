@@ -51,6 +51,7 @@ struct ShParams {
   int NS;
   unsigned slot_bytes, w_slab, tmem_cols;     // w_slab: bytes reserved per weight plane inside a slot
   unsigned wres_bytes;                        // resident-weights mode: bytes of the weight region in front of the ring
+  int noemit;                                 // diagnostics (KG_SH_NOEMIT=1): the register-shuffle epilogue skips conversion + stores
 };
 
 // Compile-time geometry of one fused launch: up to three convs with O0 / O1 / O2 output channels, TAPS x TAPS filters.
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
             const int cb = half * 32;                        // this warp's 32 channels
             const ShGroup& G = p.grp[0];
             auto emit32 = [&](const float* v, long long pix) __attribute__((always_inline)) {
+              if (p.noemit) return;
               const bool keep = p.mask == nullptr || p.mask[pix] != 0;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -627,6 +629,7 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   if (ns > 8) ns = 8;
   KG_REQUIRE(ns >= 2, "tc_shift_prepare: tile does not fit in shared memory");
   p.NS = ns;
+  p.noemit = getenv("KG_SH_NOEMIT") != nullptr ? 1 : 0;
   op->smem_bytes = (unsigned)(1024 + p.wres_bytes + (size_t)ns * p.slot_bytes + 16 * ns + 64 + buf_bytes + 64);
   op->grid = (unsigned)std::min(p.num_work, tc_num_sms());
   op->params = sp;
