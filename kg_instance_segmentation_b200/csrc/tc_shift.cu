@@ -41,6 +41,8 @@ struct ShGroup { const float* bias; float* out32; int in_coff; float inv_scale; 
 struct ShParams {
   CUtensorMap a_map[2];                       // activation planes (hi, lo)
   CUtensorMap w_map[SH_MAX_UNITS][2];         // weight slab of each unit, planes (hi, lo)
+  CUtensorMap o_map[2];                       // NHWC output planes, boxes of 64 channels x 128 pixels (TMA-store epilogue)
+  unsigned stage_bytes;                       // 0, or 32 KiB of output staging (hi 16 KiB + lo 16 KiB) in front of everything else
   ShGroup grp[SH_MAX_GROUPS];
   __half* out_hi; __half* out_lo;             // NHWC output mode (conv 0)
   const uint8_t* mask;
@@ -125,8 +127,9 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t smem0 = (smem_base + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t wres = smem0;                               // resident weights: [r][chunk][plane] slabs of w_slab bytes
-  const uint32_t ring = smem0 + (WRES ? p.wres_bytes : 0u);
+  const uint32_t stage = smem0;                              // output staging of the register-shuffle epilogue (p.stage_bytes, may be 0)
+  const uint32_t wres = smem0 + p.stage_bytes;               // resident weights: [r][chunk][plane] slabs of w_slab bytes
+  const uint32_t ring = wres + (WRES ? p.wres_bytes : 0u);
   const uint32_t bars = ring + (uint32_t)p.NS * p.slot_bytes;
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (p.NS + s); };
@@ -135,7 +138,8 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
   auto tmem_empty = [&](int a) { return tbar + 16u + 8u * a; };
   const uint32_t wres_bar = tbar + 32u;
   const uint32_t tmem_slot = tbar + 40u;
-  float* buf = reinterpret_cast<float*>(smem_raw + (smem0 - smem_base) + (WRES ? p.wres_bytes : 0u) + (size_t)p.NS * p.slot_bytes + 16u * p.NS + 64u);
+  float* buf = reinterpret_cast<float*>(smem_raw + (smem0 - smem_base) + p.stage_bytes + (WRES ? p.wres_bytes : 0u) + (size_t)p.NS * p.slot_bytes +
+                                        16u * p.NS + 64u);
   const uint32_t w_off = (uint32_t)NPA * SH_A_TILE;          // weight planes follow the activation planes inside a slot
   float* s_bias = buf + p.RB * RS;                           // biases of all convs (a global load per output pixel stalls the emission)
   float* s_edge = s_bias + ((Cfg::NOUT + 3) & ~3);           // register-shuffle epilogue: warp / tile edge exchange (832 floats)
@@ -296,7 +300,12 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
             float* pend = s_edge + 768;                      // partial sum of the previous tile's last pixel
             const int cb = half * 32;                        // this warp's 32 channels
             const ShGroup& G = p.grp[0];
-            auto emit32 = [&](const float* v, long long pix) __attribute__((always_inline)) {
+            // Finished pixels leave through a staging tile in shared memory and ONE TMA store per plane and tile: a lane-per-pixel
+            // direct store writes 16 B per lane at a 128-byte stride, i.e. 32 partial-sector L2 transactions per instruction, and
+            // that alone cost half of the kernel time (c0_conv.2: 2.25 ms with, 1.14 ms without the stores).  Staging row j holds
+            // pixel x0 + j for j < 127; the tile's last pixel waits in "pend" and is stored directly by the next tile.
+            const bool staged = p.stage_bytes != 0;
+            auto emit32 = [&](const float* v, long long pix, int srow) __attribute__((always_inline)) {
               if (p.noemit) return;
               const bool keep = p.mask == nullptr || p.mask[pix] != 0;
 #pragma unroll
@@ -316,10 +325,18 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                   hh[e] = h;
                   ll[e] = __floats2half2_rn(a - hf.x, bq - hf.y);
                 }
-                *reinterpret_cast<uint4*>(p.out_hi + pix * 64 + cb + 8 * k) = h4;
-                if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * 64 + cb + 8 * k) = l4;
+                if (srow >= 0) {                               // 128-byte swizzle of the store's tensor map: 16-byte piece j of row r at (j ^ (r & 7))
+                  const uint32_t a0 = stage + (uint32_t)srow * 128u + ((((uint32_t)(half * 4 + k)) ^ ((uint32_t)srow & 7u)) << 4);
+                  st_shared_v4(a0, h4);
+                  if (p.out_lo != nullptr) st_shared_v4(a0 + 16384u, l4);
+                } else {
+                  *reinterpret_cast<uint4*>(p.out_hi + pix * 64 + cb + 8 * k) = h4;
+                  if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * 64 + cb + 8 * k) = l4;
+                }
               }
             };
+            if (staged && warp == 2 && lane == 0) bulk_wait_read0();   // the previous tile's TMA stores have read the staging tile
+            __syncwarp();                                              // (tcgen05.ld below is warp-collective)
             const long long pix0 = ((long long)n * p.H + y0) * p.W + (long long)tx * 128;
             float z0[32], z2[32];
 #pragma unroll
@@ -335,14 +352,15 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
             if (lane == 0) {
 #pragma unroll
               for (int c = 0; c < 32; ++c) e2[quad * 64 + cb + c] = z2[c];
-              if (!first && quad == 0) {                     // the previous tile's last pixel is complete now
-                float v[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = pend[cb + c] + z2[c];
-                emit32(v, pix0 - 1);
-              }
             }
-            epi_bar();
+            epi_bar();                                       // (also orders the staging writes below after bulk_wait_read0 above)
+            if (lane == 0 && !first && quad == 0) {          // the previous tile's last pixel is complete now
+              float v[32];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = pend[cb + c] + z2[c];
+              emit32(v, pix0 - 1, -1);                         // one pixel per tile: direct store
+            }
+            __syncwarp();                                    // reconverge before the warp-collective shuffles / tcgen05.ld below
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               z0[c] = __shfl_up_sync(0xffffffffu, z0[c], 1);       // left neighbour's tap 0
@@ -371,9 +389,16 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
 #pragma unroll
               for (int c = 0; c < 32; ++c) pend[cb + c] = z0[c];
             } else {
-              emit32(z0, pix0 + t);
+              emit32(z0, pix0 + t, (staged && t < 127) ? t : -1);       // the row's very last pixel goes out directly
             }
+            if (staged) fence_proxy_async_smem();
             epi_bar();
+            if (staged && warp == 2 && lane == 0 && !p.noemit) {
+              tma_store_4d(&p.o_map[0], stage, 0, tx * 128, y0, n);                  // pixels x0 .. x0 + 126
+              if (p.out_lo != nullptr) tma_store_4d(&p.o_map[1], stage + 16384u, 0, tx * 128, y0, n);
+              bulk_commit();
+            }
+            __syncwarp();
             continue;
           }
         }
@@ -481,6 +506,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
       }
     }
   }
+  if (p.stage_bytes != 0 && warp == 2 && lane == 0) bulk_wait_all();   // every TMA store has landed before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -618,7 +644,22 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   }
   p.w_slab = (unsigned)align_up((size_t)maxN * 128, 1024);
   const size_t buf_bytes = ((size_t)p.RB * Cfg::RS + Cfg::NOUT + 4 + 832) * sizeof(float);
-  const size_t fixed = 1024 + 16 * 16 + 64 + buf_bytes + 64;
+  // TMA-store epilogue of the register-shuffle path (64-channel NHWC output, whole-row tiles)
+  { const char* e = getenv("KG_SH_STAGE"); p.stage_bytes = (std::is_same<Cfg, C64Cfg>::value && p.row_mode && op->out_hi != nullptr && !(e && e[0] == '0')) ? 32768u : 0u; }
+  if (p.stage_bytes) {
+    for (int pl = 0; pl < 2; ++pl) {
+      __half* base = pl == 0 ? op->out_hi : op->out_lo;
+      if (base == nullptr) continue;
+      cuuint64_t dims[4] = {64, (cuuint64_t)op->W, (cuuint64_t)op->H, (cuuint64_t)op->N};
+      cuuint64_t strides[3] = {128, (cuuint64_t)op->W * 128, (cuuint64_t)op->H * op->W * 128};
+      cuuint32_t box[4] = {64, 127, 1, 1};                   // pixels x0 .. x0 + 126 of a tile; the 128th is finished by the next tile
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = encode(&p.o_map[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("tc_shift_prepare: cuTensorMapEncodeTiled(output) failed: %d", (int)r); return KG_ERR_CUDA; }
+    }
+  }
+  const size_t fixed = 1024 + 16 * 16 + 64 + buf_bytes + 64 + p.stage_bytes;
   // resident weights: the whole [R][chunks][planes] weight tensor stays in smem when it leaves room for >= 3 activation slots
   const size_t wres_total = (size_t)R * p.kchunks * NPW * p.w_slab;
   const char* wr = getenv("KG_TC_SHIFT_WRES");
@@ -630,7 +671,7 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   KG_REQUIRE(ns >= 2, "tc_shift_prepare: tile does not fit in shared memory");
   p.NS = ns;
   p.noemit = getenv("KG_SH_NOEMIT") != nullptr ? 1 : 0;
-  op->smem_bytes = (unsigned)(1024 + p.wres_bytes + (size_t)ns * p.slot_bytes + 16 * ns + 64 + buf_bytes + 64);
+  op->smem_bytes = (unsigned)(1024 + p.stage_bytes + p.wres_bytes + (size_t)ns * p.slot_bytes + 16 * ns + 64 + buf_bytes + 64);
   op->grid = (unsigned)std::min(p.num_work, tc_num_sms());
   op->params = sp;
   if (getenv("KG_TC_DEBUG"))
