@@ -13,8 +13,11 @@
 //   precision      passes = 1: fp16 x fp16.  passes = 3: split-fp16 (hi*hi + lo*hi + hi*lo), ~fp32 accuracy.
 //   concat         torch.cat((a, b), 1) feeding a conv = two TMA sources walked back to back along K.
 //   epilogue       tcgen05.ld -> * 1/scale + bias (+ residual) -> ReLU / sigmoid -> split-fp16 NHWC and/or fp32 NCHW.
-//   roles          warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue (one TMEM lane quadrant each);
-//                  smem full/empty mbarrier ring between producer and MMA, one tmem_full barrier to the epilogue.
+//   roles          warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (two warps per TMEM lane quadrant);
+//                  smem full/empty mbarrier rings between producer and MMA, tmem_full / tmem_empty barriers per
+//                  accumulator buffer between MMA issuer and epilogue.  Persistent CTAs (one per SM).
+//   CTA pair       tc_conv2_kernel below: the same conv as ONE M = 256 MMA over two SMs (cta_group::2) for the
+//                  single-pass first-layer head convs, where the shared-memory pipe bounds the one-CTA kernel.
 #include "tc_conv.cuh"
 #include "tc_ptx.cuh"
 
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const uint32_t w_tile = (uint32_t)p.BN * 128u;
   const uint32_t w_plane = (uint32_t)p.wg * w_tile;                   // one plane of one W slot: wg taps back to back
   const uint32_t w_slot = (uint32_t)NPL * w_plane;
-  const uint32_t stage0 = smem0;                                      // output staging: 4 epilogue warps x (hi 4 KiB + lo 4 KiB)
+  const uint32_t stage0 = smem0;                                      // output staging (opt-in TMA-store epilogue): 8 epilogue warps x (hi 4 KiB + lo 4 KiB)
   const uint32_t a_ring = smem0 + (p.o_tma ? 65536u : 0u), w_ring = a_ring + (uint32_t)p.NA * a_slot;
   const uint32_t bars = w_ring + (uint32_t)p.NW * w_slot;
   auto a_full = [&](int s) { return bars + 8u * s; };

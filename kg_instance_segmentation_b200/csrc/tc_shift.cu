@@ -17,8 +17,10 @@
 // 1/scale, bias, (sigmoid) and go to the fp32 NCHW head outputs.
 //
 //   roles   warp 0: TMA producer (A tile 128 px x 64 ch + the unit's weight slab per slot), warp 1: MMA issuer,
-//           warps 2-5: epilogue.  One smem ring of NS uniform slots, full/empty mbarriers; single TMEM accumulator set
-//           (tmem_full / tmem_empty hand-off: the MMAs of tile i+1 start as soon as tile i's Z has been read).
+//           warps 2-9: epilogue (two per TMEM lane quadrant, alternate 16-channel batches).  One smem ring of NS uniform
+//           slots, full/empty mbarriers; one or two TMEM accumulator sets (tmem_full / tmem_empty hand-off).
+//   64-channel 3x3 convs (NHWC out): 1 / 2 / 3 split-fp16 passes, weights resident in smem when they fit, shift-add in
+//           registers by warp shuffle for whole-row tiles, outputs staged in smem and written by TMA stores.
 #include "tc_shift.cuh"
 #include "tc_conv.cuh"
 #include "tc_ptx.cuh"
