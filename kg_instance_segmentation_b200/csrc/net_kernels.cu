@@ -313,34 +313,55 @@ int launch_fill_rects(uint8_t* mask, const RectProb* rects, int nrect, cudaStrea
 
 // ------------------------------------------------------------------------------------------------
 // nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (KGnet.py:134,282).
+// One thread = one output pixel x 8 channels (16-byte loads / stores per plane; the scalar version moved 2 bytes per lane).
 __global__ void __launch_bounds__(256) maxpool_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                                                       __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int Hin,
                                                       int Win, int Hout, int Wout, int C) {
-  const long long total = (long long)N * Hout * Wout * C;
+  const int cg = C >> 3;
+  const long long total = (long long)N * Hout * Wout * cg;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
-  const int c = (int)(e % C);
-  long long q = e / C;
+  const int c = (int)(e % cg) * 8;
+  long long q = e / cg;
   const int ox = (int)(q % Wout); q /= Wout;
   const int oy = (int)(q % Hout);
   const int n = (int)(q / Hout);
-  float m = -INFINITY;
+  float m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
   for (int dy = -1; dy <= 1; ++dy) {
     const int iy = oy * 2 + dy;
     if (iy < 0 || iy >= Hin) continue;
     for (int dx = -1; dx <= 1; ++dx) {
       const int ix = ox * 2 + dx;
       if (ix < 0 || ix >= Win) continue;
-      m = fmaxf(m, ld_split(in_hi, in_lo, (((long long)n * Hin + iy) * Win + ix) * C + c));
+      float v[8];
+      ld8_split(in_hi, in_lo, (((long long)n * Hin + iy) * Win + ix) * C + c, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
     }
   }
-  st_split(out_hi, out_lo, e, m);
+  uint4 h4, l4;
+  __half2* hh = reinterpret_cast<__half2*>(&h4);
+  __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = fminf(fmaxf(m[2 * j], -65504.f), 65504.f), b2 = fminf(fmaxf(m[2 * j + 1], -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b2);
+    const float2 hf = __half22float2(h);
+    hh[j] = h;
+    ll[j] = __floats2half2_rn(a - hf.x, b2 - hf.y);
+  }
+  const long long o = (((long long)n * Hout + oy) * Wout + ox) * C + c;
+  *reinterpret_cast<uint4*>(out_hi + o) = h4;
+  if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + o) = l4;
 }
 
 int launch_maxpool3x3s2(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int N, int Hin, int Win, int C,
                         cudaStream_t s) {
+  KG_REQUIRE((C & 7) == 0, "maxpool: channel count must be a multiple of 8 (C=%d)", C);
   const int Hout = (Hin + 2 - 3) / 2 + 1, Wout = (Win + 2 - 3) / 2 + 1;
-  const long long total = (long long)N * Hout * Wout * C;
+  const long long total = (long long)N * Hout * Wout * (C >> 3);
   maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, N, Hin, Win, Hout, Wout, C);
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;

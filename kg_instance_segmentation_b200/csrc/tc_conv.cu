@@ -284,11 +284,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             v[j + 2] = fmaf(v[j + 2], p.inv_scale, b.z); v[j + 3] = fmaf(v[j + 3], p.inv_scale, b.w);
           }
           if (p.res_hi != nullptr && valid) {
-            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + pix * p.Cout + co0);
-            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + pix * p.Cout + co0);
+            uint4 rhv[2], rlv[2];
+            ld_global_nc_v8(p.res_hi + pix * p.Cout + co0, rhv[0], rhv[1]);
+            ld_global_nc_v8(p.res_lo + pix * p.Cout + co0, rlv[0], rlv[1]);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const uint4 a = __ldg(rh + q), b = __ldg(rl + q);
+              const uint4 a = rhv[q], b = rlv[q];
               const __half2* ah = reinterpret_cast<const __half2*>(&a);
               const __half2* bh = reinterpret_cast<const __half2*>(&b);
 #pragma unroll
@@ -346,12 +347,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 }
               }
             } else {
-              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0);
-              oh[0] = hi4[0]; oh[1] = hi4[1];
-              if (p.out_lo != nullptr) {
-                uint4* ol = reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + co0);
-                ol[0] = lo4[0]; ol[1] = lo4[1];
-              }
+              st_global_v8(p.out_hi + pix * p.Cout + co0, hi4[0], hi4[1]);
+              if (p.out_lo != nullptr) st_global_v8(p.out_lo + pix * p.Cout + co0, lo4[0], lo4[1]);
             }
           }
           if (p.out32 != nullptr && valid) {
@@ -556,8 +553,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_co
             hh[j / 2] = __floats2half2_rn(fminf(fmaxf(v0, -65504.f), 65504.f), fminf(fmaxf(v1, -65504.f), 65504.f));
             hh[j / 2 + 1] = __floats2half2_rn(fminf(fmaxf(v2, -65504.f), 65504.f), fminf(fmaxf(v3, -65504.f), 65504.f));
           }
-          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + co0);
-          oh[0] = hi4[0]; oh[1] = hi4[1];
+          st_global_v8(p.out_hi + pix * p.Cout + co0, hi4[0], hi4[1]);
         }
       }
       tc_fence_before();

@@ -137,6 +137,17 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on 
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane-per-pixel epilogue moves 16 channels = one full 32-byte sector per
+// instruction instead of two partial-sector 16-byte pieces.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y),
+               "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
 // 8 consecutive fp32 columns of this warp's 32 TMEM lanes (no wait: pair with tmem_ld_wait)
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

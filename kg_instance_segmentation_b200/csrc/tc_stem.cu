@@ -143,10 +143,8 @@ __global__ void __launch_bounds__(ST_THREADS) tc_stem_kernel(const StemParams p)
           hh[e] = h;
           ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
         }
-        uint4* oh = reinterpret_cast<uint4*>(p.out_hi + g * 64 + c0);
-        uint4* ol = reinterpret_cast<uint4*>(p.out_lo + g * 64 + c0);
-        oh[0] = hi4[0]; oh[1] = hi4[1];
-        ol[0] = lo4[0]; ol[1] = lo4[1];
+        st_global_v8(p.out_hi + g * 64 + c0, hi4[0], hi4[1]);
+        st_global_v8(p.out_lo + g * 64 + c0, lo4[0], lo4[1]);
       }
     }
     tc_fence_before();
