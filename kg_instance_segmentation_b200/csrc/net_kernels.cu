@@ -245,11 +245,11 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict_
                                                        int out_ps, int C, const ResizeProb* __restrict__ probs) {
   const ResizeProb pb = probs[blockIdx.z];
   const int cg = C >> 3;   // channel octets: one 16-byte load per plane per corner
-  const long long total = (long long)pb.Hout * pb.Wout * cg;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)pb.Hout * (unsigned)pb.Wout * (unsigned)cg;   // < 2^31 (checked by the launcher): 32-bit index math
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
-  const int c = (int)(e % cg) * 8;
-  const int q = (int)(e / cg);
+  const int q = (int)(e / (unsigned)cg);
+  const int c = (int)(e - (unsigned)q * (unsigned)cg) * 8;
   const int oy = q / pb.Wout, ox = q - oy * pb.Wout;
   const float rh = (float)pb.Hin / (float)pb.Hout, rw = (float)pb.Win / (float)pb.Wout;
   float sy = rh * ((float)oy + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
@@ -288,6 +288,7 @@ int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half*
                     const ResizeProb* probs, int nprob, int max_pix, cudaStream_t s) {
   if (nprob <= 0 || max_pix <= 0) return KG_OK;
   KG_REQUIRE((C & 7) == 0 && (in_ps & 7) == 0 && (out_ps & 7) == 0, "bilinear: channel counts must be multiples of 8 (C=%d)", C);
+  KG_REQUIRE((long long)max_pix * (C >> 3) < (1ll << 31), "bilinear: problem too large (%d pixels x %d channels)", max_pix, C);
   dim3 grid((unsigned)(((long long)max_pix * (C >> 3) + 255) / 256), 1, nprob);
   bilinear_kernel<<<grid, 256, 0, s>>>(in_hi, in_lo, in_ps, out_hi, out_lo, out_ps, C, probs);
   KG_CUDA_CHECK(cudaGetLastError());
