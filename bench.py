@@ -439,8 +439,11 @@ def main():
     import torch
     dist = None
     if world > 1:
+        # NCCL's version banner / debug log must not share stdout with the JSON line: NCCL honours NCCL_DEBUG_FILE only above
+        # the VERSION level, so VERSION (or unset) is raised to WARN and the log goes to stderr
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
