@@ -1,0 +1,32 @@
+"""bench.py contract checks that need no GPU: the reference arm prints exactly one JSON line with the required keys, and the
+roofline `traffic` figure is read from the committed ncu capture."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert "workload" in d["config"]
+
+
+def test_roofline_traffic_comes_from_the_committed_capture():
+    sys.path.insert(0, ROOT)
+    import bench
+    per_launch, src = bench.profiled_traffic()
+    assert src is not None and src.endswith("_traffic.json") and per_launch > 1e8
+    blur, _ = bench.profiled_traffic("decode")
+    assert 5e7 < blur < 5e8        # ~446 MB of accumulators per step over four launches
