@@ -185,6 +185,23 @@ int kg_heads_l2_nchw(const float* d_x, int N, int Cin, int H, int W, const float
  * of the backbone, decoder, first-layer heads, second-layer heads.  n >= 8. */
 int kg_net_plan_info(kg_net* net, double* out, int n);
 
+/* ------------------------------------------------------------------------------------------------
+ * Callers either side of the network.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* test.py:92 for a batch of already-resized images: uint8 NHWC (cv2 BGR order) -> fp32 NCHW, x / 255 - 0.5.
+ * Lets the input cross PCIe as 3 bytes per pixel instead of 12. */
+int kg_preprocess_u8(const uint8_t* d_img, int N, int H, int W, float* d_x, void* stream);
+
+/* InstanceHeat.post_processing (test.py:127-157): for each of the n mask patches (fp32, patch k at
+ * d_masks + d_mask_off[k], row stride d_mask_pitch[k], size d_mask_hw[2k] x d_mask_hw[2k+1]) and its detection row
+ * d_dets[5k..] = (y1, x1, y2, x2, conf) fp32: resize the patch to the rounded box (cv2.resize INTER_LINEAR), paste it
+ * into an input_h x input_w canvas, resize the canvas to image_h x image_w and threshold at seg_thresh.
+ * d_out_masks: [n, image_h, image_w] uint8 in {0, 1}; d_out_dets (or NULL): [n, 5] fp32 boxes in image coordinates. */
+int kg_paste_masks(const float* d_masks, const long long* d_mask_off, const int* d_mask_pitch, const int* d_mask_hw,
+                   const float* d_dets, int n, int input_h, int input_w, int image_h, int image_w, float seg_thresh,
+                   uint8_t* d_out_masks, float* d_out_dets, void* stream);
+
 /* 1 when the tcgen05/TMA path initialised on the current device; kg_tc_status() says why not otherwise. */
 int kg_tc_available(void);
 const char* kg_tc_status(void);

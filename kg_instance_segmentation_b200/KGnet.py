@@ -79,8 +79,15 @@ class _Combination(nn.Module):
 class ResNet(nn.Module):
     """KGnet (KGnet.py:123-350): ResNet truncated after layer3 + decoder + keypoint heads + mask branch."""
 
-    def __init__(self, layers=(3, 4, 6, 3), precision="fast"):
+    def __init__(self, block=None, layers=(3, 4, 6, 3), num_classes=1000, zero_init_residual=False, precision="fast"):
+        """Same positional signature as the reference's ResNet(block, layers, num_classes, zero_init_residual)
+        (KGnet.py:125); `num_classes` is unused there too (no fc layer is built).  `precision` is this package's
+        only extra knob ("fast" | "exact" | "reference")."""
         super().__init__()
+        if block is not None and not isinstance(block, type):     # ResNet([3, 4, 6, 3]) shorthand: first positional = layers
+            block, layers = None, block
+        if block is BasicBlock:
+            _no_basic_block("ResNet(BasicBlock, ...)")
         self.blocks = tuple(int(b) for b in layers[:3])       # layer4 is never built (KGnet.py:131-137)
         self.conv1, self.bn1 = _Conv(3, 64, 7, False), _BN(64)
         inpl = 64
@@ -105,8 +112,13 @@ class ResNet(nn.Module):
         for s, c in ((3, 512), (2, 256), (1, 64), (0, 64)):
             for name, co in _HEADS:
                 setattr(self, f"{name}_c{s}", _seq(_0=_Conv(c, c, 7, True), _2=_Conv(c, co, 7, True)))
+        if zero_init_residual:                                 # KGnet.py:219-224
+            for m in self.modules():
+                if isinstance(m, _Bottleneck):
+                    nn.init.constant_(m.bn3.weight, 0)
         self.precision = precision
         self.export_feats = True
+        self._fwd_serial = 0
         self._handle = None
         self._weights_sig = None
         self._ws = {}
@@ -208,22 +220,24 @@ class ResNet(nn.Module):
             _cabi.check(_cabi.lib().kg_net_forward_dec(self._handle, x.data_ptr(), N, H, W, heads_p, feats_p, prec, ws.data_ptr(),
                                                        ws.numel(), torch.cuda.current_stream().cuda_stream, C.byref(nl)))
         self.last_launches = nl.value
+        # every forward_dec gets a serial number: a _FeatList from an EARLIER pass must not match the workspace contents
+        # of a later one (with export_feats=False the list holds no tensors that could tell the two apart)
+        self._fwd_serial += 1
         feat_list = _FeatList(feats if feats is not None else [None] * 5)
-        feat_list.owner_key = (id(self), N, H, W, prec)
+        feat_list.owner_key = (id(self), N, H, W, prec, self._fwd_serial)
         self._last = (feat_list.owner_key, ws, [None if t is None else (t.data_ptr(), t._version) for t in feat_list])
         return outs[0], outs[1], outs[2], outs[3], feat_list
 
     # ---- KGnet.py:246-256 -----------------------------------------------------------------------
     def get_patches(self, box, feat):
-        y1, x1, y2, x2 = box
-        _, h, w = feat.shape
-        y1 = np.maximum(0, np.int32(np.round(y1 * h)))
-        x1 = np.maximum(0, np.int32(np.round(x1 * w)))
-        y2 = np.minimum(np.int32(np.round(y2 * h)), h - 1)
-        x2 = np.minimum(np.int32(np.round(x2 * w)), w - 1)
-        if y2 < y1 or x2 < x1 or y2 - y1 < 2 or x2 - x1 < 2:
+        """Crop of one [C,h,w] feature map for a box given in normalised (y1,x1,y2,x2) coordinates, or None when the
+        crop is thinner than 2 px.  Same rounding as the device path (`patch_rect` in csrc/net.cu): half-to-even on
+        float32 products, clamped to the map."""
+        rect = patch_rect(box, feat.shape[-2], feat.shape[-1])
+        if rect is None:
             return None
-        return feat[:, y1:y2, x1:x2].unsqueeze(0)
+        top, left, bottom, right = rect
+        return feat[None, :, top:bottom, left:right]
 
     # ---- KGnet.py:321-350 -----------------------------------------------------------------------
     def forward_seg(self, feat_seg, bboxes):
@@ -242,7 +256,7 @@ class ResNet(nn.Module):
                     all((t is None and s is None) or (t is not None and s is not None and (t.data_ptr(), t._version) == s)
                         for t, s in zip(feat_seg, self._last[2])))
         if internal:
-            _, N, H, W, prec = self._last[0]
+            _, N, H, W, prec, _ = self._last[0]
             ws = self._last[1]
             device = ws.device
         else:
@@ -301,6 +315,19 @@ class ResNet(nn.Module):
         return dec0, dec1, dec2, dec3, seg
 
 
+def patch_rect(box_norm, h, w):
+    """Integer crop rectangle (top, left, bottom, right) of a normalised box on an h x w map (KGnet.py:246-256), or
+    None.  float32 arithmetic, round-half-to-even, like NumPy on the reference's float32 scalars."""
+    b = np.asarray(box_norm, np.float32)
+    lo = np.rint(b[:2] * np.float32([h, w])).astype(np.int64)
+    hi = np.rint(b[2:4] * np.float32([h, w])).astype(np.int64)
+    lo = np.maximum(lo, 0)
+    hi = np.minimum(hi, [h - 1, w - 1])
+    if (hi - lo < 2).any():
+        return None
+    return int(lo[0]), int(lo[1]), int(hi[0]), int(hi[1])
+
+
 class SegResult:
     """Packed output of forward_seg: `masks` is one fp32 device buffer; patch k of the concatenated box list lives at
     masks[off[slot] + y * pitch[slot] + x] for slot = index[k] >= 0 (index -1: the box was skipped, KGnet.py:341-342)."""
@@ -320,6 +347,8 @@ class SegResult:
         """[mask_patches, mask_dets] nested like the reference's forward_seg return value (KGnet.py:346-350)."""
         mask_patches = [[] for _ in range(self.nimg)]
         mask_dets = [[] for _ in range(self.nimg)]
+        out = _SegLists([mask_patches, mask_dets])
+        out.packed = self
         k = 0
         for i in range(self.nimg):
             for _ in range(int(self.counts[i])):
@@ -328,7 +357,17 @@ class SegResult:
                     mask_patches[i].append(pt)
                     mask_dets[i].append(torch.Tensor(np.append(self.boxes[k, :4], self.boxes[k, 4])))
                 k += 1
-        return [mask_patches, mask_dets]
+        return out
+
+    def paste_geometry(self):
+        """(buffer, float offsets, row pitches, (h, w)) of the kept patches in as_lists() order (for kg_paste_masks)."""
+        slots = self.index[self.index >= 0]
+        return self.masks, self.off[slots], self.pitch[slots], self.hw[slots]
+
+
+class _SegLists(list):
+    """[mask_patches, mask_dets] (a plain list to every caller) that remembers the packed buffer its patches view."""
+    packed = None
 
 
 class _FeatList(list):
@@ -350,24 +389,61 @@ def resnet34(pretrained=False, **kwargs):
     _no_basic_block("resnet34")
 
 
-def _make(layers, pretrained, kwargs):
-    model = ResNet(layers, **kwargs)
+class Bottleneck:
+    """Block-type marker with the reference's name and expansion (KGnet.py:64-66) for `ResNet(Bottleneck, layers)`."""
+    expansion = 4
+
+
+class BasicBlock:
+    """Marker only: the reference's BasicBlock variants cannot run its own decoder (see _no_basic_block)."""
+    expansion = 1
+
+
+model_urls = {   # KGnet.py:12-18 (never fetched here: see _load_pretrained)
+    "resnet50": "https://download.pytorch.org/models/resnet50-19c8e357.pth",
+    "resnet101": "https://download.pytorch.org/models/resnet101-5d3b4d8f.pth",
+    "resnet152": "https://download.pytorch.org/models/resnet152-b121ed2d.pth",
+}
+
+
+def _load_pretrained(model, arch):
+    """`pretrained=True` in the reference pulls the ImageNet trunk with model_zoo.load_url and loads it with strict=False
+    (KGnet.py:383-386); test.py:53 / eval.py:31 construct the model that way and then overwrite EVERY tensor with
+    `load_weights(end_model.pth)`.  This package never touches the network: a local copy of the torchvision checkpoint
+    is used when one exists ($KGNET_PRETRAINED, or the torch hub cache), otherwise construction proceeds with the random
+    initialisation and a warning -- the result after load_weights() is identical."""
+    import os
+    import warnings
+    name = os.path.basename(model_urls[arch])
+    cands = [os.environ.get("KGNET_PRETRAINED", ""),
+             os.path.join(torch.hub.get_dir(), "checkpoints", name),
+             os.path.join(os.path.expanduser("~"), ".torch", "models", name)]
+    for c in cands:
+        if c and os.path.isfile(c):
+            model.load_state_dict(torch.load(c, map_location="cpu"), strict=False)
+            return True
+    warnings.warn(f"KGnet.{arch}(pretrained=True): no local copy of {name} (offline; set KGNET_PRETRAINED=<file>): keeping the "
+                  "random initialisation. Load a trained checkpoint with load_state_dict().", stacklevel=3)
+    return False
+
+
+def _make(arch, layers, pretrained, kwargs):
+    model = ResNet(Bottleneck, layers, **kwargs)
     if pretrained:
-        raise RuntimeError("pretrained=True downloads ImageNet weights in the reference (KGnet.py:383-386); there is no "
-                           "network here: construct with pretrained=False and load_state_dict() a checkpoint")
+        _load_pretrained(model, arch)
     return model
 
 
 def resnet50(pretrained=False, **kwargs):
     """KGnet.py:377-386."""
-    return _make((3, 4, 6, 3), pretrained, kwargs)
+    return _make("resnet50", (3, 4, 6, 3), pretrained, kwargs)
 
 
 def resnet101(pretrained=False, **kwargs):
     """KGnet.py:389-398."""
-    return _make((3, 4, 23, 3), pretrained, kwargs)
+    return _make("resnet101", (3, 4, 23, 3), pretrained, kwargs)
 
 
 def resnet152(pretrained=False, **kwargs):
     """KGnet.py:401-410."""
-    return _make((3, 8, 36, 3), pretrained, kwargs)
+    return _make("resnet152", (3, 8, 36, 3), pretrained, kwargs)

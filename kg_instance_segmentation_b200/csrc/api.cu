@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "decode.cuh"
 
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -54,14 +55,15 @@ void stage_end(int id, cudaStream_t s) {
   g_timing.recs.push_back({id, g_timing.open_ev[id], e});
 }
 
-// Cached device buffers of kg_decode_host (grown on demand, never shrunk).
+// Cached device buffers of kg_decode_host (grown on demand, never shrunk), one set per CUDA device.
 struct HostDecodeCtx {
-  std::mutex mu;
   void* d_in = nullptr; size_t in_bytes = 0;
   void* d_ws = nullptr; size_t ws_bytes = 0;
   void* d_out = nullptr; size_t out_bytes = 0;
+  int* h_status = nullptr;     // pinned
 };
-static HostDecodeCtx g_hd;
+static std::mutex g_hd_mu;
+static std::map<int, HostDecodeCtx> g_hd_by_device;
 
 static int grow(void** p, size_t* have, size_t need) {
   if (*have >= need) return KG_OK;
@@ -128,7 +130,11 @@ int kg_decode_host(const kg_decode_config* cfg, const float* const* h_kp, const 
              "kg_decode_host: null argument");
   KG_REQUIRE(cfg->n_scales >= 1 && cfg->n_scales <= KG_MAX_SCALES, "kg_decode_host: n_scales=%d", cfg->n_scales);
   cudaStream_t stream = (cudaStream_t)stream_;
-  std::lock_guard<std::mutex> lock(g_hd.mu);
+  std::lock_guard<std::mutex> lock(g_hd_mu);
+  int dev = 0;
+  KG_CUDA_CHECK(cudaGetDevice(&dev));
+  HostDecodeCtx& g_hd = g_hd_by_device[dev];
+  if (g_hd.h_status == nullptr) KG_CUDA_CHECK(cudaMallocHost(&g_hd.h_status, sizeof(int)));
   kg_decode_scale sc[KG_MAX_SCALES] = {};
   size_t in_bytes = 0;
   for (int s = 0; s < cfg->n_scales; ++s) {
@@ -158,11 +164,11 @@ int kg_decode_host(const kg_decode_config* cfg, const float* const* h_kp, const 
   out.d_det_count = o.take<int>(cfg->N);
   out.d_status = o.take<int>(1);
   KG_TRY(kg::decode_launch(cfg, sc, &out, g_hd.d_ws, g_hd.ws_bytes, stream, nullptr));
-  int status = 0;
   KG_CUDA_CHECK(cudaMemcpyAsync(h_dets, out.d_dets, det_bytes, cudaMemcpyDeviceToHost, stream));
   KG_CUDA_CHECK(cudaMemcpyAsync(h_det_count, out.d_det_count, sizeof(int) * cfg->N, cudaMemcpyDeviceToHost, stream));
-  KG_CUDA_CHECK(cudaMemcpyAsync(&status, out.d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  KG_CUDA_CHECK(cudaMemcpyAsync(g_hd.h_status, out.d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
   KG_CUDA_CHECK(cudaStreamSynchronize(stream));
+  const int status = *g_hd.h_status;
   if (status != 0) {
     kg::set_error("kg_decode_host: device list overflow (status=%d): raise max_peaks/max_boxes", status);
     return KG_ERR_CAPACITY;

@@ -16,7 +16,7 @@
 namespace kg {
 
 // scipy.ndimage._filters._gaussian_kernel1d(sigma=2, order=0, radius=8) (postprocessing.py:144);
-// symmetric, taps 0..8 (tap 8 = centre).  tests/test_host_constants.py checks these against SciPy.
+// symmetric, taps 0..8 (tap 8 = centre).  tests/test_cabi_cpu.py (test_gaussian_taps_and_constants_match_scipy) checks these against SciPy.
 __constant__ double c_gauss[9] = {0x1.18aad19e4159bp-14, 0x1.c98b8c5d0dda5p-12, 0x1.227362b5fc92dp-9,
                                   0x1.1f30504e20207p-7,  0x1.ba4d4125ffd2ap-6,  0x1.0941b71ceef37p-4,
                                   0x1.ef9093fc46e5ap-4,  0x1.68856f9ab1982p-3,  0x1.98862a07ae7b4p-3};
@@ -453,6 +453,58 @@ __global__ void __launch_bounds__(256) nms_kernel(const double* __restrict__ sbo
   if (tid == 0) det_count_g[n] = nkeep;
 }
 
+// nms.py:4-53 for lists that do not fit the shared-memory kernel (kg_nms_host with > 8192 boxes): one CTA, sort keys and
+// suppression flags in global scratch ([cap] f64 conf, [cap] i32 index, [cap] u8 flag).  Same order and arithmetic as nms_kernel.
+__global__ void __launch_bounds__(1024) nms_big_kernel(const double* __restrict__ boxes, int B, int Bp, double nms_thresh,
+                                                       unsigned char* __restrict__ scratch, double* __restrict__ dets,
+                                                       int* __restrict__ det_count) {
+  double* s_conf = reinterpret_cast<double*>(scratch);
+  int* s_idx = reinterpret_cast<int*>(s_conf + Bp);
+  unsigned char* s_supp = reinterpret_cast<unsigned char*>(s_idx + Bp);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < Bp; e += blockDim.x) {
+    s_conf[e] = e < B ? boxes[(size_t)e * 5 + 4] : -DBL_MAX;
+    s_idx[e] = e < B ? e : -1;
+    s_supp[e] = 0;
+  }
+  __syncthreads();
+  for (int k = 2; k <= Bp; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int e = tid; e < Bp; e += blockDim.x) {
+        const int p = e ^ j;
+        if (p > e) {
+          const double ca = s_conf[e], cb = s_conf[p];
+          const int ia = s_idx[e], ib = s_idx[p];
+          const bool up = (e & k) == 0;
+          const bool in_order = ca > cb || (ca == cb && ia > ib);
+          if (up != in_order) { s_conf[e] = cb; s_conf[p] = ca; s_idx[e] = ib; s_idx[p] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  int nkeep = 0;
+  for (int a = 0; a < B; ++a) {
+    if (s_supp[a]) continue;
+    const int c = s_idx[a];
+    const double cy1 = boxes[(size_t)c * 5], cx1 = boxes[(size_t)c * 5 + 1], cy2 = boxes[(size_t)c * 5 + 2], cx2 = boxes[(size_t)c * 5 + 3];
+    if (tid < 5) dets[(size_t)nkeep * 5 + tid] = boxes[(size_t)c * 5 + tid];
+    ++nkeep;
+    const double carea = (cx2 - cx1) * (cy2 - cy1);
+    for (int b = a + 1 + tid; b < B; b += blockDim.x) {
+      if (s_supp[b]) continue;
+      const double* o = boxes + (size_t)s_idx[b] * 5;
+      const double yy1 = fmax(o[0], cy1), xx1 = fmax(o[1], cx1), yy2 = fmin(o[2], cy2), xx2 = fmin(o[3], cx2);
+      const double w = fmax(0., xx2 - xx1), h = fmax(0., yy2 - yy1);
+      const double inter = w * h;
+      const double oarea = (o[3] - o[1]) * (o[2] - o[0]);
+      const double iou = inter / ((oarea - inter) + carea);
+      if (!(iou <= nms_thresh)) s_supp[b] = 1;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *det_count = nkeep;
+}
+
 // standalone refine/box kernel for host lists (kg_skeletons_to_boxes_host)
 __global__ void __launch_bounds__(256) skeleton_box_kernel(const double* __restrict__ skel, int nskel, double scale,
                                                            int apply_refine, double* __restrict__ boxes,
@@ -588,27 +640,46 @@ int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const 
 }
 
 // ---- host-list helpers ------------------------------------------------------------------------
+// (convenience entry points: allocate, copy and synchronise on a private stream; buffers are released on every path)
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct OwnStream {
+  cudaStream_t s = nullptr;
+  ~OwnStream() { if (s) cudaStreamDestroy(s); }
+};
+}  // namespace
+
 int skeletons_to_boxes_host(const double* h_skel, int n, int box_scale, int apply_refine, uint8_t* h_keep,
                             double* h_boxes, int* n_boxes) {
   KG_REQUIRE(n >= 0 && n_boxes != nullptr, "kg_skeletons_to_boxes_host: bad arguments");
   *n_boxes = 0;
   if (n == 0) return KG_OK;
   KG_REQUIRE(h_skel && h_boxes, "kg_skeletons_to_boxes_host: null buffer");
-  double *d_skel = nullptr, *d_boxes = nullptr; int* d_n = nullptr; uint8_t* d_keep = nullptr;
-  KG_CUDA_CHECK(cudaMalloc(&d_skel, sizeof(double) * 15 * n));
-  KG_CUDA_CHECK(cudaMalloc(&d_boxes, sizeof(double) * 5 * n));
-  KG_CUDA_CHECK(cudaMalloc(&d_n, sizeof(int)));
-  KG_CUDA_CHECK(cudaMalloc(&d_keep, n));
-  KG_CUDA_CHECK(cudaMemcpy(d_skel, h_skel, sizeof(double) * 15 * n, cudaMemcpyHostToDevice));
-  skeleton_box_kernel<<<1, 256>>>(d_skel, n, (double)box_scale, apply_refine, d_boxes, d_n, d_keep);
+  DevBuf skel, boxes, cnt, keep;
+  OwnStream st;
+  KG_CUDA_CHECK(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+  KG_CUDA_CHECK(cudaMalloc(&skel.p, sizeof(double) * 15 * n));
+  KG_CUDA_CHECK(cudaMalloc(&boxes.p, sizeof(double) * 5 * n));
+  KG_CUDA_CHECK(cudaMalloc(&cnt.p, sizeof(int)));
+  KG_CUDA_CHECK(cudaMalloc(&keep.p, n));
+  KG_CUDA_CHECK(cudaMemcpyAsync(skel.p, h_skel, sizeof(double) * 15 * n, cudaMemcpyHostToDevice, st.s));
+  skeleton_box_kernel<<<1, 256, 0, st.s>>>(skel.as<double>(), n, (double)box_scale, apply_refine, boxes.as<double>(), cnt.as<int>(),
+                                           keep.as<uint8_t>());
   KG_CUDA_CHECK(cudaGetLastError());
-  KG_CUDA_CHECK(cudaMemcpy(n_boxes, d_n, sizeof(int), cudaMemcpyDeviceToHost));
-  if (*n_boxes > 0) KG_CUDA_CHECK(cudaMemcpy(h_boxes, d_boxes, sizeof(double) * 5 * *n_boxes, cudaMemcpyDeviceToHost));
-  if (h_keep) KG_CUDA_CHECK(cudaMemcpy(h_keep, d_keep, n, cudaMemcpyDeviceToHost));
-  cudaFree(d_skel); cudaFree(d_boxes); cudaFree(d_n); cudaFree(d_keep);
+  KG_CUDA_CHECK(cudaMemcpyAsync(n_boxes, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st.s));
+  KG_CUDA_CHECK(cudaStreamSynchronize(st.s));
+  if (*n_boxes > 0) KG_CUDA_CHECK(cudaMemcpyAsync(h_boxes, boxes.p, sizeof(double) * 5 * *n_boxes, cudaMemcpyDeviceToHost, st.s));
+  if (h_keep) KG_CUDA_CHECK(cudaMemcpyAsync(h_keep, keep.p, n, cudaMemcpyDeviceToHost, st.s));
+  KG_CUDA_CHECK(cudaStreamSynchronize(st.s));
   return KG_OK;
 }
 
+// nms.py:4-53 for a host list of any length: up to 8192 boxes in the shared-memory kernel, more through the
+// global-memory variant (nms_big_kernel: same order, same arithmetic).
 int nms_host(const double* h_boxes, int n, double nms_thresh, double* h_out, int* n_out) {
   KG_REQUIRE(n >= 0 && n_out != nullptr, "kg_nms_host: bad arguments");
   *n_out = 0;
@@ -616,23 +687,32 @@ int nms_host(const double* h_boxes, int n, double nms_thresh, double* h_out, int
   KG_REQUIRE(h_boxes && h_out, "kg_nms_host: null buffer");
   int cap = 64;
   while (cap < n) cap <<= 1;
-  KG_REQUIRE(cap <= 8192, "kg_nms_host: at most 8192 boxes (got %d)", n);
-  double *d_in = nullptr, *d_boxes = nullptr, *d_dets = nullptr; int* d_ints = nullptr;
-  KG_CUDA_CHECK(cudaMalloc(&d_in, sizeof(double) * 5 * cap));
-  KG_CUDA_CHECK(cudaMalloc(&d_boxes, sizeof(double) * 5 * cap));
-  KG_CUDA_CHECK(cudaMalloc(&d_dets, sizeof(double) * 5 * cap));
-  KG_CUDA_CHECK(cudaMalloc(&d_ints, sizeof(int) * 4));
+  KG_REQUIRE(cap <= (1 << 20), "kg_nms_host: at most 2^20 boxes (got %d)", n);
+  DevBuf in, boxes, dets, ints, scratch;
+  OwnStream st;
+  KG_CUDA_CHECK(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+  KG_CUDA_CHECK(cudaMalloc(&in.p, sizeof(double) * 5 * cap));
+  KG_CUDA_CHECK(cudaMalloc(&boxes.p, sizeof(double) * 5 * cap));
+  KG_CUDA_CHECK(cudaMalloc(&dets.p, sizeof(double) * 5 * cap));
+  KG_CUDA_CHECK(cudaMalloc(&ints.p, sizeof(int) * 4));
   int h_ints[4] = {n, 0, 0, 0};   // [0] list count, [1] box_count, [2] det_count, [3] status
-  KG_CUDA_CHECK(cudaMemcpy(d_ints, h_ints, sizeof(h_ints), cudaMemcpyHostToDevice));
-  KG_CUDA_CHECK(cudaMemcpy(d_in, h_boxes, sizeof(double) * 5 * n, cudaMemcpyHostToDevice));
-  KG_CUDA_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem(8192)));
-  nms_kernel<<<1, 256, nms_smem(cap)>>>(d_in, d_ints, 1, cap, cap, nms_thresh, d_boxes, d_ints + 1, d_dets, d_ints + 2,
-                                        d_ints + 3);
+  KG_CUDA_CHECK(cudaMemcpyAsync(ints.p, h_ints, sizeof(h_ints), cudaMemcpyHostToDevice, st.s));
+  KG_CUDA_CHECK(cudaMemcpyAsync(in.p, h_boxes, sizeof(double) * 5 * n, cudaMemcpyHostToDevice, st.s));
+  int* d_ints = ints.as<int>();
+  if (cap <= 8192) {
+    KG_CUDA_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem(8192)));
+    nms_kernel<<<1, 256, nms_smem(cap), st.s>>>(in.as<double>(), d_ints, 1, cap, cap, nms_thresh, boxes.as<double>(), d_ints + 1,
+                                                dets.as<double>(), d_ints + 2, d_ints + 3);
+  } else {
+    KG_CUDA_CHECK(cudaMalloc(&scratch.p, (size_t)cap * 13));
+    nms_big_kernel<<<1, 1024, 0, st.s>>>(in.as<double>(), n, cap, nms_thresh, scratch.as<unsigned char>(), dets.as<double>(), d_ints + 2);
+  }
   KG_CUDA_CHECK(cudaGetLastError());
-  KG_CUDA_CHECK(cudaMemcpy(h_ints, d_ints, sizeof(h_ints), cudaMemcpyDeviceToHost));
+  KG_CUDA_CHECK(cudaMemcpyAsync(h_ints, ints.p, sizeof(h_ints), cudaMemcpyDeviceToHost, st.s));
+  KG_CUDA_CHECK(cudaStreamSynchronize(st.s));
   *n_out = h_ints[2];
-  if (*n_out > 0) KG_CUDA_CHECK(cudaMemcpy(h_out, d_dets, sizeof(double) * 5 * *n_out, cudaMemcpyDeviceToHost));
-  cudaFree(d_in); cudaFree(d_boxes); cudaFree(d_dets); cudaFree(d_ints);
+  if (*n_out > 0) KG_CUDA_CHECK(cudaMemcpyAsync(h_out, dets.p, sizeof(double) * 5 * *n_out, cudaMemcpyDeviceToHost, st.s));
+  KG_CUDA_CHECK(cudaStreamSynchronize(st.s));
   return KG_OK;
 }
 

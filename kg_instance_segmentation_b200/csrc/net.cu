@@ -172,6 +172,8 @@ static int set_conv(Net* net, const char* name, const float* w, int Cout, int Ci
   KG_REQUIRE(Cout > 0 && Cin > 0 && R > 0 && S > 0, "kg_net_set_conv(%s): bad shape", name);
   ConvW& c = net->convs[name];
   c.name = name; c.Cout = Cout; c.Cin = Cin; c.R = R; c.S = S;
+  // lazily built packings of the PREVIOUS weights (stem image, shift-add slabs) must not survive a weight update
+  c.stemw = TcStemWeights(); c.shift1 = TcShiftPacked(); c.shift3 = TcShiftPacked();
   c.h_w.assign((size_t)R * S * Cin * Cout, 0.f);
   c.h_b.assign(Cout, 0.f);
   for (int co = 0; co < Cout; ++co) {

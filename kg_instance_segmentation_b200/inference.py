@@ -1,21 +1,66 @@
-"""Inference orchestration: the reference's `InstanceHeat.test_inference` (test.py:88-125) for one image, and the
-batched device pipeline `detect_batch` the benchmark times (forward_dec -> decode/group/NMS -> forward_seg)."""
+"""Inference orchestration: the reference's `InstanceHeat.test_inference` / `post_processing` (test.py:88-157) and the
+batched device pipeline `detect_batch` the benchmark times (preprocess -> forward_dec -> decode/group/NMS -> forward_seg
+-> mask paste).  Everything between the host image and the final masks runs in the CUDA library."""
 from __future__ import annotations
 
+import ctypes as C
 import os
 from typing import List, Optional
 
 import numpy as np
 import torch
 
-from . import KGnet, postprocessing
+from . import KGnet, postprocessing, _cabi
 from . import config as cfg
+
+
+def preprocess_u8(images: torch.Tensor) -> torch.Tensor:
+    """uint8 NHWC CUDA batch (cv2 BGR order, already at the network size) -> fp32 NCHW `x / 255 - 0.5` (test.py:92)."""
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3 or not images.is_cuda:
+        raise ValueError(f"expected a CUDA uint8 [N,H,W,3] batch, got {tuple(images.shape)} {images.dtype} {images.device}")
+    images = images.contiguous()
+    N, H, W, _ = images.shape
+    x = torch.empty(N, 3, H, W, dtype=torch.float32, device=images.device)
+    with torch.cuda.device(images.device):
+        _cabi.check(_cabi.lib().kg_preprocess_u8(images.data_ptr(), N, H, W, x.data_ptr(),
+                                                 torch.cuda.current_stream(images.device).cuda_stream))
+    return x
+
+
+def paste_masks(patches: List[torch.Tensor], dets: np.ndarray, input_h, input_w, image_h, image_w, seg_thresh, packed=None):
+    """Device version of the per-box loop of test.py:132-156.  patches: fp32 CUDA tensors (h_k x w_k), dets: (M,5) fp32 rows
+    (y1,x1,y2,x2,conf).  Returns (masks uint8 CUDA [M,image_h,image_w], dets fp32 CUDA [M,5] in image coordinates)."""
+    M = len(patches)
+    dev = patches[0].device if M else torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty(M, image_h, image_w, dtype=torch.uint8, device=dev)
+    out_dets = torch.empty(M, 5, dtype=torch.float32, device=dev)
+    if M == 0:
+        return out, out_dets
+    if packed is not None:        # patches are windows of ONE device buffer (SegResult): no gathering needed
+        buf, off, pitch, hw = packed
+    else:
+        flat = [p.detach().to(torch.float32).contiguous().view(-1) for p in patches]
+        buf = torch.cat(flat)
+        sizes = np.asarray([f.numel() for f in flat], np.int64)
+        off = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        hw = np.asarray([tuple(p.shape) for p in patches], np.int32).reshape(M, 2)
+        pitch = hw[:, 1].copy()
+    meta = np.concatenate([np.ascontiguousarray(off, np.int64).view(np.int32), np.ascontiguousarray(pitch, np.int32),
+                           np.ascontiguousarray(hw, np.int32).reshape(-1),
+                           np.ascontiguousarray(dets, np.float32).reshape(-1).view(np.int32)])
+    d_meta = torch.from_numpy(meta).to(dev)                      # one small H2D for all the geometry
+    p0 = d_meta.data_ptr()
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().kg_paste_masks(buf.data_ptr(), p0, p0 + 8 * M, p0 + 12 * M, p0 + 20 * M, M, int(input_h), int(input_w),
+                                               int(image_h), int(image_w), float(seg_thresh), out.data_ptr(), out_dets.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream))
+    return out, out_dets
 
 
 class InstanceHeat:
     def __init__(self, model=None, precision="fast", device="cuda:0"):
         self.device = torch.device(device)
-        self.model = model if model is not None else KGnet.resnet50(pretrained=False, precision=precision)
+        self.model = model if model is not None else KGnet.resnet50(pretrained=True, precision=precision)   # test.py:53
         self.model.to(self.device).eval()
         self._decoders = {}
         self.last_launches = 0
@@ -34,24 +79,29 @@ class InstanceHeat:
         return d
 
     def detect_batch(self, x, nms_thresh=0.5, with_masks=True, head_override=None, max_peaks=4096, max_boxes=4096, packed=False):
-        """x: [N,3,H,W] fp32 CUDA tensor in the reference's input convention (BGR/255 - 0.5, test.py:92).
+        """x: [N,3,H,W] fp32 CUDA tensor in the reference's input convention (BGR/255 - 0.5, test.py:92), or a uint8
+        [N,H,W,3] CUDA batch (normalised on the device).
         Returns (detections, seg): detections[i] = (M_i,5) float64 array or None (nms.py convention);
         seg = [mask_patches, mask_dets] of forward_seg, or the packed KGnet.SegResult when packed=True (None when
         with_masks is False).
         head_override: optional per-scale (kp, short, mid) CUDA tensors decoded INSTEAD of the network's own head
         outputs (teacher-forced decode load for benchmarking; the network still computes all of its heads)."""
         model = self.model
+        launches = 0
+        if x.dtype == torch.uint8:
+            x = preprocess_u8(x)
+            launches += 1
         keep = model.export_feats
         model.export_feats = False
         try:
             out = model.forward_dec(x)
         finally:
             model.export_feats = keep
-        launches = model.last_launches
+        launches += model.last_launches
         heads = head_override if head_override is not None else [tuple(o) for o in out[:4]]
         N = x.shape[0]
-        dec = self._decoder(N, [tuple(h[0].shape[2:]) for h in heads], nms_thresh, max_peaks, max_boxes)
-        res = dec(heads)
+        shapes = [tuple(h[0].shape[2:]) for h in heads]
+        res = postprocessing.run_with_growth(lambda mp, mb: self._decoder(N, shapes, nms_thresh, mp, mb), heads, max_peaks, max_boxes)
         launches += res.n_launches
         dets = res.detections()                     # the one host sync of the pipeline: boxes are needed on the host
         self.last_result = res
@@ -66,37 +116,28 @@ class InstanceHeat:
 
     # ---- test.py:88-125 ---------------------------------------------------------------------------
     def test_inference(self, args, image, bbox_flag=False):
+        """image: HWC uint8 (cv2.imread).  Returns [masks (M,h,w) f32, dets (M,5) f32], the boxes (bbox_flag) or None."""
         import cv2
-        height, width, c = image.shape
-        img_input = cv2.resize(image, (args.input_w, args.input_h))
-        img_input = torch.FloatTensor(np.transpose(img_input.copy(), (2, 0, 1))).unsqueeze(0) / 255 - 0.5
-        img_input = img_input.to(self.device)
-        dets, seg = self.detect_batch(img_input, nms_thresh=args.nms_thresh, with_masks=not bbox_flag)
-        bboxes = dets[0]
-        if bbox_flag:
-            return bboxes
-        if bboxes is None:
-            return None
+        height, width = image.shape[:2]
+        resized = cv2.resize(image, (args.input_w, args.input_h))                          # host, like the reference (:91)
+        batch = torch.from_numpy(np.ascontiguousarray(resized)).unsqueeze(0).to(self.device)   # 3 B / pixel over PCIe
+        dets, seg = self.detect_batch(batch, nms_thresh=args.nms_thresh, with_masks=not bbox_flag)
+        if bbox_flag or dets[0] is None:
+            return dets[0]
         return self.post_processing(args, seg, width, height)
 
-    # ---- test.py:127-157 (host-side paste/resize with OpenCV, exactly as the reference does) ----
+    # ---- test.py:127-157 ---------------------------------------------------------------------------
     def post_processing(self, args, predictions, image_w, image_h):
-        import cv2
+        """predictions: [mask_patches, mask_dets] as returned by forward_seg.  One device launch (csrc/paste.cu) replaces
+        the reference's per-box download + 2 x cv2.resize; the masks come back as ONE uint8 transfer."""
         if predictions is None:
             return predictions
-        out_masks, out_dets = [], []
         mask_patches, mask_dets = predictions
-        for mask_b_patches, mask_b_dets in zip(mask_patches, mask_dets):
-            for mask_n_patch, mask_n_det in zip(mask_b_patches, mask_b_dets):
-                mask_patch = mask_n_patch.data.cpu().numpy()
-                y1, x1, y2, x2, conf = mask_n_det.data.cpu().numpy()
-                y1 = np.maximum(0, np.int32(np.round(y1))); x1 = np.maximum(0, np.int32(np.round(x1)))
-                y2 = np.minimum(np.int32(np.round(y2)), args.input_h - 1); x2 = np.minimum(np.int32(np.round(x2)), args.input_w - 1)
-                mask = np.zeros((args.input_h, args.input_w), dtype=np.float32)
-                mask[y1:y2, x1:x2] = cv2.resize(mask_patch, (x2 - x1, y2 - y1))
-                mask = cv2.resize(mask, (image_w, image_h))
-                mask = np.where(mask >= args.seg_thresh, 1, 0)
-                out_masks.append(mask)
-                out_dets.append([float(y1) / args.input_h * image_h, float(x1) / args.input_w * image_w,
-                                 float(y2) / args.input_h * image_h, float(x2) / args.input_w * image_w, conf])
-        return [np.asarray(out_masks, np.float32), np.asarray(out_dets, np.float32)]
+        patches = [p for per_image in mask_patches for p in per_image]
+        rows = [np.asarray(d.detach().cpu() if isinstance(d, torch.Tensor) else d, np.float32) for per_image in mask_dets for d in per_image]
+        if not patches:
+            return [np.zeros((0,), np.float32), np.zeros((0,), np.float32)]        # np.asarray([]) twice (test.py:157)
+        packed = getattr(predictions, "packed", None)
+        geom = packed.paste_geometry() if packed is not None else None
+        masks, dets = paste_masks(patches, np.stack(rows), args.input_h, args.input_w, image_h, image_w, args.seg_thresh, geom)
+        return [masks.cpu().numpy().astype(np.float32), dets.cpu().numpy()]

@@ -17,12 +17,18 @@ from . import _cabi
 from . import config as cfg
 
 
-def _as_cuda_f32(t):
+MAX_CAPACITY = 8192      # largest per-(image, scale) peak list / per-image box list the device kernels hold in shared memory
+
+
+def _as_cuda_f32(t, device=None):
+    """Contiguous fp32 CUDA tensor: CUDA inputs stay on THEIR device, host inputs go to `device` (default: current)."""
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(np.asarray(t))
     if not torch.cuda.is_available():
         raise RuntimeError("kg_instance_segmentation_b200 needs a CUDA device (no CPU fallback)")
-    return t.detach().to(device="cuda", dtype=torch.float32).contiguous()
+    if device is None:
+        device = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
 @dataclass
@@ -43,8 +49,12 @@ class DecodeResult:
     status: Optional[torch.Tensor] = None
     n_launches: int = 0
 
+    def overflow(self) -> int:
+        """0, or the status bits of a list overflow (bit0: a peak list, bit1: a box list).  Synchronises."""
+        return int(self.status.item())
+
     def check(self):
-        st = int(self.status.item())
+        st = self.overflow()
         if st:
             raise _cabi.KgError(-3, f"decode list overflow (status={st}: bit0 peaks, bit1 boxes); raise max_peaks/max_boxes")
 
@@ -75,6 +85,10 @@ class Decoder:
         if ws == 0:
             raise _cabi.KgError(-1, self.L.kg_last_error().decode())
         dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.max_peaks, self.max_boxes = int(max_peaks), int(max_boxes)
         self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev)
         self.debug = debug
         f64, i32 = torch.float64, torch.int32
@@ -111,15 +125,17 @@ class Decoder:
         for s, (kp, sh, mid) in enumerate(heads):
             h, w = self.shapes[s]
             for t, c in ((kp, 5), (sh, 10), (mid, 40)):
-                if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != (self.N, c, h, w):
-                    raise ValueError(f"scale {s}: expected contiguous cuda float32 [{self.N},{c},{h},{w}], got "
+                if (t.dtype != torch.float32 or t.device != self.device or not t.is_contiguous() or
+                        tuple(t.shape) != (self.N, c, h, w)):
+                    raise ValueError(f"scale {s}: expected contiguous float32 [{self.N},{c},{h},{w}] on {self.device}, got "
                                      f"{tuple(t.shape)} {t.dtype} {t.device}")
             self.sc[s].d_kp, self.sc[s].d_short, self.sc[s].d_mid = kp.data_ptr(), sh.data_ptr(), mid.data_ptr()
             keep.append((kp, sh, mid))
-        st = stream if stream is not None else torch.cuda.current_stream()
         nl = C.c_int(0)
-        _cabi.check(self.L.kg_decode(C.byref(self.cfg), self.sc, C.byref(self.out), self.workspace.data_ptr(),
-                                     self.workspace.numel(), st.cuda_stream, C.byref(nl)))
+        with torch.cuda.device(self.device):           # kernels must launch on the device that owns the buffers
+            st = stream if stream is not None else torch.cuda.current_stream(self.device)
+            _cabi.check(self.L.kg_decode(C.byref(self.cfg), self.sc, C.byref(self.out), self.workspace.data_ptr(),
+                                         self.workspace.numel(), st.cuda_stream, C.byref(nl)))
         self.result.n_launches = nl.value
         self._keepalive = keep
         return self.result
@@ -128,24 +144,45 @@ class Decoder:
 _decoders = {}
 
 
-def _decoder(N, shapes, box_scales, **kw) -> Decoder:
-    key = (N, tuple(shapes), tuple(box_scales), tuple(sorted(kw.items())))
+def _decoder(N, shapes, box_scales, device, **kw) -> Decoder:
+    key = (N, tuple(shapes), tuple(box_scales), str(device), tuple(sorted(kw.items())))
     d = _decoders.get(key)
     if d is None:
         if len(_decoders) > 8:
             _decoders.clear()
-        d = _decoders[key] = Decoder(N, shapes, box_scales, **kw)
+        d = _decoders[key] = Decoder(N, shapes, box_scales, device=device, **kw)
     return d
 
 
+def run_with_growth(make_decoder, heads, max_peaks, max_boxes):
+    """Run a decode; when a bounded device list overflowed, re-run with doubled capacities (the reference has no caps:
+    postprocessing.py builds Python lists).  Raises only past MAX_CAPACITY entries per (image, scale) list."""
+    while True:
+        res = make_decoder(max_peaks, max_boxes)(heads)
+        st = res.overflow()
+        if not st:
+            return res
+        grown = False
+        if st & 1 and max_peaks < MAX_CAPACITY:
+            max_peaks, grown = max_peaks * 2, True
+        if st & 2 and max_boxes < MAX_CAPACITY:
+            max_boxes, grown = max_boxes * 2, True
+        if not grown:
+            res.check()
+
+
 def decode_batched(heads, nms_thresh=0.5, max_peaks=4096, max_boxes=4096, debug=False) -> DecodeResult:
-    """test.py:105-116 for a whole batch: heads = [[kp_s, short_s, mid_s] for s in 0..3] (NCHW torch tensors)."""
-    hs = [tuple(_as_cuda_f32(t) for t in h) for h in heads]
+    """test.py:105-116 for a whole batch: heads = [[kp_s, short_s, mid_s] for s in 0..3] (NCHW torch tensors).
+    List capacities grow on overflow (up to 8192 peaks per image-scale)."""
+    first = heads[0][0]
+    dev = first.device if isinstance(first, torch.Tensor) and first.is_cuda else None
+    hs = [tuple(_as_cuda_f32(t, dev) for t in h) for h in heads]
+    dev = hs[0][0].device
     N = hs[0][0].shape[0]
     shapes = [tuple(h[0].shape[2:]) for h in hs]
-    d = _decoder(N, shapes, cfg.BOX_SCALES[:len(hs)], nms_thresh=float(nms_thresh), max_peaks=max_peaks,
-                 max_boxes=max_boxes, debug=debug)
-    return d(hs)
+    mk = lambda mp, mb: _decoder(N, shapes, cfg.BOX_SCALES[:len(hs)], dev, nms_thresh=float(nms_thresh), max_peaks=mp,
+                                 max_boxes=mb, debug=debug)
+    return run_with_growth(mk, hs, max_peaks, max_boxes)
 
 
 def _skeleton_list(res: DecodeResult, n, s):
@@ -157,10 +194,10 @@ def _skeleton_list(res: DecodeResult, n, s):
 def get_skeletons_and_masks(kp_maps, short_offsets, mid_offsets):
     """postprocessing.py:129-147: batch x {5,10,40} x H x W tensors -> list of (5,3) float64 [x,y,conf]
     skeletons of batch element 0 (missing keypoints are all-zero rows)."""
-    kp, sh, mid = (_as_cuda_f32(t)[0:1] for t in (kp_maps, short_offsets, mid_offsets))
-    d = _decoder(1, [tuple(kp.shape[2:])], (1,), max_peaks=4096, max_boxes=4096, debug=False)
-    res = d([(kp.contiguous(), sh.contiguous(), mid.contiguous())])
-    res.check()
+    dev = kp_maps.device if isinstance(kp_maps, torch.Tensor) and kp_maps.is_cuda else None
+    kp, sh, mid = (_as_cuda_f32(t, dev)[0:1].contiguous() for t in (kp_maps, short_offsets, mid_offsets))
+    mk = lambda mp, mb: _decoder(1, [tuple(kp.shape[2:])], (1,), kp.device, max_peaks=mp, max_boxes=mb, debug=False)
+    res = run_with_growth(mk, [(kp, sh, mid)], 4096, 4096)
     return _skeleton_list(res, 0, 0)
 
 

@@ -104,18 +104,30 @@ def planted_scene(seed, H, W, n_cells, side=(24, 110), gap=12, noise=0.3):
             pts = np.stack([np.stack([x1, y1], 1), np.stack([x2, y1], 1), np.stack([x1, y2], 1), np.stack([x2, y2], 1),
                             np.stack([(x1 + x2) / 2, (y1 + y2) / 2], 1)], 1)            # [n,5,(x,y)]
             pts = np.floor(pts)
-            yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
             amp = rs.uniform(0.6, 1.0, size=(n, 5))
             owner = np.full((5, h, w), -1, np.int64)
+            R = KP_RADIUS
             for k in range(5):
-                d = np.sqrt((xx[None] - pts[:, k, 0, None, None]) ** 2 + (yy[None] - pts[:, k, 1, None, None]) ** 2)
-                j = d.argmin(0)
-                inside = np.take_along_axis(d, j[None], 0)[0] <= KP_RADIUS
-                owner[k] = np.where(inside, j, -1)
-                jj = np.clip(j, 0, n - 1)
+                # nearest-instance assignment inside the discs, stamped window by window (a disc of radius R lies inside
+                # the (2R+1)^2 window around its centre); strict '<' keeps the FIRST instance on distance ties, like argmin
+                dist = np.full((h, w), np.inf)
+                for j in range(n):
+                    cx, cy = int(pts[j, k, 0]), int(pts[j, k, 1])
+                    xa, xb, ya, yb = max(cx - R, 0), min(cx + R + 1, w), max(cy - R, 0), min(cy + R + 1, h)
+                    if xa >= xb or ya >= yb:
+                        continue
+                    yy, xx = np.meshgrid(np.arange(ya, yb), np.arange(xa, xb), indexing="ij")
+                    d = np.sqrt((xx - pts[j, k, 0]) ** 2 + (yy - pts[j, k, 1]) ** 2)
+                    upd = (d <= R) & (d < dist[ya:yb, xa:xb])
+                    dist[ya:yb, xa:xb] = np.where(upd, d, dist[ya:yb, xa:xb])
+                    owner[k, ya:yb, xa:xb] = np.where(upd, j, owner[k, ya:yb, xa:xb])
+                inside = owner[k] >= 0
+                jj = np.clip(owner[k], 0, n - 1)
+                yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
                 kp[k] = np.where(inside, amp[jj, k], 0.0)
                 short[2 * k] = np.where(inside, pts[jj, k, 0] - xx, 0.0)
                 short[2 * k + 1] = np.where(inside, pts[jj, k, 1] - yy, 0.0)
+            yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
             for m, (a, b) in enumerate(DIR_EDGES):
                 inside = owner[a] >= 0
                 jj = np.clip(owner[a], 0, n - 1)

@@ -413,6 +413,52 @@ def forward_seg(sd, feat_seg, bboxes):
 
 
 # ---------------------------------------------------------------------------------------------
+# InstanceHeat.post_processing / test_inference restated: test.py:88-157
+
+def post_processing(predictions, input_h, input_w, image_w, image_h, seg_thresh):
+    """test.py:127-157: every mask patch is resized to its rounded box, pasted into an input-sized canvas, the canvas is
+    resized to the original image and thresholded.  Returns [masks (M,image_h,image_w) f32 in {0,1}, dets (M,5) f32]."""
+    import cv2
+    if predictions is None:
+        return None
+    masks, dets = [], []
+    for patches_b, dets_b in zip(*predictions):
+        for patch, det in zip(patches_b, dets_b):
+            patch = np.asarray(patch.cpu() if hasattr(patch, "cpu") else patch, np.float32)
+            y1, x1, y2, x2, conf = np.asarray(det.cpu() if hasattr(det, "cpu") else det, np.float32)
+            y1 = np.maximum(0, np.int32(np.round(y1))); x1 = np.maximum(0, np.int32(np.round(x1)))             # :137-138
+            y2 = np.minimum(np.int32(np.round(y2)), input_h - 1); x2 = np.minimum(np.int32(np.round(x2)), input_w - 1)
+            canvas = np.zeros((input_h, input_w), np.float32)
+            canvas[y1:y2, x1:x2] = cv2.resize(patch, (int(x2 - x1), int(y2 - y1)))                           # :143-146
+            canvas = cv2.resize(canvas, (image_w, image_h))                                                  # :147
+            masks.append(np.where(canvas >= seg_thresh, 1, 0))                                               # :148
+            dets.append([float(y1) / input_h * image_h, float(x1) / input_w * image_w,
+                         float(y2) / input_h * image_h, float(x2) / input_w * image_w, conf])
+    return [np.asarray(masks, np.float32), np.asarray(dets, np.float32)]
+
+
+def preprocess_image(image, input_h, input_w):
+    """test.py:91-92: cv2.resize (bilinear) to the network size, HWC uint8 BGR -> [1,3,H,W] f32 in [-0.5, 0.5]."""
+    import cv2
+    torch, _ = _t()
+    img = cv2.resize(image, (input_w, input_h))
+    return torch.FloatTensor(np.transpose(img.copy(), (2, 0, 1))).unsqueeze(0) / 255 - 0.5
+
+
+def test_inference(sd, image, input_h, input_w, nms_thresh=0.5, seg_thresh=0.5, bbox_flag=False):
+    """test.py:88-125 on a reference-format state dict: image HWC uint8 -> [masks, dets] / boxes / None."""
+    height, width, _ = image.shape
+    out = forward_dec(sd, preprocess_image(image, input_h, input_w))
+    heads = [tuple(t[0].numpy() for t in out[s]) for s in range(4)]
+    boxes, _, _ = decode_image(heads, nms_thresh)
+    if bbox_flag:
+        return boxes
+    if boxes is None:
+        return None
+    return post_processing(forward_seg(sd, out[4], [boxes]), input_h, input_w, width, height, seg_thresh)
+
+
+# ---------------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY.md §8d) live in the product package (they are data generators, not the algorithm);
 # re-exported here because the tests and golden generator historically call them through the oracle.
 from kg_instance_segmentation_b200.synthetic import make_state_dict, planted_scene  # noqa: E402,F401

@@ -38,3 +38,46 @@ def test_cpu_input_and_train_mode_are_rejected_loudly():
         m.forward_dec(torch.zeros(1, 3, 64, 64))     # CPU tensor: no CPU fallback
     with pytest.raises(NotImplementedError):
         KGnet.resnet18()
+
+
+def test_reference_constructor_calls_work_unmodified():
+    """test.py:53 / eval.py:31 construct `KGnet.resnet50(pretrained=True)`; train.py-style `ResNet(Bottleneck, layers)` too.
+    Offline there is no ImageNet checkpoint: construction must proceed (with a warning), not raise."""
+    import warnings
+    from kg_instance_segmentation_b200 import KGnet
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = KGnet.resnet50(pretrained=True)
+    assert len(m.state_dict()) == 346
+    assert any("pretrained=True" in str(x.message) for x in w) or True   # a local checkpoint may exist
+    m2 = KGnet.ResNet(KGnet.Bottleneck, [3, 4, 6, 3])
+    assert set(m2.state_dict()) == set(m.state_dict())
+    with pytest.raises(NotImplementedError):
+        KGnet.ResNet(KGnet.BasicBlock, [2, 2, 2, 2])
+
+
+def test_pretrained_loads_a_local_torchvision_checkpoint(tmp_path, monkeypatch):
+    """KGnet.py:385: load_state_dict(..., strict=False) of the ImageNet trunk when a local file exists."""
+    from kg_instance_segmentation_b200 import KGnet
+    donor = KGnet.resnet50(pretrained=False)
+    trunk = {k: torch.full_like(v, 0.25) for k, v in donor.state_dict().items() if k.startswith(("conv1.", "bn1.weight", "layer1.0.conv1"))}
+    trunk["fc.weight"] = torch.zeros(10, 10)          # torchvision keys the truncated model does not have
+    f = tmp_path / "resnet50-19c8e357.pth"
+    torch.save(trunk, f)
+    monkeypatch.setenv("KGNET_PRETRAINED", str(f))
+    m = KGnet.resnet50(pretrained=True)
+    assert float(m.conv1.weight.mean()) == 0.25 and float(m.layer1[0].conv1.weight.mean()) == 0.25
+
+
+def test_patch_rect_matches_oracle_rounding():
+    import numpy as np
+    from kg_instance_segmentation_b200 import KGnet
+    rs = np.random.RandomState(0)
+    for _ in range(500):
+        y1, x1 = rs.uniform(-0.1, 0.9, 2); y2, x2 = y1 + rs.uniform(0, 0.5), x1 + rs.uniform(0, 0.5)
+        h, w = rs.randint(2, 300, 2)
+        b = np.asarray([y1, x1, y2, x2], np.float32)
+        assert KGnet.patch_rect(b, int(h), int(w)) == O.get_patch_rect(list(b), int(h), int(w))
+    for v in (0.5, 1.5, 2.5, 3.5):      # exact .5 products: half-to-even
+        b = np.asarray([0.0, 0.0, v / 8, v / 8], np.float32)
+        assert KGnet.patch_rect(b, 8, 8) == O.get_patch_rect(list(b), 8, 8)

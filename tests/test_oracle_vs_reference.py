@@ -105,3 +105,46 @@ def test_forward_dec_and_seg_match_reference_module(reference):
         assert torch.equal(a, b)
     for a, b in zip(rseg[1][0], oseg[1][0]):
         assert torch.equal(a, b)
+
+
+def _reference_instance_heat():
+    """The reference's InstanceHeat class (test.py) without running its constructor (which downloads ImageNet weights)."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("kg_reference_test_py", "/root/reference/test.py")
+    mod = importlib.util.module_from_spec(spec)
+    argv = sys.argv
+    try:
+        sys.argv = ["test.py"]
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = argv
+    return mod.InstanceHeat
+
+
+def test_post_processing_restatement_matches_reference(reference):
+    """oracle.post_processing against test.py:127-157 (same cv2 in the same process): bit-identical."""
+    import types
+    IH = _reference_instance_heat()
+    obj = IH.__new__(IH)
+    rs = np.random.RandomState(0)
+    args = types.SimpleNamespace(input_h=96, input_w=128, seg_thresh=0.5)
+    patches = [torch.from_numpy(rs.rand(37, 56).astype(np.float32)), torch.from_numpy(rs.rand(20, 30).astype(np.float32)),
+               torch.from_numpy(rs.rand(17, 23).astype(np.float32))]
+    dets = [torch.Tensor([3.2, 4.7, 40.4, 60.6, 0.9]), torch.Tensor([10., 20., 30., 50., 0.5]), torch.Tensor([8., 9., 41., 70., 0.3])]
+    preds = [[patches[:2], patches[2:]], [dets[:2], dets[2:]]]
+    for iw, ih in ((128, 96), (200, 150), (61, 47)):
+        ref = IH.post_processing(obj, args, preds, iw, ih)
+        ora = O.post_processing(preds, 96, 128, iw, ih, 0.5)
+        assert ref[0].dtype == ora[0].dtype and np.array_equal(ref[0], ora[0]) and np.array_equal(ref[1], ora[1])
+    assert O.post_processing(None, 96, 128, 10, 10, 0.5) is None
+
+
+def test_preprocess_restatement_matches_reference_lines(reference):
+    """oracle.preprocess_image = test.py:91-92."""
+    import cv2
+    rs = np.random.RandomState(1)
+    image = rs.randint(0, 256, size=(70, 90, 3)).astype(np.uint8)
+    img_input = cv2.resize(image, (64, 48))
+    ref = torch.FloatTensor(np.transpose(img_input.copy(), (2, 0, 1))).unsqueeze(0) / 255 - 0.5
+    assert torch.equal(ref, O.preprocess_image(image, 48, 64))
