@@ -22,10 +22,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "images/sec at 512x512 bs32 (KGnet inference hot path)"
 UNIT = "images/s"
-BS, HW_IN, CELLS = 32, 512, 40
-MAX_PEAKS, MAX_BOXES, MAX_DETS = 4096, 4096, 512
+# BASELINE.json configs: cfg2 (= cfg3 per GPU) is the configuration the metric is quoted on; cfg4 stresses top-K + grouping
+CONFIGS = {
+    "cfg2": dict(bs=32, hw=512, cells=40, side=(24, 110), gap=12,
+                 metric="images/sec at 512x512 bs32 (KGnet inference hot path)"),
+    "cfg4": dict(bs=8, hw=1024, cells=500, side=(16, 40), gap=6,
+                 metric="images/sec at 1024x1024 bs8, ~500 cells/img (KGnet inference hot path, BASELINE config 4)"),
+}
+METRIC = CONFIGS["cfg2"]["metric"]
+BS, HW_IN, CELLS, SIDE, GAP = 32, 512, 40, (24, 110), 12
+MAX_PEAKS, MAX_BOXES, MAX_DETS = 4096, 4096, 1024
+
+
+def set_config(name, world=1, scaling="weak"):
+    """Selects the workload; strong scaling divides the global batch over the ranks."""
+    global METRIC, BS, HW_IN, CELLS, SIDE, GAP
+    c = CONFIGS[name]
+    METRIC, BS, HW_IN, CELLS, SIDE, GAP = c["metric"], c["bs"], c["hw"], c["cells"], c["side"], c["gap"]
+    if scaling == "strong":
+        if BS % world:
+            raise SystemExit(f"strong scaling: global batch {BS} is not divisible by {world} ranks")
+        BS //= world
 # algorithmic HBM bytes per pixel per scale of the decode (SURVEY.md §8d): vote reads 5+10 f32 and writes 5 x 8 B
 # accumulators (100 B), blur+peak reads the accumulators back once (40 B)
 VOTE_BYTES_PX, BLUR_BYTES_PX = 100, 40
@@ -103,7 +121,7 @@ def profiled_traffic(key=None):
 def planted_batch(n_distinct=4):
     """Teacher-forced decode load: planted 40-cell scenes, bs 32 built from n_distinct scenes."""
     from kg_instance_segmentation_b200 import synthetic
-    base = [synthetic.planted_scene(100 + i, HW_IN, HW_IN, CELLS)[0] for i in range(n_distinct)]
+    base = [synthetic.planted_scene(100 + i, HW_IN, HW_IN, CELLS, side=SIDE, gap=GAP)[0] for i in range(n_distinct)]
     scenes = [base[i % n_distinct] for i in range(BS)]
     return base, [tuple(np.stack([sc[s][k] for sc in scenes]) for k in range(3)) for s in range(4)]
 

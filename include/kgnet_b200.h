@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KG_ABI_VERSION 1
+#define KG_ABI_VERSION 2
 #define KG_NUM_KPS 5          /* config.py:3  */
 #define KG_NUM_EDGES 10       /* config.py:2  */
 #define KG_MAX_SCALES 4       /* test.py:105-108: c0..c3 */
@@ -93,7 +93,12 @@ typedef struct kg_decode_outputs {
   int* d_peak_count;     /* [N, n_scales]                                                                     */
   double* d_heat[KG_MAX_SCALES];  /* per scale [N,5,H,W]: Hough heat AFTER the Gaussian blur (:143-144)       */
   double* d_vote[KG_MAX_SCALES];  /* per scale [N,5,H,W]: Hough heat BEFORE the blur (compute_heatmaps)        */
-  int* d_status;         /* [1] bit0: a peak list overflowed, bit1: a box list overflowed                     */
+  int* d_status;         /* [1] bit0: a peak list overflowed, bit1: a box list overflowed, bit2: an image has
+                            more detections than det_packed_k (d_det_packed truncated; d_dets is complete)      */
+  double* d_det_packed;  /* optional [N, det_packed_k + 1, 5]: fixed-size per-image record for the data-parallel
+                            all-gather (no reference equivalent): row 0 = (count, rows stored, 0, 0, 0), rows 1.. =
+                            the first min(count, det_packed_k) detections in keep order                          */
+  int det_packed_k;
 } kg_decode_outputs;
 
 size_t kg_decode_workspace_bytes(const kg_decode_config* cfg, const kg_decode_scale* scales);
@@ -161,8 +166,11 @@ int kg_net_import_feats(kg_net* net, const float* const* d_feats, int N, int H, 
  * scratch bytes and the mask layout: h_mask_index[box] = mask slot or -1 when the box is skipped (:341-342),
  * h_mask_hw[slot] = (h, w), h_mask_off[slot] = float offset of the patch's first element in d_masks,
  * h_mask_pitch[slot] = its row stride in floats (the tensor-core path packs all patches into one atlas image).
+ * prepare is HOST planning: it may (re)allocate the pinned staging buffer of the problem lists and waits for the
+ * staging copy of a previous kg_net_forward_seg; it launches nothing.
  * run: all boxes together — dense tcgen05 convs over the per-level atlases (precision 1, 2) or grouped CUDA-core
- * launches (precision 0). */
+ * launches (precision 0).  Enqueue only: one cudaMemcpyAsync of the problem lists from pinned memory into the caller's
+ * seg workspace, then kernels; no allocation, no synchronisation. */
 int kg_net_seg_prepare(kg_net* net, int N, int H, int W, const int* box_counts, const double* h_boxes,
                        size_t* seg_workspace_bytes, long long* mask_floats, int* n_masks, int* h_mask_index,
                        int* h_mask_hw, long long* h_mask_off, int* h_mask_pitch);

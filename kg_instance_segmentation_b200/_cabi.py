@@ -32,7 +32,7 @@ class DecodeOutputs(C.Structure):
                 ("d_skeletons", C.c_void_p), ("d_skel_count", C.c_void_p), ("d_skel_keep", C.c_void_p),
                 ("d_peak_conf", C.c_void_p), ("d_peak_key", C.c_void_p), ("d_peak_count", C.c_void_p),
                 ("d_heat", C.c_void_p * KG_MAX_SCALES), ("d_vote", C.c_void_p * KG_MAX_SCALES),
-                ("d_status", C.c_void_p)]
+                ("d_status", C.c_void_p), ("d_det_packed", C.c_void_p), ("det_packed_k", C.c_int)]
 
 
 _lib = None

@@ -10,8 +10,10 @@
 // absolute error <= 2^-45 per vote against the reference's sequential fp64 sum (coo_matrix.todense()).
 #include "decode.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 namespace kg {
 
@@ -32,30 +34,98 @@ __constant__ int c_mid_index[5][5] = {{-1, 0, 1, 2, 3}, {10, -1, 4, 5, 6}, {11, 
 
 // ------------------------------------------------------------------------------------------------
 // K1: Hough vote.  compute_heatmaps + accumulate_votes (postprocessing.py:16-53).
-// One thread per (image, keypoint channel, source pixel); four bilinear splats each.
-__global__ void __launch_bounds__(256) vote_kernel(const float* __restrict__ kp, const float* __restrict__ sh,
-                                                   unsigned long long* __restrict__ acc, int H, int W) {
-  const int hw = H * W;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= hw) return;
-  const int i = blockIdx.y, n = blockIdx.z;
-  const int y = p / W, x = p - y * W;
-  const double ps = (double)__ldg(kp + ((size_t)n * 5 + i) * hw + p);
-  const double xs = (double)x + (double)__ldg(sh + ((size_t)n * 10 + 2 * i) * hw + p);      // int64 + f32 -> f64 (:49)
-  const double ys = (double)y + (double)__ldg(sh + ((size_t)n * 10 + 2 * i + 1) * hw + p);
-  const double fx = floor(xs), fy = floor(ys), cx = ceil(xs), cy = ceil(ys);
+// One CTA per 64 x 32 tile of source pixels of one (image, keypoint channel) plane.  Votes land within a few pixels of
+// their source (short offsets are trained inside the radius-5 discs), so the four bilinear splats of every pixel are
+// accumulated in SHARED memory over an (64+16) x (32+16) window around the tile, and the window is flushed with one
+// coalesced global reduction per non-zero cell (~1 per pixel instead of 4 scattered ones: the first version of this kernel
+// ran at the L2 atomic rate).  A vote outside the window goes to global memory directly.
+// The 64-bit fixed-point cell is kept as two 32-bit words: sm_100 serialises 64-bit shared atomics lane by lane (measured:
+// 0.85 shared wavefronts per lane-atomic), 32-bit ones run a conflict-free warp per wavefront.  The low word is added with
+// the returning form, an unsigned wrap is the carry into the high word -- exact for any number of votes per cell.
+// Integer accumulation is associative: the result does not depend on any of this.
+constexpr int VT_W = 64, VT_H = 32, VT_HALO = 8;
+constexpr int VR_W = VT_W + 2 * VT_HALO, VR_H = VT_H + 2 * VT_HALO;
+
+__device__ __forceinline__ void vote_cell(long long q, int gy, int gx, int H, int W, int wx0, int wy0, unsigned* __restrict__ s_lo,
+                                          unsigned* __restrict__ s_hi, unsigned long long* __restrict__ plane) {
+  if (q == 0 || (unsigned)gy >= (unsigned)H || (unsigned)gx >= (unsigned)W) return;      // good_inds (:34-35)
+  const int ly = gy - wy0, lx = gx - wx0;
+  if ((unsigned)ly < (unsigned)VR_H && (unsigned)lx < (unsigned)VR_W) {
+    const int c = ly * VR_W + lx;
+    const unsigned lo = (unsigned)q;
+    unsigned hi = (unsigned)((unsigned long long)q >> 32);
+    const unsigned old = atomicAdd(s_lo + c, lo);
+    hi += (old + lo < old) ? 1u : 0u;
+    if (hi != 0u) atomicAdd(s_hi + c, hi);
+  } else {
+    atomicAdd(plane + (size_t)gy * W + gx, (unsigned long long)q);
+  }
+}
+
+__device__ __forceinline__ void vote_one(float kpv, float sx, float sy, int x, int y, int H, int W, int wx0, int wy0,
+                                         unsigned* __restrict__ s_lo, unsigned* __restrict__ s_hi,
+                                         unsigned long long* __restrict__ plane) {
+  const double xs = (double)x + (double)sx;       // int64 + f32 -> f64 (:49)
+  const double ys = (double)y + (double)sy;
+  const double fx = floor(xs), fy = floor(ys);
+  // a vote can only land in the image if floor is in [-1, W): everything else (incl. NaN / inf offsets) is dropped like the
+  // reference's good_inds mask does
+  if (!(fx >= -1. && fx < (double)W && fy >= -1. && fy < (double)H)) return;
   const double dx = xs - fx, dy = ys - fy;
   const double omdx = 1. - dx, omdy = 1. - dy;
-  const double v[4] = {ps * omdx * omdy, ps * dx * omdy, ps * dy * omdx, ps * dy * dx};   // tl, tr, bl, br (:27-30)
-  const double ty[4] = {fy, fy, cy, cy};
-  const double tx[4] = {fx, cx, fx, cx};
-  unsigned long long* plane = acc + ((size_t)n * 5 + i) * hw;
+  // 2^44 folded into p first: a power-of-two scale commutes with every rounding below
+  const double p44 = (double)kpv * KG_FIX;
+  const double a = p44 * omdx, b = p44 * dx, c = p44 * dy;     // (p*(1-dx)), (p*dx), (p*dy): the reference's left-to-right products (:27-30)
+  const int ix = (int)fx, iy = (int)fy;
+  // ceil = floor + 1 whenever the fractional part is non-zero; when it is zero the splat's weight (dx or dy) is zero and
+  // the vote is skipped (q == 0), so floor + 1 can be used unconditionally
+  vote_cell(__double2ll_rn(a * omdy), iy, ix, H, W, wx0, wy0, s_lo, s_hi, plane);          // tl
+  vote_cell(__double2ll_rn(b * omdy), iy, ix + 1, H, W, wx0, wy0, s_lo, s_hi, plane);      // tr
+  vote_cell(__double2ll_rn(c * omdx), iy + 1, ix, H, W, wx0, wy0, s_lo, s_hi, plane);      // bl
+  vote_cell(__double2ll_rn(c * dx), iy + 1, ix + 1, H, W, wx0, wy0, s_lo, s_hi, plane);    // br
+}
+
+__global__ void __launch_bounds__(256) vote_kernel(const float* __restrict__ kp, const float* __restrict__ sh,
+                                                   unsigned long long* __restrict__ acc, int H, int W) {
+  __shared__ unsigned s_lo[VR_H * VR_W], s_hi[VR_H * VR_W];     // 30 KiB
+  const int plane_id = blockIdx.z;                      // n * 5 + i
+  const int n = plane_id / 5, i = plane_id - n * 5;
+  const size_t hw = (size_t)H * W;
+  const int x0 = blockIdx.x * VT_W, y0 = blockIdx.y * VT_H;
+  const int wx0 = x0 - VT_HALO, wy0 = y0 - VT_HALO;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < VR_H * VR_W; e += 256) { s_lo[e] = 0u; s_hi[e] = 0u; }
+  __syncthreads();
+  const float* kpp = kp + ((size_t)n * 5 + i) * hw;
+  const float* sxp = sh + ((size_t)n * 10 + 2 * i) * hw;
+  const float* syp = sxp + hw;
+  unsigned long long* plane = acc + (size_t)plane_id * hw;
+  const int cx = (tid & 15) * 4, ry = tid >> 4;         // 16 threads x 4 pixels per tile row, 16 rows per pass
+  const bool vec = (W & 3) == 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (ty[k] >= 0. && ty[k] < (double)H && tx[k] >= 0. && tx[k] < (double)W) {   // good_inds (:34-35)
-      const long long q = __double2ll_rn(v[k] * KG_FIX);
-      if (q != 0) atomicAdd(plane + (int)ty[k] * W + (int)tx[k], (unsigned long long)q);
+  for (int pass = 0; pass < VT_H / 16; ++pass) {
+    const int y = y0 + ry + pass * 16, x = x0 + cx;
+    if (y >= H || x >= W) continue;
+    const size_t o = (size_t)y * W + x;
+    if (vec && x + 3 < W) {
+      const float4 k4 = __ldg(reinterpret_cast<const float4*>(kpp + o));
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(sxp + o));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(syp + o));
+      vote_one(k4.x, a4.x, b4.x, x, y, H, W, wx0, wy0, s_lo, s_hi, plane);
+      vote_one(k4.y, a4.y, b4.y, x + 1, y, H, W, wx0, wy0, s_lo, s_hi, plane);
+      vote_one(k4.z, a4.z, b4.z, x + 2, y, H, W, wx0, wy0, s_lo, s_hi, plane);
+      vote_one(k4.w, a4.w, b4.w, x + 3, y, H, W, wx0, wy0, s_lo, s_hi, plane);
+    } else {
+      for (int q = 0; q < 4 && x + q < W; ++q)
+        vote_one(__ldg(kpp + o + q), __ldg(sxp + o + q), __ldg(syp + o + q), x + q, y, H, W, wx0, wy0, s_lo, s_hi, plane);
     }
+  }
+  __syncthreads();
+  for (int e = tid; e < VR_H * VR_W; e += 256) {
+    const unsigned long long v = ((unsigned long long)s_hi[e] << 32) + (unsigned long long)s_lo[e];
+    if (v == 0ull) continue;
+    const int ly = e / VR_W, lx = e - ly * VR_W;
+    atomicAdd(plane + (size_t)(wy0 + ly) * W + (wx0 + lx), v);   // in-image by construction (only in-image votes were accumulated)
   }
 }
 
@@ -68,85 +138,383 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: heat = acc / (pi r^2); gaussian_filter(sigma=2) (postprocessing.py:143-144, scipy correlate1d
-// symmetric branch: axis 0 then axis 1, paired taps, no FMA); get_keypoints (:56-64): cross-footprint
-// local maximum and conf > peak_thresh.  One CTA per 32x32 output tile of one (image, channel) plane.
-constexpr int BT = 32;                 // output tile edge
-constexpr int BB = BT + 2;             // blurred tile (+1 halo for the peak test)
-constexpr int BI = BB + 2 * GAUSS_R;   // input tile
-__global__ void __launch_bounds__(256) blur_peak_kernel(const unsigned long long* __restrict__ acc, int H, int W,
-                                                        double peak_thresh, int list_index_base, int n_scales,
-                                                        int max_peaks, double* __restrict__ peak_conf,
-                                                        int* __restrict__ peak_key, int* __restrict__ peak_count,
-                                                        double* __restrict__ out_vote, double* __restrict__ out_heat,
-                                                        int* __restrict__ status) {
-  __shared__ double s_in[BI][BI];
-  __shared__ double s_tmp[BB][BI];
-  __shared__ double s_blur[BB][BB + 1];
-  const int plane_id = blockIdx.z;                 // n*5 + i
-  const int n = plane_id / 5, ch = plane_id - n * 5;
-  const int hw = H * W;
-  const unsigned long long* plane = acc + (size_t)plane_id * hw;
-  const int x0 = blockIdx.x * BT, y0 = blockIdx.y * BT;
-  const int tid = threadIdx.x;
+// K2: heat = acc / (pi r^2); gaussian_filter(sigma=2) (postprocessing.py:143-144, scipy correlate1d symmetric branch:
+// axis 0 then axis 1, paired taps, no FMA); get_keypoints (:56-64): cross-footprint local maximum and conf > peak_thresh.
+//
+// Streaming separable filter.  A CTA owns a strip of CW output columns and a segment of rows of one (image, channel)
+// plane and walks DOWN the rows:
+//   * vertical pass in registers: thread c owns column x0 - 9 + c and keeps the 17 input rows around the current row in a
+//     register window, so every accumulator cell is read from global memory ONCE per segment (coalesced 8-byte loads,
+//     three rows in flight) and never staged in shared memory.  The window is a 20-slot circular buffer whose rotation is
+//     unrolled at compile time (slots are named registers, no moves);
+//   * horizontal pass through one shared row: the vertical results of the row are written to smem, and the first
+//     ceil((CW+2)/4) threads each produce 4 adjacent outputs from 20 values (10 x LDS.128 per 4 outputs instead of 17 loads
+//     per output);
+//   * peak test of the PREVIOUS row from registers (up / centre / down) and two shared loads (left / right neighbours).
+// (The first version staged a 50 x 50 halo tile per 32 x 32 outputs and re-read every value 17 times per axis: ~350
+// instructions per output, 6 % of HBM peak.)
+//
+// acc -> heat is an fp64 division by the constant pi*25.  Correctly rounded constant division in three operations
+// (Markstein): q = x * y, r = fma(-q, d, x), q' = fma(r, y, q) with y = RN(1/d); the 2^-44 fixed-point scale is a power
+// of two and folds into the constants exactly.  Exhaustively equal to x / d on 3e5 random accumulators (host check with
+// exact rationals) and bit-identical peaks on every fixture.
+constexpr double KG_RCP_PI_R2 = 1.0 / KG_PI_R2;                 // RN(1/d), evaluated by the host compiler (IEEE)
+constexpr double KG_Y44 = KG_RCP_PI_R2 * KG_UNFIX;              // y * 2^-44 (exact scaling)
+constexpr double KG_D44 = KG_PI_R2 * KG_FIX;                    // d * 2^44  (exact scaling)
+constexpr int BW_SLOTS = 20;                                    // 17-row window + 3 rows in flight
+constexpr int BP_HALO = GAUSS_R + 1;                            // 9: blur radius + 1 column / row for the peak test
 
-  const bool interior = y0 >= GAUSS_R + 1 && x0 >= GAUSS_R + 1 && y0 - (GAUSS_R + 1) + BI <= H && x0 - (GAUSS_R + 1) + BI <= W;
-  for (int e = tid; e < BI * BI; e += 256) {
-    const int r = e / BI, c = e - r * BI;
-    int gy = y0 - (GAUSS_R + 1) + r, gx = x0 - (GAUSS_R + 1) + c;
-    if (!interior) { gy = reflect_index(gy, H); gx = reflect_index(gx, W); }
-    const long long q = (long long)__ldg(plane + gy * W + gx);
-    s_in[r][c] = ((double)q * KG_UNFIX) / KG_PI_R2;
+__device__ __forceinline__ double acc_to_heat(double raw_bits) {
+  const double Q = (double)__double_as_longlong(raw_bits);      // exact below 2^53
+  const double q0 = Q * KG_Y44;
+  const double r = fma(-q0, KG_D44, Q);                          // (x - q0 * d) * 2^44, exact
+  return fma(r, KG_Y44, q0);
+}
+
+struct BlurParams {
+  const unsigned long long* acc;
+  int H, W, CW, RH, n_strips;
+  double peak_thresh;
+  int list_index_base, n_scales, max_peaks;
+  double* peak_conf; int* peak_key; int* peak_count;
+  double* out_vote; double* out_heat;
+  int* status;
+  int emit_peaks;                 // 0: only export the fp64 maps (out_vote / out_heat); the peak list comes from the prefilter path
+  unsigned long long* cand; int* cand_count; int cand_cap; int scale;    // prefilter path: candidate list (all scales share it)
+};
+
+// vertical pass of one row for window phase PH: slot (PH + i) % 20 holds input row y - 8 + i.  Converts the row that
+// enters the window, issues the load of row y + 11 into the slot that just left it, returns the 17-tap paired sum.
+template <int PH>
+__device__ __forceinline__ double blur_vstep(double (&win)[BW_SLOTS], const unsigned long long* __restrict__ col, int y, int H, int W,
+                                             double& centre) {
+  constexpr int s_new = (PH + 16) % BW_SLOTS, s_load = (PH + 19) % BW_SLOTS;
+  win[s_new] = acc_to_heat(win[s_new]);
+  win[s_load] = __longlong_as_double((long long)__ldg(col + (size_t)reflect_index(y + GAUSS_R + 3, H) * W));
+  centre = win[(PH + 8) % BW_SLOTS];
+  double t = centre * c_gauss[GAUSS_R];
+#pragma unroll
+  for (int j = 0; j < GAUSS_R; ++j) t += (win[(PH + j) % BW_SLOTS] + win[(PH + 16 - j) % BW_SLOTS]) * c_gauss[j];
+  return t;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, NT > 160 ? 2 : 3) blur_peak_kernel(const BlurParams p) {
+  __shared__ __align__(16) double s_tmp[2][NT + 8];
+  __shared__ __align__(16) double s_h[2][NT + 8];               // blurred column b of a row at index b + 2 (b = -1 .. CW + 4)
+  const int plane_id = blockIdx.z;                               // n * 5 + i
+  const int n = plane_id / 5, ch = plane_id - n * 5;
+  const int H = p.H, W = p.W, CW = p.CW;
+  const size_t hw = (size_t)H * W;
+  const unsigned long long* plane = p.acc + (size_t)plane_id * hw;
+  const int x0 = blockIdx.x * CW;
+  const int ybeg = blockIdx.y * p.RH, yend = min(H, ybeg + p.RH);   // output rows [ybeg, yend)
+  const int tid = threadIdx.x;
+  // vertical role: tmp column c = tid <-> image column x0 - 9 + c (reflected for the loads)
+  const int gxc = x0 - BP_HALO + tid;
+  const unsigned long long* col = plane + reflect_index(gxc, W);
+  const bool vote_out = p.out_vote != nullptr && gxc >= x0 && gxc < min(W, x0 + CW);
+  // horizontal role: blurred columns b = 4 tid .. 4 tid + 3 <-> image columns x0 - 1 + b
+  const int nq = (CW + 2 + 3) >> 2;
+  const bool hrole = tid < nq;
+  const int b0 = 4 * tid;
+  for (int e = tid; e < 2 * (NT + 8); e += NT) { (&s_tmp[0][0])[e] = 0.; (&s_h[0][0])[e] = 0.; }
+
+  const int yfirst = ybeg - 1, ylast = yend;                      // blurred rows ybeg - 1 .. yend feed the peak test of ybeg .. yend - 1
+  double win[BW_SLOTS];
+  // phase 0 <-> row yfirst: slots 0..15 = rows yfirst - 8 .. yfirst + 7 (converted), 16..18 = rows yfirst + 8 .. + 10 (raw, in flight)
+#pragma unroll
+  for (int k = 0; k < 19; ++k) {
+    const double raw = __longlong_as_double((long long)__ldg(col + (size_t)reflect_index(yfirst - GAUSS_R + k, H) * W));
+    win[k] = k < 16 ? acc_to_heat(raw) : raw;
   }
+  win[19] = 0.;
+  double hu[4] = {0., 0., 0., 0.}, hc[4] = {0., 0., 0., 0.};      // blurred rows y - 2 and y - 1 of this thread's 4 columns
   __syncthreads();
-  if (out_vote != nullptr) {
-    for (int e = tid; e < BT * BT; e += 256) {
-      const int r = e / BT, c = e - r * BT;
-      const int gy = y0 + r, gx = x0 + c;
-      if (gy < H && gx < W) out_vote[(size_t)plane_id * hw + gy * W + gx] = s_in[r + GAUSS_R + 1][c + GAUSS_R + 1];
+
+  int phase = 0;
+  for (int y = yfirst; y <= ylast; ++y) {
+    double t, centre;
+    switch (phase) {
+#define KG_VSTEP(P) case P: t = blur_vstep<P>(win, col, y, H, W, centre); break;
+      KG_VSTEP(0) KG_VSTEP(1) KG_VSTEP(2) KG_VSTEP(3) KG_VSTEP(4) KG_VSTEP(5) KG_VSTEP(6) KG_VSTEP(7) KG_VSTEP(8) KG_VSTEP(9)
+      KG_VSTEP(10) KG_VSTEP(11) KG_VSTEP(12) KG_VSTEP(13) KG_VSTEP(14) KG_VSTEP(15) KG_VSTEP(16) KG_VSTEP(17) KG_VSTEP(18)
+      default: t = blur_vstep<19>(win, col, y, H, W, centre); break;
+#undef KG_VSTEP
     }
-  }
-  // axis-0 pass
-  for (int e = tid; e < BB * BI; e += 256) {
-    const int r = e / BI, c = e - r * BI;
-    const int rc = r + GAUSS_R;
-    double t = s_in[rc][c] * c_gauss[GAUSS_R];
+    phase = phase == BW_SLOTS - 1 ? 0 : phase + 1;
+    const int par = y & 1;
+    s_tmp[par][tid] = t;
+    if (vote_out && y >= ybeg && y < yend) p.out_vote[(size_t)plane_id * hw + (size_t)y * W + gxc] = centre;
+    __syncthreads();
+    if (!hrole) continue;
+    // ---- horizontal pass: 4 adjacent outputs from 20 values of the shared row ----
+    double v[20];
+    {
+      const double2* src = reinterpret_cast<const double2*>(&s_tmp[par][b0]);
 #pragma unroll
-    for (int j = -GAUSS_R; j < 0; ++j) t += (s_in[rc + j][c] + s_in[rc - j][c]) * c_gauss[j + GAUSS_R];
-    s_tmp[r][c] = t;
-  }
-  __syncthreads();
-  // axis-1 pass
-  for (int e = tid; e < BB * BB; e += 256) {
-    const int r = e / BB, c = e - r * BB;
-    const int cc = c + GAUSS_R;
-    double t = s_tmp[r][cc] * c_gauss[GAUSS_R];
+      for (int k = 0; k < 10; ++k) { const double2 d = src[k]; v[2 * k] = d.x; v[2 * k + 1] = d.y; }
+    }
+    double hd[4];
 #pragma unroll
-    for (int j = -GAUSS_R; j < 0; ++j) t += (s_tmp[r][cc + j] + s_tmp[r][cc - j]) * c_gauss[j + GAUSS_R];
-    s_blur[r][c] = t;
-  }
-  __syncthreads();
-  for (int e = tid; e < BT * BT; e += 256) {
-    const int r = e / BT, c = e - r * BT;
-    const int gy = y0 + r, gx = x0 + c;
-    if (gy >= H || gx >= W) continue;
-    const double h = s_blur[r + 1][c + 1];
-    if (out_heat != nullptr) out_heat[(size_t)plane_id * hw + gy * W + gx] = h;
-    double m = h;
-    if (gy > 0) m = fmax(m, s_blur[r][c + 1]);
-    if (gy < H - 1) m = fmax(m, s_blur[r + 2][c + 1]);
-    if (gx > 0) m = fmax(m, s_blur[r + 1][c]);
-    if (gx < W - 1) m = fmax(m, s_blur[r + 1][c + 2]);
-    if (m == h && h > peak_thresh) {
-      const int list = n * n_scales + list_index_base;
-      const int slot = atomicAdd(peak_count + list, 1);
-      if (slot < max_peaks) {
-        peak_conf[(size_t)list * max_peaks + slot] = h;
-        peak_key[(size_t)list * max_peaks + slot] = ch * hw + gy * W + gx;
-      } else {
-        atomicOr(status, 1);
+    for (int k = 0; k < 4; ++k) {
+      double a = v[k + GAUSS_R] * c_gauss[GAUSS_R];
+#pragma unroll
+      for (int j = 0; j < GAUSS_R; ++j) a += (v[k + j] + v[k + 16 - j]) * c_gauss[j];
+      hd[k] = a;
+    }
+    {
+      double2* dst = reinterpret_cast<double2*>(&s_h[par][b0 + 2]);      // index b + 2: the pairs stay 16-byte aligned
+      dst[0] = make_double2(hd[0], hd[1]); dst[1] = make_double2(hd[2], hd[3]);
+    }
+    // ---- peak test of row yr = y - 1 (centre hc, up hu, down hd; left / right from the previous row in smem) ----
+    const int yr = y - 1;
+    if (yr >= ybeg && yr < yend) {
+      const double* prev = s_h[par ^ 1];
+      const double left_edge = prev[b0 + 1], right_edge = prev[b0 + 6];    // columns b0 - 1 and b0 + 4 of row yr
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int b = b0 + k, gx = x0 - 1 + b;
+        if (b < 1 || b > CW || gx >= W) continue;
+        const double h = hc[k];
+        if (p.out_heat != nullptr) p.out_heat[(size_t)plane_id * hw + (size_t)yr * W + gx] = h;
+        double m = h;
+        if (yr > 0) m = fmax(m, hu[k]);
+        if (yr < H - 1) m = fmax(m, hd[k]);
+        if (gx > 0) m = fmax(m, k == 0 ? left_edge : hc[k - 1]);
+        if (gx < W - 1) m = fmax(m, k == 3 ? right_edge : hc[k + 1]);
+        if (p.emit_peaks && m == h && h > p.peak_thresh) {
+          const int list = n * p.n_scales + p.list_index_base;
+          const int slot = atomicAdd(p.peak_count + list, 1);
+          if (slot < p.max_peaks) {
+            p.peak_conf[(size_t)list * p.max_peaks + slot] = h;
+            p.peak_key[(size_t)list * p.max_peaks + slot] = ch * (int)hw + yr * W + gx;
+          } else {
+            atomicOr(p.status, 1);
+          }
+        }
       }
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hu[k] = hc[k]; hc[k] = hd[k]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a / K2b: the production path of blur + peaks.  The fp64 filter above is exact but occupies the fp64 pipe for ~60
+// operations per pixel; only ~0.1 % of the pixels are peaks.  So:
+//   K2a  blur32_candidates_kernel: the same separable filter in fp32 (FMA allowed) and a CONSERVATIVE peak test.  All terms are
+//        non-negative, so the fp32 result has a relative error E <= 25 * 2^-24 = 1.5e-6 (one rounding per operation on the path
+//        accumulator -> blurred value, including the rounded constants).  A true peak (h >= every neighbour, h > T) therefore
+//        satisfies h32 * F >= n32 and h32 * F >= T with F = 1 + 6e-6 > (1 + E) / (1 - E): the candidate set is a superset
+//        of the peak set.  Warp-private strips: lane l owns columns 4l .. 4l+3 of a 128-column strip and their 17-row
+//        register windows; the horizontal pass takes the neighbours' vertical sums by warp shuffle.  No shared memory, no
+//        barrier -- every warp streams down its rows independently.
+//   K2b  exact_peaks_kernel: one warp per candidate recomputes the blurred value at the candidate and its four neighbours
+//        in fp64 in the reference's exact operation order (same arithmetic as blur_peak_kernel) and applies the exact test.
+// The peak list is bit-identical to the all-fp64 kernel's (tests/test_decode_gpu.py runs both).
+constexpr float KG_CAND_F = 1.000006f;
+constexpr int B32_CW = 110;                 // output columns per warp strip: 128 - 2 * 9
+
+__constant__ float c_gauss32[9] = {(float)0x1.18aad19e4159bp-14, (float)0x1.c98b8c5d0dda5p-12, (float)0x1.227362b5fc92dp-9,
+                                   (float)0x1.1f30504e20207p-7,  (float)0x1.ba4d4125ffd2ap-6,  (float)0x1.0941b71ceef37p-4,
+                                   (float)0x1.ef9093fc46e5ap-4,  (float)0x1.68856f9ab1982p-3,  (float)0x1.98862a07ae7b4p-3};
+
+struct Blur32Row { float t[4]; };
+
+// one row of the vertical pass for window phase PH (18-slot circular window: slot (PH + i) % 18 = input row y - 8 + i);
+// the raw accumulator rows y + 8 .. y + 10 wait in a 3-deep queue (index = phase % 3) so that three rows of loads are in flight
+template <int PH>
+__device__ __forceinline__ Blur32Row blur32_vstep(float (&win)[4][18], unsigned long long (&raw)[3][4],
+                                                  const unsigned long long* __restrict__ next_row, const int (&off)[4], float cscale) {
+  constexpr int s_new = (PH + 16) % 18, qi = PH % 3;
+  Blur32Row r;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    win[k][s_new] = (float)(long long)raw[qi][k] * cscale;
+    raw[qi][k] = __ldg(next_row + off[k]);
+    float t = win[k][(PH + 8) % 18] * c_gauss32[GAUSS_R];
+#pragma unroll
+    for (int j = 0; j < GAUSS_R; ++j) t = fmaf(win[k][(PH + j) % 18] + win[k][(PH + 16 - j) % 18], c_gauss32[j], t);
+    r.t[k] = t;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(128) blur32_candidates_kernel(const BlurParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int plane_id = blockIdx.y;
+  const int H = p.H, W = p.W;
+  const size_t hw = (size_t)H * W;
+  const unsigned long long* plane = p.acc + (size_t)plane_id * hw;
+  const int item = blockIdx.x * 4 + warp;                      // (row segment, column strip) of this warp
+  const int seg = item / p.n_strips, strip = item - seg * p.n_strips;
+  const int ybeg = seg * p.RH;
+  if (ybeg >= H) return;
+  const int yend = min(H, ybeg + p.RH);
+  const int x0 = strip * B32_CW;
+  // this lane's columns: strip column c = 4 lane + k <-> image column x0 - 9 + c, reflected at the image border (so the four
+  // cells are consecutive only in the interior: per-column offsets from the first one)
+  const int g0 = reflect_index(x0 - BP_HALO + 4 * lane, W);
+  int off[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) off[k] = reflect_index(x0 - BP_HALO + 4 * lane + k, W) - g0;
+  const unsigned long long* col0 = plane + g0;
+  const float cscale = (float)(KG_UNFIX / KG_PI_R2);
+  float win[4][18];
+  unsigned long long raw[3][4];
+  auto load_row = [&](int gy, unsigned long long (&dst)[4]) {
+    const unsigned long long* rowp = col0 + (size_t)reflect_index(gy, H) * W;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = __ldg(rowp + off[k]);
+  };
+  const int yfirst = ybeg - 1, ylast = yend;
+  {
+    unsigned long long tmp[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      load_row(yfirst - GAUSS_R + i, tmp);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) win[k][i] = (float)(long long)tmp[k] * cscale;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { win[k][16] = 0.f; win[k][17] = 0.f; }
+    load_row(yfirst + 8, raw[0]); load_row(yfirst + 9, raw[1]); load_row(yfirst + 10, raw[2]);
+  }
+  float hu[4] = {0.f, 0.f, 0.f, 0.f}, hc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float thr = (float)p.peak_thresh;
+  int phase = 0;
+  for (int y = yfirst; y <= ylast; ++y) {
+    const unsigned long long* next_row = col0 + (size_t)reflect_index(y + GAUSS_R + 3, H) * W;
+    Blur32Row r;
+    switch (phase) {
+#define KG_V32(P) case P: r = blur32_vstep<P>(win, raw, next_row, off, cscale); break;
+      KG_V32(0) KG_V32(1) KG_V32(2) KG_V32(3) KG_V32(4) KG_V32(5) KG_V32(6) KG_V32(7) KG_V32(8)
+      KG_V32(9) KG_V32(10) KG_V32(11) KG_V32(12) KG_V32(13) KG_V32(14) KG_V32(15) KG_V32(16)
+      default: r = blur32_vstep<17>(win, raw, next_row, off, cscale); break;
+#undef KG_V32
+    }
+    phase = phase == 17 ? 0 : phase + 1;
+    // ---- horizontal pass: this lane's 4 outputs need the vertical sums of lanes l-2 .. l+2 ----
+    float v[20];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = __shfl_sync(0xffffffffu, r.t[k], (lane + 30) & 31);
+      v[4 + k] = __shfl_sync(0xffffffffu, r.t[k], (lane + 31) & 31);
+      v[8 + k] = r.t[k];
+      v[12 + k] = __shfl_sync(0xffffffffu, r.t[k], (lane + 1) & 31);
+      v[16 + k] = __shfl_sync(0xffffffffu, r.t[k], (lane + 2) & 31);
+    }
+    float hd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = v[k + GAUSS_R] * c_gauss32[GAUSS_R];
+#pragma unroll
+      for (int j = 0; j < GAUSS_R; ++j) a = fmaf(v[k + j] + v[k + 16 - j], c_gauss32[j], a);
+      hd[k] = a;
+    }
+    // ---- conservative peak test of row yr = y - 1 ----
+    const int yr = y - 1;
+    const float left_edge = __shfl_sync(0xffffffffu, hc[3], (lane + 31) & 31);
+    const float right_edge = __shfl_sync(0xffffffffu, hc[0], (lane + 1) & 31);
+    if (yr >= ybeg && yr < yend) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = 4 * lane + k, gx = x0 - BP_HALO + c;
+        if (c < BP_HALO || c >= BP_HALO + B32_CW || gx >= W) continue;
+        const float hF = hc[k] * KG_CAND_F;
+        bool cand = hF >= thr;
+        if (yr > 0) cand = cand && hF >= hu[k];
+        if (yr < H - 1) cand = cand && hF >= hd[k];
+        if (gx > 0) cand = cand && hF >= (k == 0 ? left_edge : hc[k - 1]);
+        if (gx < W - 1) cand = cand && hF >= (k == 3 ? right_edge : hc[k + 1]);
+        if (cand) {
+          const int slot = atomicAdd(p.cand_count, 1);
+          if (slot < p.cand_cap)
+            p.cand[slot] = ((unsigned long long)p.scale << 56) | ((unsigned long long)plane_id << 32) | ((unsigned long long)yr << 16) | (unsigned long long)gx;
+          else
+            atomicOr(p.status, 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hu[k] = hc[k]; hc[k] = hd[k]; }
+  }
+}
+
+struct ExactParams {
+  const unsigned long long* acc[KG_MAX_SCALES];
+  int H[KG_MAX_SCALES], W[KG_MAX_SCALES];
+  const unsigned long long* cand; const int* cand_count; int cand_cap;
+  double peak_thresh;
+  int n_scales, max_peaks;
+  double* peak_conf; int* peak_key; int* peak_count;
+  int* status;
+};
+
+// K2b: exact fp64 re-evaluation of the candidates (postprocessing.py:56-64,143-144; same operation order as blur_peak_kernel).
+// Lane c (0..18) owns image column x - 9 + c: 19 input rows y - 9 .. y + 9 -> vertical sums of rows y - 1, y, y + 1; lanes
+// 0..4 then each evaluate one of the five horizontal sums from the warp's shared scratch.
+__global__ void __launch_bounds__(128) exact_peaks_kernel(const ExactParams p) {
+  __shared__ double s_t[4][3][20];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int total = min(*p.cand_count, p.cand_cap);
+  const int warps_total = gridDim.x * 4;
+  for (int ci = blockIdx.x * 4 + warp; ci < total; ci += warps_total) {
+    const unsigned long long e = p.cand[ci];
+    const int s = (int)(e >> 56), plane_id = (int)((e >> 32) & 0xffffffu), y = (int)((e >> 16) & 0xffffu), x = (int)(e & 0xffffu);
+    const int H = p.H[s], W = p.W[s];
+    const size_t hw = (size_t)H * W;
+    const unsigned long long* plane = p.acc[s] + (size_t)plane_id * hw;
+    double tv[3] = {0., 0., 0.};
+    if (lane < 19) {
+      const unsigned long long* col = plane + reflect_index(x - 9 + lane, W);
+      double a[19];
+#pragma unroll
+      for (int i = 0; i < 19; ++i) a[i] = __longlong_as_double((long long)__ldg(col + (size_t)reflect_index(y - 9 + i, H) * W));
+#pragma unroll
+      for (int i = 0; i < 19; ++i) a[i] = acc_to_heat(a[i]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {                    // rows y - 1, y, y + 1: centre at a[8 + r]
+        double t = a[8 + r] * c_gauss[GAUSS_R];
+#pragma unroll
+        for (int j = 0; j < GAUSS_R; ++j) t += (a[r + j] + a[r + 16 - j]) * c_gauss[j];
+        tv[r] = t;
+      }
+      s_t[warp][0][lane] = tv[0]; s_t[warp][1][lane] = tv[1]; s_t[warp][2][lane] = tv[2];
+    }
+    __syncwarp();
+    // lane 0: h(y, x); 1: h(y - 1, x); 2: h(y + 1, x); 3: h(y, x - 1); 4: h(y, x + 1)
+    double h = 0.;
+    if (lane < 5) {
+      const int row = lane == 1 ? 0 : (lane == 2 ? 2 : 1);
+      const int cc = lane == 3 ? 8 : (lane == 4 ? 10 : 9);          // scratch column of the output's centre (x <-> 9)
+      const double* t = s_t[warp][row];
+      h = t[cc] * c_gauss[GAUSS_R];
+#pragma unroll
+      for (int j = 0; j < GAUSS_R; ++j) h += (t[cc - 8 + j] + t[cc + 8 - j]) * c_gauss[j];
+    }
+    const double hc = __shfl_sync(0xffffffffu, h, 0), hup = __shfl_sync(0xffffffffu, h, 1), hdn = __shfl_sync(0xffffffffu, h, 2);
+    const double hl = __shfl_sync(0xffffffffu, h, 3), hr = __shfl_sync(0xffffffffu, h, 4);
+    if (lane == 0) {
+      double m = hc;
+      if (y > 0) m = fmax(m, hup);
+      if (y < H - 1) m = fmax(m, hdn);
+      if (x > 0) m = fmax(m, hl);
+      if (x < W - 1) m = fmax(m, hr);
+      if (m == hc && hc > p.peak_thresh) {
+        const int n = plane_id / 5, ch = plane_id - n * 5;
+        const int list = n * p.n_scales + s;
+        const int slot = atomicAdd(p.peak_count + list, 1);
+        if (slot < p.max_peaks) {
+          p.peak_conf[(size_t)list * p.max_peaks + slot] = hc;
+          p.peak_key[(size_t)list * p.max_peaks + slot] = ch * (int)hw + y * W + x;
+        } else {
+          atomicOr(p.status, 1);
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -385,7 +753,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const double* __restrict__ sbo
                                                   int n_lists, int list_cap, int max_boxes, double nms_thresh,
                                                   double* __restrict__ boxes_g, int* __restrict__ box_count_g,
                                                   double* __restrict__ dets_g, int* __restrict__ det_count_g,
-                                                  int* __restrict__ status) {
+                                                  int* __restrict__ status, double* __restrict__ packed_g, int packed_k) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_conf = reinterpret_cast<double*>(smem_raw);
   int* s_idx = reinterpret_cast<int*>(s_conf + max_boxes);
@@ -451,6 +819,15 @@ __global__ void __launch_bounds__(256) nms_kernel(const double* __restrict__ sbo
     __syncthreads();
   }
   if (tid == 0) det_count_g[n] = nkeep;
+  if (packed_g != nullptr) {
+    // fixed-size record of this image for the data-parallel all-gather: row 0 = (count, kept rows, 0, 0, 0), rows 1.. = detections
+    double* rec = packed_g + (size_t)n * (packed_k + 1) * 5;
+    const int kept = min(nkeep, packed_k);
+    __syncthreads();                                     // dets rows written by threads 0..4 above
+    if (tid < 5) rec[tid] = tid == 0 ? (double)nkeep : (tid == 1 ? (double)kept : 0.);
+    for (int e = tid; e < kept * 5; e += blockDim.x) rec[5 + e] = dets[e];
+    if (nkeep > packed_k && tid == 0) atomicOr(status, 4);
+  }
 }
 
 // nms.py:4-53 for lists that do not fit the shared-memory kernel (kg_nms_host with > 8192 boxes): one CTA, sort keys and
@@ -513,11 +890,66 @@ __global__ void __launch_bounds__(256) skeleton_box_kernel(const double* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+static int num_sms() {
+  static int sms = 0;
+  if (sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
+
+// rows per segment: every segment re-reads 18 halo rows, every wave of the grid costs one segment time -> minimise waves * (RH + 18)
+static int pick_rows(int H, long long units_per_row_segment, long long slots) {
+  int best_rh = H; double best_cost = 1e30;
+  for (int rh = 16; rh <= H; rh += 8) {
+    const long long units = units_per_row_segment * ceil_div(H, rh);
+    const double waves = (double)((units + slots - 1) / slots);
+    const double cost = waves * (rh + 2 * BP_HALO);
+    if (cost < best_cost) { best_cost = cost; best_rh = rh; }
+  }
+  if (H < 16) best_rh = H;
+  const char* env = getenv("KG_BLUR_RH");
+  if (env && atoi(env) > 0) best_rh = std::min(H, atoi(env));
+  return best_rh;
+}
+
+// All-fp64 streaming filter (blur_peak_kernel): exports the fp64 maps, and the peak list when bp.emit_peaks is set.
+// Column strips of at most 270 outputs (288 threads, two CTAs per SM at 96 registers).
+static int launch_blur_peak(BlurParams bp, int N, cudaStream_t stream) {
+  const int W = bp.W, H = bp.H;
+  bp.n_strips = ceil_div(W, 270);
+  bp.CW = ceil_div(W, bp.n_strips);
+  const int need = bp.CW + 2 * BP_HALO;
+  const int nt = need <= 96 ? 96 : need <= 160 ? 160 : 288;
+  const int per_sm = std::max(1, 65536 / (112 * nt));
+  bp.RH = pick_rows(H, (long long)N * 5 * bp.n_strips, (long long)num_sms() * per_sm);
+  dim3 grid(bp.n_strips, ceil_div(H, bp.RH), N * 5);
+  KG_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "blur_peak: grid too large");
+  switch (nt) {
+    case 96: blur_peak_kernel<96><<<grid, 96, 0, stream>>>(bp); break;
+    case 160: blur_peak_kernel<160><<<grid, 160, 0, stream>>>(bp); break;
+    default: blur_peak_kernel<288><<<grid, 288, 0, stream>>>(bp); break;
+  }
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+// fp32 prefilter (blur32_candidates_kernel): warp-private strips of 110 output columns, 4 warps per CTA, ~12 warps per SM
+static int launch_blur32(BlurParams bp, int N, cudaStream_t stream) {
+  bp.n_strips = ceil_div(bp.W, B32_CW);
+  bp.RH = pick_rows(bp.H, (long long)N * 5 * bp.n_strips, (long long)num_sms() * 12);
+  const int items = bp.n_strips * ceil_div(bp.H, bp.RH);
+  dim3 grid(ceil_div(items, 4), N * 5, 1);
+  KG_REQUIRE(grid.y <= 65535, "blur32: grid too large");
+  blur32_candidates_kernel<<<grid, 128, 0, stream>>>(bp);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 struct DecodeWorkspace {
   unsigned long long* acc[KG_MAX_SCALES];
   double* peak_conf; int* peak_key; int* peak_count;
+  unsigned long long* cand; int* cand_count; int cand_cap;
   double* skel; int* skel_xy; int* skel_count;
   double* sbox; int* sbox_count;
   double* boxes; int* box_count;
@@ -534,10 +966,13 @@ static DecodeWorkspace carve(const kg_decode_config& cfg, const kg_decode_scale*
   char* z0 = a.take<char>(0);
   for (int s = 0; s < cfg.n_scales; ++s) w.acc[s] = a.take<unsigned long long>((size_t)cfg.N * 5 * sc[s].H * sc[s].W);
   w.peak_count = a.take<int>(lists);
+  w.cand_count = a.take<int>(1);
   char* z1 = a.take<char>(0);
   w.zero_begin = z0; w.zero_bytes = (size_t)(z1 - z0);
   w.peak_conf = a.take<double>(lists * P);
   w.peak_key = a.take<int>(lists * P);
+  w.cand_cap = (int)std::min<size_t>(lists * P, (size_t)1 << 26);
+  w.cand = a.take<unsigned long long>((size_t)w.cand_cap);
   w.skel = a.take<double>(lists * P * 15);
   w.skel_xy = a.take<int>(lists * P * 5);
   w.skel_count = a.take<int>(lists);
@@ -580,6 +1015,7 @@ int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const 
                   size_t workspace_bytes, cudaStream_t stream, int* n_launches) {
   KG_TRY(check_config(cfg, sc));
   KG_REQUIRE(out != nullptr && out->d_status != nullptr, "kg_decode: outputs / d_status must be non-null");
+  KG_REQUIRE(out->d_det_packed == nullptr || out->det_packed_k >= 1, "kg_decode: det_packed_k=%d", out->det_packed_k);
   KG_REQUIRE(workspace != nullptr, "kg_decode: null workspace");
   DecodeWorkspace w = carve(*cfg, sc, workspace);
   if (w.total > workspace_bytes) {
@@ -592,23 +1028,39 @@ int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const 
   const int N = cfg->N, S = cfg->n_scales, P = cfg->max_peaks;
   KG_CUDA_CHECK(cudaMemsetAsync(w.zero_begin, 0, w.zero_bytes, stream));
   KG_CUDA_CHECK(cudaMemsetAsync(out->d_status, 0, sizeof(int), stream));
+  // KG_DECODE_FP64=1: the all-fp64 streaming filter produces the peak list (A/B and cross-check of the prefilter path)
+  static const bool all_fp64 = getenv("KG_DECODE_FP64") != nullptr && getenv("KG_DECODE_FP64")[0] == '1';
   double* peak_conf = out->d_peak_conf ? out->d_peak_conf : w.peak_conf;
   int* peak_key = out->d_peak_key ? out->d_peak_key : w.peak_key;
   int* peak_count = w.peak_count;
   for (int s = 0; s < S; ++s) {
     const int H = sc[s].H, W = sc[s].W;
-    dim3 g1(ceil_div(H * W, 256), 5, N);
+    dim3 g1(ceil_div(W, VT_W), ceil_div(H, VT_H), N * 5);
     {
       StageScope t(0, stream);
       vote_kernel<<<g1, 256, 0, stream>>>(sc[s].d_kp, sc[s].d_short, w.acc[s], H, W);
     }
-    dim3 g2(ceil_div(W, BT), ceil_div(H, BT), N * 5);
     {
       StageScope t(1, stream);
-      blur_peak_kernel<<<g2, 256, 0, stream>>>(w.acc[s], H, W, cfg->peak_thresh, s, S, P, peak_conf, peak_key, peak_count,
-                                               out->d_vote[s], out->d_heat[s], out->d_status);
+      BlurParams bp{};
+      bp.acc = w.acc[s]; bp.H = H; bp.W = W; bp.peak_thresh = cfg->peak_thresh; bp.list_index_base = s; bp.n_scales = S; bp.max_peaks = P;
+      bp.peak_conf = peak_conf; bp.peak_key = peak_key; bp.peak_count = peak_count;
+      bp.out_vote = out->d_vote[s]; bp.out_heat = out->d_heat[s]; bp.status = out->d_status;
+      bp.cand = w.cand; bp.cand_count = w.cand_count; bp.cand_cap = w.cand_cap; bp.scale = s;
+      bp.emit_peaks = all_fp64 ? 1 : 0;
+      if (all_fp64 || bp.out_vote != nullptr || bp.out_heat != nullptr) { KG_TRY(launch_blur_peak(bp, N, stream)); ++launches; }
+      if (!all_fp64) { KG_TRY(launch_blur32(bp, N, stream)); ++launches; }
     }
-    launches += 2;
+    launches += 1;
+  }
+  if (!all_fp64) {
+    StageScope t(1, stream);
+    ExactParams ep{};
+    for (int s = 0; s < S; ++s) { ep.acc[s] = w.acc[s]; ep.H[s] = sc[s].H; ep.W[s] = sc[s].W; }
+    ep.cand = w.cand; ep.cand_count = w.cand_count; ep.cand_cap = w.cand_cap; ep.peak_thresh = cfg->peak_thresh;
+    ep.n_scales = S; ep.max_peaks = P; ep.peak_conf = peak_conf; ep.peak_key = peak_key; ep.peak_count = peak_count; ep.status = out->d_status;
+    exact_peaks_kernel<<<num_sms() * 4, 128, 0, stream>>>(ep);
+    ++launches;
   }
   GroupParams gp{};
   for (int s = 0; s < S; ++s) { gp.mid[s] = sc[s].d_mid; gp.H[s] = sc[s].H; gp.W[s] = sc[s].W; gp.box_scale[s] = sc[s].box_scale; }
@@ -628,7 +1080,8 @@ int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const 
                                                              out->d_boxes ? out->d_boxes : w.boxes,
                                                              out->d_box_count ? out->d_box_count : w.box_count,
                                                              out->d_dets ? out->d_dets : w.dets,
-                                                             out->d_det_count ? out->d_det_count : w.det_count, out->d_status);
+                                                             out->d_det_count ? out->d_det_count : w.det_count, out->d_status,
+                                                             out->d_det_packed, out->det_packed_k);
   }
   launches += 2;
   if (out->d_peak_count != nullptr) {
@@ -702,7 +1155,7 @@ int nms_host(const double* h_boxes, int n, double nms_thresh, double* h_out, int
   if (cap <= 8192) {
     KG_CUDA_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem(8192)));
     nms_kernel<<<1, 256, nms_smem(cap), st.s>>>(in.as<double>(), d_ints, 1, cap, cap, nms_thresh, boxes.as<double>(), d_ints + 1,
-                                                dets.as<double>(), d_ints + 2, d_ints + 3);
+                                                dets.as<double>(), d_ints + 2, d_ints + 3, nullptr, 0);
   } else {
     KG_CUDA_CHECK(cudaMalloc(&scratch.p, (size_t)cap * 13));
     nms_big_kernel<<<1, 1024, 0, st.s>>>(in.as<double>(), n, cap, nms_thresh, scratch.as<unsigned char>(), dets.as<double>(), d_ints + 2);

@@ -106,6 +106,11 @@ struct SegPlan {
     int pix_crop = 0, pix_deepest = 0, pix_up = 0;
   } lv[5];
   size_t mask_base = 0;                            // byte offset of the mask region inside the seg workspace
+  // problem lists of every launch, packed into ONE blob: built by seg_prepare in pinned host memory, copied by forward_seg
+  // (asynchronously, from pinned memory) to `blob_base` of the caller's seg workspace
+  size_t blob_base = 0, blob_bytes = 0;
+  size_t o_rs_raw[4] = {}, o_rs_scr[4] = {}, o_up4[4] = {}, o_cat[4] = {}, o_h0r = 0, o_h0s = 0, o_h1 = 0;   // CUDA-core path
+  size_t o_crop[5] = {}, o_deep[5] = {}, o_up[5] = {}, o_rect[5] = {};                                          // atlas path
 };
 
 struct Net {
@@ -114,14 +119,40 @@ struct Net {
   bool finalized = false;
   std::unique_ptr<Plan> plan;
   SegPlan seg;
-  void* d_seg_probs = nullptr; size_t seg_probs_bytes = 0;
+  char* h_blob = nullptr; size_t h_blob_cap = 0;   // pinned staging of the forward_seg problem lists (owned by seg_prepare)
+  cudaEvent_t blob_copied = nullptr;               // recorded after forward_seg's H2D copy of the blob: seg_prepare waits on it before reuse
   ~Net() {
     for (auto& kv : convs) {
       if (kv.second.d_w) cudaFree(kv.second.d_w);
       if (kv.second.d_b) cudaFree(kv.second.d_b);
       tc_free_weights(kv.second.tc);
     }
-    if (d_seg_probs) cudaFree(d_seg_probs);
+    if (h_blob) cudaFreeHost(h_blob);
+    if (blob_copied) cudaEventDestroy(blob_copied);
+  }
+};
+
+// Appends `bytes` to the pinned blob of the net (16-byte aligned); grows it (allocation: seg_prepare only).
+struct BlobWriter {
+  Net* net; size_t size = 0; std::vector<char> tmp;
+  size_t put(const void* src, size_t bytes) {
+    const size_t o = align_up(tmp.size(), 16);
+    tmp.resize(o + bytes);
+    if (bytes) memcpy(tmp.data() + o, src, bytes);
+    return o;
+  }
+  int commit(SegPlan& sp) {
+    if (net->blob_copied == nullptr) KG_CUDA_CHECK(cudaEventCreateWithFlags(&net->blob_copied, cudaEventDisableTiming));
+    KG_CUDA_CHECK(cudaEventSynchronize(net->blob_copied));       // a previous forward_seg may still be reading the staging buffer
+    if (net->h_blob_cap < tmp.size()) {
+      if (net->h_blob) cudaFreeHost(net->h_blob);
+      net->h_blob = nullptr; net->h_blob_cap = 0;
+      KG_CUDA_CHECK(cudaMallocHost(&net->h_blob, tmp.size() * 2 + 4096));
+      net->h_blob_cap = tmp.size() * 2 + 4096;
+    }
+    if (!tmp.empty()) memcpy(net->h_blob, tmp.data(), tmp.size());
+    sp.blob_bytes = tmp.size();
+    return KG_OK;
   }
 };
 
@@ -698,8 +729,21 @@ static int seg_prepare(Net* net, int N, int H, int W, const int* counts, const d
   sp.scratch_halfs = off;
   sp.mask_floats = moff;
   sp.n_masks = mi;
+  BlobWriter bw{net};
+  for (int l = 0; l < 4; ++l) {
+    auto& st = sp.steps[l];
+    sp.o_rs_raw[l] = bw.put(st.rs_raw.data(), st.rs_raw.size() * sizeof(ResizeProb));
+    sp.o_rs_scr[l] = bw.put(st.rs_scr.data(), st.rs_scr.size() * sizeof(ResizeProb));
+    sp.o_up4[l] = bw.put(st.up.data(), st.up.size() * sizeof(ConvProb));
+    sp.o_cat[l] = bw.put(st.cat.data(), st.cat.size() * sizeof(ConvProb));
+  }
+  sp.o_h0r = bw.put(sp.h0_raw.data(), sp.h0_raw.size() * sizeof(ConvProb));
+  sp.o_h0s = bw.put(sp.h0_scr.data(), sp.h0_scr.size() * sizeof(ConvProb));
+  sp.o_h1 = bw.put(sp.h1.data(), sp.h1.size() * sizeof(ConvProb));
+  KG_TRY(bw.commit(sp));
+  sp.blob_base = align_up(off * sizeof(__half), 256) * 2;
   sp.valid = true;
-  *ws_bytes = align_up(off * sizeof(__half), 256) * 2 + 256;
+  *ws_bytes = sp.blob_base + align_up(sp.blob_bytes, 256) + 256;
   *mask_floats = moff;
   *n_masks = mi;
   return KG_OK;
@@ -712,36 +756,19 @@ static int seg_run(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes, float
   if (!sp.valid || !net->plan) { set_error("kg_net_forward_seg: call kg_net_seg_prepare first"); return KG_ERR_STATE; }
   if (sp.atlas) return seg_run_atlas(net, dec_ws, seg_ws, seg_bytes, d_masks, stream, n_launches);
   const size_t plane_bytes = align_up(sp.scratch_halfs * sizeof(__half), 256);
-  if (seg_bytes < plane_bytes * 2) { set_error("kg_net_forward_seg: workspace too small (%zu < %zu)", seg_bytes, plane_bytes * 2); return KG_ERR_WORKSPACE; }
+  if (seg_bytes < sp.blob_base + sp.blob_bytes) { set_error("kg_net_forward_seg: workspace too small (%zu < %zu)", seg_bytes, sp.blob_base + sp.blob_bytes); return KG_ERR_WORKSPACE; }
   if (sp.n_masks == 0) { if (n_launches) *n_launches = 0; return KG_OK; }
   KG_REQUIRE(dec_ws && seg_ws && d_masks, "kg_net_forward_seg: null buffer");
   Plan* p = net->plan.get();
   Ptrs P{(char*)dec_ws};
   __half* s_hi = reinterpret_cast<__half*>(seg_ws);
   __half* s_lo = reinterpret_cast<__half*>((char*)seg_ws + plane_bytes);
-  // one upload of every problem descriptor
-  std::vector<char> blob;
-  auto put = [&](const void* src, size_t bytes) { const size_t o = align_up(blob.size(), 16); blob.resize(o + bytes); memcpy(blob.data() + o, src, bytes); return o; };
-  size_t o_rs_raw[4], o_rs_scr[4], o_up[4], o_cat[4];
-  for (int l = 0; l < 4; ++l) {
-    auto& st = sp.steps[l];
-    o_rs_raw[l] = put(st.rs_raw.data(), st.rs_raw.size() * sizeof(ResizeProb));
-    o_rs_scr[l] = put(st.rs_scr.data(), st.rs_scr.size() * sizeof(ResizeProb));
-    o_up[l] = put(st.up.data(), st.up.size() * sizeof(ConvProb));
-    o_cat[l] = put(st.cat.data(), st.cat.size() * sizeof(ConvProb));
-  }
-  const size_t o_h0r = put(sp.h0_raw.data(), sp.h0_raw.size() * sizeof(ConvProb));
-  const size_t o_h0s = put(sp.h0_scr.data(), sp.h0_scr.size() * sizeof(ConvProb));
-  const size_t o_h1 = put(sp.h1.data(), sp.h1.size() * sizeof(ConvProb));
-  if (net->seg_probs_bytes < blob.size()) {
-    if (net->d_seg_probs) cudaFree(net->d_seg_probs);
-    net->d_seg_probs = nullptr; net->seg_probs_bytes = 0;
-    KG_CUDA_CHECK(cudaMalloc(&net->d_seg_probs, blob.size() * 2));
-    net->seg_probs_bytes = blob.size() * 2;
-  }
-  KG_CUDA_CHECK(cudaMemcpyAsync(net->d_seg_probs, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
-  KG_CUDA_CHECK(cudaStreamSynchronize(stream));   // blob is a pageable temporary
-  char* dp = (char*)net->d_seg_probs;
+  // the problem descriptors: one asynchronous copy from the pinned staging buffer seg_prepare filled
+  KG_CUDA_CHECK(cudaMemcpyAsync((char*)seg_ws + sp.blob_base, net->h_blob, sp.blob_bytes, cudaMemcpyHostToDevice, stream));
+  KG_CUDA_CHECK(cudaEventRecord(net->blob_copied, stream));
+  const size_t *o_rs_raw = sp.o_rs_raw, *o_rs_scr = sp.o_rs_scr, *o_up = sp.o_up4, *o_cat = sp.o_cat;
+  const size_t o_h0r = sp.o_h0r, o_h0s = sp.o_h0s, o_h1 = sp.o_h1;
+  char* dp = (char*)seg_ws + sp.blob_base;
   int launches = 0;
   StageScope ts(ST_SEG, stream);
   auto feat = [&](int l) -> const Tensor& { return p->tensors[p->feat_ids[l]]; };
@@ -905,8 +932,18 @@ static int seg_prepare_atlas(Net* net, int N, int H, int W, const int* counts, c
     }
   }
   sp.mask_floats = (long long)sp.lv[0].HA * sp.lv[0].WA;
+  BlobWriter bw{net};
+  for (int l = 0; l < 5; ++l) {
+    auto& L = sp.lv[l];
+    sp.o_crop[l] = bw.put(L.crop.data(), L.crop.size() * sizeof(ResizeProb));
+    sp.o_deep[l] = bw.put(L.deepest.data(), L.deepest.size() * sizeof(ResizeProb));
+    sp.o_up[l] = bw.put(L.up.data(), L.up.size() * sizeof(ResizeProb));
+    sp.o_rect[l] = bw.put(L.rects.data(), L.rects.size() * sizeof(RectProb));
+  }
+  KG_TRY(bw.commit(sp));
+  sp.blob_base = align_up(sp.mask_base + moff, 256);
   sp.valid = true;
-  *ws_bytes = sp.mask_base + moff + 256;
+  *ws_bytes = sp.blob_base + align_up(sp.blob_bytes, 256) + 256;
   *mask_floats = sp.mask_floats;
   *n_masks = mi;
   return KG_OK;
@@ -915,8 +952,7 @@ static int seg_prepare_atlas(Net* net, int N, int H, int W, const int* counts, c
 static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes, float* d_masks, cudaStream_t stream, int* n_launches) {
   SegPlan& sp = net->seg;
   Plan* p = net->plan.get();
-  size_t need = sp.mask_base + 256;
-  for (int l = 0; l < 5; ++l) need += align_up((size_t)sp.lv[l].HA * sp.lv[l].WA, 256);
+  const size_t need = sp.blob_base + sp.blob_bytes;
   if (seg_bytes < need) { set_error("kg_net_forward_seg: workspace too small (%zu < %zu)", seg_bytes, need); return KG_ERR_WORKSPACE; }
   if (sp.n_masks == 0) { if (n_launches) *n_launches = 0; return KG_OK; }
   KG_REQUIRE(dec_ws && seg_ws && d_masks, "kg_net_forward_seg: null buffer");
@@ -925,26 +961,11 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
   __half* s_hi = reinterpret_cast<__half*>(seg_ws);
   __half* s_lo = reinterpret_cast<__half*>((char*)seg_ws + plane_bytes);
   uint8_t* masks = reinterpret_cast<uint8_t*>((char*)seg_ws + sp.mask_base);
-  // upload every problem list in one blob
-  std::vector<char> blob;
-  auto put = [&](const void* src, size_t bytes) { const size_t o = align_up(blob.size(), 16); blob.resize(o + bytes); if (bytes) memcpy(blob.data() + o, src, bytes); return o; };
-  size_t o_crop[5], o_deep[5], o_up[5], o_rect[5];
-  for (int l = 0; l < 5; ++l) {
-    auto& L = sp.lv[l];
-    o_crop[l] = put(L.crop.data(), L.crop.size() * sizeof(ResizeProb));
-    o_deep[l] = put(L.deepest.data(), L.deepest.size() * sizeof(ResizeProb));
-    o_up[l] = put(L.up.data(), L.up.size() * sizeof(ResizeProb));
-    o_rect[l] = put(L.rects.data(), L.rects.size() * sizeof(RectProb));
-  }
-  if (net->seg_probs_bytes < blob.size()) {
-    if (net->d_seg_probs) cudaFree(net->d_seg_probs);
-    net->d_seg_probs = nullptr; net->seg_probs_bytes = 0;
-    KG_CUDA_CHECK(cudaMalloc(&net->d_seg_probs, blob.size() * 2));
-    net->seg_probs_bytes = blob.size() * 2;
-  }
-  KG_CUDA_CHECK(cudaMemcpyAsync(net->d_seg_probs, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
-  KG_CUDA_CHECK(cudaStreamSynchronize(stream));   // blob is a pageable temporary
-  const char* dp = (const char*)net->d_seg_probs;
+  // the problem lists: one asynchronous copy from the pinned staging buffer seg_prepare filled (no allocation, no sync here)
+  KG_CUDA_CHECK(cudaMemcpyAsync((char*)seg_ws + sp.blob_base, net->h_blob, sp.blob_bytes, cudaMemcpyHostToDevice, stream));
+  KG_CUDA_CHECK(cudaEventRecord(net->blob_copied, stream));
+  const size_t *o_crop = sp.o_crop, *o_deep = sp.o_deep, *o_up = sp.o_up, *o_rect = sp.o_rect;
+  const char* dp = (const char*)seg_ws + sp.blob_base;
   int launches = 0;
   StageScope ts(ST_SEG, stream);
   // precision "fast": the whole mask branch runs single-pass fp16 on hi planes only (KG_SEG_1PASS_LEVELS=n keeps the levels

@@ -47,6 +47,7 @@ class DecodeResult:
     heat: Optional[list] = None
     vote: Optional[list] = None
     status: Optional[torch.Tensor] = None
+    packed: Optional[torch.Tensor] = None        # [N, packed_k + 1, 5] f64: all-gather record (row 0 = count, rows stored)
     n_launches: int = 0
 
     def overflow(self) -> int:
@@ -55,7 +56,7 @@ class DecodeResult:
 
     def check(self):
         st = self.overflow()
-        if st:
+        if st & 3:
             raise _cabi.KgError(-3, f"decode list overflow (status={st}: bit0 peaks, bit1 boxes); raise max_peaks/max_boxes")
 
     def detections(self) -> List[Optional[np.ndarray]]:
@@ -72,7 +73,7 @@ class Decoder:
     calls launch kernels only (no allocation, no host sync)."""
 
     def __init__(self, N, shapes: Sequence[tuple], box_scales: Sequence[int] = None, max_peaks=4096, max_boxes=4096,
-                 nms_thresh=0.5, peak_thresh=cfg.PEAK_THRESH, debug=False, device="cuda"):
+                 nms_thresh=0.5, peak_thresh=cfg.PEAK_THRESH, debug=False, device="cuda", packed_k=0):
         self.L = _cabi.lib()
         self.N, self.shapes = int(N), [tuple(map(int, s)) for s in shapes]
         S = len(self.shapes)
@@ -104,6 +105,8 @@ class Decoder:
             r.skel_keep = torch.zeros(self.N, S, max_peaks, dtype=torch.uint8, device=dev)
             r.heat = [torch.zeros(self.N, 5, h, w, dtype=f64, device=dev) for h, w in self.shapes]
             r.vote = [torch.zeros(self.N, 5, h, w, dtype=f64, device=dev) for h, w in self.shapes]
+        if packed_k > 0:
+            r.packed = torch.zeros(self.N, packed_k + 1, 5, dtype=f64, device=dev)
         r.skeletons = torch.zeros(self.N, S, max_peaks, 5, 3, dtype=f64, device=dev)
         r.skel_count = torch.zeros(self.N, S, dtype=i32, device=dev)
         self.result = r
@@ -116,6 +119,7 @@ class Decoder:
             o.d_heat[s] = p(r.heat[s]) if debug else None
             o.d_vote[s] = p(r.vote[s]) if debug else None
         o.d_status = p(r.status)
+        o.d_det_packed, o.det_packed_k = p(r.packed), int(packed_k)
         self.out = o
 
     def __call__(self, heads, stream: Optional[torch.cuda.Stream] = None) -> DecodeResult:
@@ -159,7 +163,7 @@ def run_with_growth(make_decoder, heads, max_peaks, max_boxes):
     postprocessing.py builds Python lists).  Raises only past MAX_CAPACITY entries per (image, scale) list."""
     while True:
         res = make_decoder(max_peaks, max_boxes)(heads)
-        st = res.overflow()
+        st = res.overflow() & 3
         if not st:
             return res
         grown = False

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 8
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/ but not exported"
-    assert _cabi.lib().kg_abi_version() == 1
+    assert _cabi.lib().kg_abi_version() == 2
     for s in _cabi.EXPORTS:
         assert s in syms
 

@@ -168,10 +168,19 @@ def test_box_case_table_and_nms_edge_cases():
 
 
 def test_overflow_is_reported_not_hidden():
+    """A fixed-capacity Decoder reports the overflow in its status word; decode_batched re-runs with doubled capacity."""
+    pp = _pp()
     heads, _ = O.planted_scene(11, 256, 256, 20, side=(24, 80))        # 70 peaks at scale 0 > cap of 64
-    res = _pp().decode_batched(_to_batch([heads]), max_peaks=64, max_boxes=64)
+    batch = [tuple(t.cuda() for t in h) for h in _to_batch([heads])]
+    dec = pp.Decoder(1, [tuple(h[0].shape[2:]) for h in batch], max_peaks=64, max_boxes=64)
+    res = dec(batch)
+    assert res.overflow() & 1
     with pytest.raises(RuntimeError):
         res.check()
+    grown = pp.decode_batched(batch, max_peaks=64, max_boxes=64)
+    assert grown.overflow() == 0
+    det, _, _ = O.decode_image(heads)
+    assert np.array_equal(grown.detections()[0][:, :4], det[:, :4])
 
 
 def test_full_size_batch_properties():
