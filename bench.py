@@ -135,18 +135,15 @@ def run_decode(args, rank, world, dist):
     host_pinned = [tuple(torch.from_numpy(a).pin_memory() for a in h) for h in host]
     dev_heads = [tuple(t.to(dev) for t in h) for h in host_pinned]
     shapes = [tuple(h[0].shape[2:]) for h in dev_heads]
-    dec = postprocessing.Decoder(BS, shapes, max_peaks=MAX_PEAKS, max_boxes=MAX_BOXES)
+    dec = postprocessing.Decoder(BS, shapes, max_peaks=MAX_PEAKS, max_boxes=MAX_BOXES, packed_k=MAX_DETS)
     stage_in = [tuple(torch.empty_like(t) for t in h) for h in dev_heads]
-    out_host = torch.empty(BS, MAX_DETS, 5, dtype=torch.float64).pin_memory()
-    cnt_host = torch.empty(BS, dtype=torch.int32).pin_memory()
-    gathered = torch.empty(world * BS, MAX_DETS, 5, dtype=torch.float64, device=dev) if world > 1 else None
-    gathered_cnt = torch.empty(world * BS, dtype=torch.int32, device=dev) if world > 1 else None
+    out_host = torch.empty(BS, MAX_DETS + 1, 5, dtype=torch.float64).pin_memory()
+    gathered = torch.empty(world * BS, MAX_DETS + 1, 5, dtype=torch.float64, device=dev) if world > 1 else None
 
     def step_device():
         r = dec(dev_heads)
-        if world > 1:   # the single collective of the path: all-gather of the padded detection list
-            dist.all_gather_into_tensor(gathered, r.dets[:, :MAX_DETS].contiguous())
-            dist.all_gather_into_tensor(gathered_cnt, r.det_count)
+        if world > 1:   # the single collective of the path: ONE all-gather of the fixed-size detection records (row 0 = count)
+            dist.all_gather_into_tensor(gathered, r.packed)
         return r
 
     def step_e2e():
@@ -155,10 +152,8 @@ def run_decode(args, rank, world, dist):
                 d.copy_(h, non_blocking=True)
         r = dec(stage_in)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, r.dets[:, :MAX_DETS].contiguous())
-            dist.all_gather_into_tensor(gathered_cnt, r.det_count)
-        out_host.copy_(r.dets[:, :MAX_DETS], non_blocking=True)
-        cnt_host.copy_(r.det_count, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, r.packed)
+        out_host.copy_(r.packed, non_blocking=True)
         return r
 
     def sync_all():
@@ -194,7 +189,7 @@ def run_decode(args, rank, world, dist):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
     h2d = sum(t.numel() * 4 for h in host_pinned for t in h)
-    d2h = out_host.numel() * 8 + cnt_host.numel() * 4
+    d2h = out_host.numel() * 8
 
     # per-kernel time of the dominant kernel, live, with CUDA events on the launching stream
     _cabi.timing_enable(True)
@@ -203,25 +198,28 @@ def run_decode(args, rank, world, dist):
     st_ms, st_cnt = _cabi.timing_collect()
     _cabi.timing_enable(False)
     px = BS * sum(h * w for h, w in shapes)
-    names = {0: "vote_kernel", 1: "blur_peak_kernel", 2: "group_kernel", 3: "nms_kernel"}
+    names = {0: "vote_kernel", 1: "blur32_candidates_kernel + exact_peaks_kernel", 2: "group_kernel", 3: "nms_kernel"}
     stage = {names[i]: {"ms_per_step": float(st_ms[i]) / args.steps, "launches_per_step": int(st_cnt[i]) // args.steps} for i in names}
-    dom = max(names, key=lambda i: st_ms[i])
-    alg_bytes = px * (VOTE_BYTES_PX if dom == 0 else BLUR_BYTES_PX if dom == 1 else 0)
+    # the HBM-bound part of the decode is heat-map -> peak list (140 B per pixel and scale: vote reads 15 f32 and
+    # writes 5 x 8 B accumulators, blur+peak reads them back once); grouping / NMS are latency-bound list kernels (~0 bytes)
+    alg_bytes = px * (VOTE_BYTES_PX + BLUR_BYTES_PX)
     pk, pk_kind = peaks()
-    dom_ms = float(st_ms[dom]) / args.steps
+    dom_ms = float(st_ms[0] + st_ms[1]) / args.steps
+    dom_launches = int(st_cnt[0] + st_cnt[1]) // args.steps
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic, traffic_src = profiled_traffic("decode" if dom == 1 else ("decode_vote" if dom == 0 else "none"))
-    roofline = {"kernel": names[dom], "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+    traffic, traffic_src = profiled_traffic("decode")
+    roofline = {"kernel": "vote_kernel + blur32_candidates_kernel + exact_peaks_kernel (head maps -> peak lists)", "bound": "hbm",
+                "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic, "traffic_source": traffic_src,
-                "peak_kind": pk_kind + " (burst copy)",
-                "algorithmic_bytes_per_launch": alg_bytes // max(1, stage[names[dom]]["launches_per_step"]),
+                "peak_kind": pk_kind + " (burst copy)", "ms_per_step": round(dom_ms, 4), "launches_per_step": dom_launches,
+                "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes // max(1, dom_launches),
                 "stages": stage}
     out = {
         "metric": METRIC, "value": round(world * BS * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (planted 40-cell scenes, teacher-forced head maps)",
-        "config": {"workload": "decode-only: bs32/GPU 512x512 head maps (4 scales) -> vote+blur+peak+group+boxes+NMS; inputs 2.45 GB > L2, no flush needed",
-                   "global_batch": world * BS, "detections_per_step": n_det},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": f"synthetic (planted {CELLS}-cell scenes, teacher-forced head maps)",
+        "config": {"workload": f"decode-only: bs{BS}/GPU {HW_IN}x{HW_IN} head maps (4 scales) -> vote+blur+peak+group+boxes+NMS; inputs 2.45 GB > L2, no flush needed",
+                   "config": args.config, "global_batch": world * BS, "detections_per_step": n_det},
         "e2e": {"value": round(world * BS * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -237,40 +235,126 @@ STAGE_NAMES = {0: "vote", 1: "blur_peak", 2: "group", 3: "nms", 8: "conv_cuda_co
                11: "tc_heads_l1", 12: "tc_heads_l2", 13: "bilinear", 14: "maxpool", 15: "export_feats", 16: "forward_seg"}
 
 
+def seg_flops(dets, H, W):
+    """Algorithmic FLOPs (2*MACs, true crop sizes) of forward_seg for a list of per-image detections: KGnet.py:258-267,321-350."""
+    from kg_instance_segmentation_b200.KGnet import patch_rect
+    up_in, lvl_out, feat_c = (64, 256, 512, 1024), (64, 64, 256, 512), (64, 64, 256, 512, 1024)
+    total, boxes = 0.0, 0
+    for d in dets:
+        if d is None:
+            continue
+        for row in d:
+            b = np.asarray(row[:4], np.float32) / np.float32([H, W, H, W])
+            areas = []
+            for l in range(5):
+                r = patch_rect(b, H >> l, W >> l)
+                if r is None:
+                    break
+                areas.append((r[2] - r[0]) * (r[3] - r[1]))
+            if not areas:
+                continue
+            boxes += 1
+            for l in range(len(areas) - 1):     # level l receives the upsampled level l+1: 3x3 up conv + 1x1 conv over the concat
+                total += 2.0 * areas[l] * (up_in[l] * lvl_out[l] * 9 + (feat_c[l] + lvl_out[l]) * lvl_out[l])
+            total += 2.0 * areas[0] * (64 * 64 * 9 + 64 * 9)      # seg_head
+    return total, boxes
+
+
+def gpu_library_baseline(dev, steps=3):
+    """forward_dec of the SAME graph through PyTorch's library kernels (cuDNN convs, ATen pooling / resize) on the same GPU:
+    the implementation the hand-written kernels have to beat.  fp32 with TF32 off (the reference's accuracy),
+    TF32 (PyTorch's default for convs) and fp16 autocast + channels_last (the fastest library path)."""
+    import torch
+    from oracle import kg_oracle as O
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(seed=0).items()}
+    torch.manual_seed(0)
+    x = torch.rand(BS, 3, HW_IN, HW_IN, device=dev) - 0.5
+    out = {}
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32, half in (("fp32_tf32_off", False, False), ("tf32", True, False), ("fp16_autocast_channels_last", True, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            sdv, xv = sd, x
+            if half:
+                sdv = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+                xv = x.contiguous(memory_format=torch.channels_last)
+            def run():
+                if half:
+                    with torch.autocast("cuda", dtype=torch.float16):
+                        return O.forward_dec(sdv, xv)
+                return O.forward_dec(sdv, xv)
+            try:
+                for _ in range(2):
+                    r = run()
+                del r
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    r = run()
+                    del r
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                out[name] = {"ms_per_step": round(ms, 3), "images_per_s": round(BS / (ms * 1e-3), 1)}
+            except Exception as ex:       # e.g. out of memory on a small part: report, do not fail the bench
+                out[name] = {"error": str(ex)[:200]}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = prev
+    out["what"] = f"forward_dec only, bs{BS} {HW_IN}x{HW_IN}, torch {torch.__version__} / cuDNN {torch.backends.cudnn.version()}"
+    return out
+
+
 def run_pipeline(args, rank, world, dist):
     import ctypes as C
     import torch
-    from kg_instance_segmentation_b200 import _cabi, parallel, synthetic
+    from kg_instance_segmentation_b200 import _cabi, synthetic
     from kg_instance_segmentation_b200.inference import InstanceHeat
     dev = torch.device("cuda", torch.cuda.current_device())
     sd = synthetic.make_state_dict(seed=0)
-    engine = InstanceHeat(precision=args.precision, device=dev)
+    engine = InstanceHeat(model=None, precision=args.precision, device=dev)
     engine.model.load_state_dict(sd, strict=True)
+    engine.packed_k = MAX_DETS
     del sd
     torch.manual_seed(0)
-    x_host = (torch.rand(BS, 3, HW_IN, HW_IN) - 0.5).pin_memory()          # test.py:92 input range
+    # the input crosses PCIe as the camera delivers it: uint8 HWC (cv2 BGR), 3 B / pixel; normalisation (test.py:92) runs on the device
+    x_host = torch.randint(0, 256, (BS, HW_IN, HW_IN, 3), dtype=torch.uint8).pin_memory()
     x_dev = x_host.to(dev)
-    x_stage = torch.empty_like(x_dev)
     base, host = planted_batch()
     forced = [tuple(torch.from_numpy(a).to(dev) for a in h) for h in host] if not args.free_running else None
-    det_host = torch.empty(BS, MAX_DETS, 5, dtype=torch.float64).pin_memory()
+    det_host = torch.empty(BS, MAX_DETS + 1, 5, dtype=torch.float64).pin_memory()
     mask_host = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
     state = {}
+    # the single collective of the path: ONE all-gather (NCCL) of the fixed-size per-image detection records
+    # [B_local, MAX_DETS + 1, 5] f64 (row 0 = count), issued on a side stream right after the decode so that it overlaps
+    # forward_seg and the next batch.  No slice copy, no second collective for the counts.
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gathered = torch.empty(world * BS, MAX_DETS + 1, 5, dtype=torch.float64, device=dev) if world > 1 else None
+    decoded, comm_done = torch.cuda.Event(), torch.cuda.Event()
 
-    def gather(res):
-        if world > 1:   # the single collective of the path: all-gather of the padded final detection list (NCCL)
-            state["gathered"] = parallel.all_gather_detections(res.dets[:, :MAX_DETS].contiguous(), res.det_count, BS)
+    def on_decoded(res):
+        if world > 1:
+            cur = torch.cuda.current_stream()
+            decoded.record(cur)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(decoded)
+                dist.all_gather_into_tensor(gathered, res.packed)
+                comm_done.record(comm_stream)
 
     def step_device():
-        dets, seg = engine.detect_batch(x_dev, head_override=forced, packed=True)
-        gather(engine.last_result)
+        if world > 1:
+            torch.cuda.current_stream().wait_event(comm_done)      # the previous gather has read the record buffer (long done)
+        dets, seg = engine.detect_batch(x_dev, head_override=forced, packed=True, on_decoded=on_decoded)
         state["dets"] = dets
         return dets
 
     # e2e: every step's input crosses PCIe inside the timed region.  The copy of step i+1 runs on a side stream while step i
     # computes (two staging buffers); detections + mask patches of every step are copied back before the step ends.
     copy_stream = torch.cuda.Stream(device=dev)
-    x_stages = [x_stage, torch.empty_like(x_dev)]
+    x_stages = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     copied = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -287,18 +371,20 @@ def run_pipeline(args, rank, world, dist):
         issue_h2d(0)
         for i in range(steps):
             b = i & 1
-            torch.cuda.current_stream().wait_event(copied[b])
+            cur = torch.cuda.current_stream()
+            cur.wait_event(copied[b])
             if i + 1 < steps:
                 issue_h2d(i + 1)
-            dets, seg = engine.detect_batch(x_stages[b], head_override=forced, packed=True)
-            consumed[b].record(torch.cuda.current_stream())
-            gather(engine.last_result)
-            det_host.copy_(engine.last_result.dets[:, :MAX_DETS], non_blocking=True)
+            if world > 1:
+                cur.wait_event(comm_done)
+            dets, seg = engine.detect_batch(x_stages[b], head_override=forced, packed=True, on_decoded=on_decoded)
+            consumed[b].record(cur)
+            det_host.copy_(engine.last_result.packed, non_blocking=True)
             m = engine.model.last_masks
             nf = min(m.numel(), mask_host.numel())
             mask_host[:nf].copy_(m[:nf], non_blocking=True)                   # D2H of the step's result: detections + mask patches
             state["mask_floats"] = nf
-            torch.cuda.current_stream().synchronize()
+            cur.synchronize()
 
     def sync_all():
         if world > 1:
@@ -311,6 +397,8 @@ def run_pipeline(args, rank, world, dist):
         e0.record()
         for _ in range(steps):
             fn()
+        if world > 1:
+            torch.cuda.current_stream().wait_event(comm_done)     # the last gather belongs to the timed region
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
@@ -324,12 +412,17 @@ def run_pipeline(args, rank, world, dist):
     for _ in range(warm):
         step_device()
     n_det = sum(0 if d is None else len(d) for d in state["dets"])
+    truncated = bool(int(engine.last_result.status.item()) & 4)
     launches_per_step = engine.last_launches
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     ms = timed(step_device, args.steps)
     clocks = sampler.stop() if sampler else None
     run_e2e(2)
     ms_e2e = timed(lambda: run_e2e(args.steps), 1)
+    if world > 1:     # the gathered records must equal every rank's own detections, ordered by global image index
+        torch.cuda.synchronize()
+        mine = engine.last_result.packed
+        assert torch.equal(gathered[rank * BS:(rank + 1) * BS], mine), "all-gather returned a different detection record"
 
     # per-stage device time, live, CUDA events on the launching stream (separate pass: events serialise nothing but
     # add host work, so they are kept out of the headline timing)
@@ -352,29 +445,45 @@ def run_pipeline(args, rank, world, dist):
         t = float(st_ms[9 + j]) / args.steps
         if t > 0:
             per_class[nme] = {"tflops": round(info[4 + j] / (t * 1e-3) / 1e12, 1), "frac": round(info[4 + j] / (t * 1e-3) / 1e12 / peak_tf, 4)}
+    sflops, sboxes = seg_flops(state["dets"], HW_IN, HW_IN)
+    seg_ms = float(st_ms[16]) / args.steps
+    if seg_ms > 0:
+        per_class["forward_seg"] = {"tflops": round(sflops / (seg_ms * 1e-3) / 1e12, 1), "frac": round(sflops / (seg_ms * 1e-3) / 1e12 / peak_tf, 4),
+                                    "algorithmic_flops_per_step": sflops, "boxes": sboxes}
+    whole = (info[0] + info[1] + sflops) / (ms / args.steps * 1e-3) / 1e12
     traffic, traffic_src = profiled_traffic()
     roofline = {"kernel": "tc_conv_kernel + tc_shift_kernel (tcgen05 implicit-GEMM / row-GEMM shift-add convs: all tensor-core launches of forward_dec)",
                 "bound": "tensor", "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(achieved / peak_tf, 4),
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_kind": pk_kind + " (cuBLAS bf16 sustained; kernel timed inside a long step)",
                 "algorithmic_flops_per_step": info[0], "launches_per_step": tc_launches, "avg_launch_ms": round(tc_ms / max(1, tc_launches), 4),
-                "cuda_core_conv_flops_per_step": info[1], "per_class": per_class, "stages": stages}
+                "cuda_core_conv_flops_per_step": info[1], "whole_step_tflops": round(whole, 1), "whole_step_frac": round(whole / peak_tf, 4),
+                "per_class": per_class, "stages": stages}
+    gbs = world * BS
     out = {
-        "metric": METRIC, "value": round(world * BS * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": warm, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": round(gbs * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "fp16 operands (split hi+lo x3 in backbone/decoder, x2 in three 64-channel decoder convs, single pass in heads), fp32 accumulate; fp64 decode"
                  if args.precision == "fast" else args.precision,
-        "data": "synthetic (seeded Kaiming weights with calibrated heads; rand-0.5 images; planted 40-cell scenes)",
-        "config": {"workload": "bs32/GPU 512x512: forward_dec (ResNet-50 trunk + decoder + 12 heads) -> vote/blur/peak/group/boxes/NMS -> forward_seg"
-                               + ("; decode teacher-forced with planted 40-cell head maps (SURVEY.md 8d-ii)" if forced is not None else "; free-running decode"),
-                   "global_batch": world * BS, "precision": args.precision, "detections_per_step": n_det,
+        "data": f"synthetic (seeded Kaiming weights with calibrated heads; uniform uint8 images; planted {CELLS}-cell scenes)",
+        "config": {"workload": f"bs{BS}/GPU {HW_IN}x{HW_IN}: uint8 HWC -> normalise -> forward_dec (ResNet-50 trunk + decoder + 12 heads) -> vote/blur/peak/group/boxes/NMS -> forward_seg"
+                               + (f"; decode teacher-forced with planted {CELLS}-cell head maps (SURVEY.md 8d-ii)" if forced is not None else "; free-running decode (the network's own head maps)"),
+                   "config": args.config, "global_batch": gbs, "precision": args.precision, "detections_per_step": n_det,
+                   "detection_record_truncated": truncated,
                    "l2_note": "activations of one step (>20 GB) exceed L2; no flush needed"},
-        "e2e": {"value": round(world * BS * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+        "e2e": {"value": round(gbs * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel(),
                 "d2h_bytes_per_step": det_host.numel() * 8 + int(state.get("mask_floats", 0)) * 4},
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_pipeline(base, n_images=1, warm=0)
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        del engine, forced
+        torch.cuda.empty_cache()
+        out["gpu_library_baseline"] = gpu_library_baseline(dev)
+        fd_ms = sum(v["ms_per_step"] for k, v in stages.items() if k in ("conv_cuda_core", "tc_backbone", "tc_decoder", "tc_heads_l1",
+                                                                         "tc_heads_l2", "bilinear", "maxpool"))
+        out["gpu_library_baseline"]["own_forward_dec_ms_per_step"] = round(fd_ms, 3)
     return out
 
 
@@ -447,9 +556,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="fast", choices=["fast", "exact", "reference"])
     ap.add_argument("--free-running", action="store_true", help="decode the network's own head outputs instead of planted maps")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configuration (cfg2 = the headline)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: bs per GPU fixed; strong: the global batch of the config divided over the ranks")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch/cuDNN forward_dec line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    set_config(args.config, world, args.scaling)
     if args.impl == "reference":
         if rank == 0:
             print(json.dumps(run_reference(args)), flush=True)

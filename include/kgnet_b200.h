@@ -178,7 +178,9 @@ int kg_net_forward_seg(kg_net* net, void* d_dec_workspace, void* d_seg_workspace
                        float* d_masks, void* stream, int* n_launches);
 
 /* One nn.Conv2d (+bias, +residual, +ReLU) on fp32 NCHW device tensors: operator-level entry for unit tests.
- * mode: 0 CUDA cores, 1 / 3 = tcgen05 with 1 / 3 split-fp16 passes.  Allocates and synchronises internally. */
+ * mode: 0 CUDA cores; 1 / 2 / 3 = tcgen05 implicit GEMM with 1 / 2 / 3 split-fp16 passes (2 = split activations x
+ * single-plane weights); 11 / 12 / 13 = the row-GEMM + shift-add kernel with 1 / 2 / 3 passes; 21 = single pass with
+ * hi-plane output (CTA-pair kernel where eligible).  Allocates and synchronises internally. */
 int kg_conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R,
                    int S, int stride, int pad, int relu, const float* d_res, int mode, float* d_y, void* stream);
 

@@ -43,9 +43,10 @@ __constant__ int c_mid_index[5][5] = {{-1, 0, 1, 2, 3}, {10, -1, 4, 5, 6}, {11, 
 // 0.85 shared wavefronts per lane-atomic), 32-bit ones run a conflict-free warp per wavefront.  The low word is added with
 // the returning form, an unsigned wrap is the carry into the high word -- exact for any number of votes per cell.
 // Integer accumulation is associative: the result does not depend on any of this.
-constexpr int VT_W = 64, VT_H = 32, VT_HALO = 8;
-constexpr int VR_W = VT_W + 2 * VT_HALO, VR_H = VT_H + 2 * VT_HALO;
+constexpr int VT_W = 64, VT_H = 64, VT_HALO = 5;
+constexpr int VR_W = VT_W + 2 * VT_HALO, VR_H = VT_H + 2 * VT_HALO;     // 74 x 74 cells, 2 x 4 B each: 43 KiB (five CTAs per SM)
 
+// one splat of the generic path: image-bounds and window tests per cell
 __device__ __forceinline__ void vote_cell(long long q, int gy, int gx, int H, int W, int wx0, int wy0, unsigned* __restrict__ s_lo,
                                           unsigned* __restrict__ s_hi, unsigned long long* __restrict__ plane) {
   if (q == 0 || (unsigned)gy >= (unsigned)H || (unsigned)gx >= (unsigned)W) return;      // good_inds (:34-35)
@@ -62,11 +63,29 @@ __device__ __forceinline__ void vote_cell(long long q, int gy, int gx, int H, in
   }
 }
 
-__device__ __forceinline__ void vote_one(float kpv, float sx, float sy, int x, int y, int H, int W, int wx0, int wy0,
+// rare path (image border, or a vote that leaves the tile's window): kept out of line so that the hot loop stays small
+__device__ __noinline__ void vote_slow(long long q0, long long q1, long long q2, long long q3, int iy, int ix, int H, int W, int wx0, int wy0,
+                                       unsigned* __restrict__ s_lo, unsigned* __restrict__ s_hi, unsigned long long* __restrict__ plane) {
+  vote_cell(q0, iy, ix, H, W, wx0, wy0, s_lo, s_hi, plane);          // tl
+  vote_cell(q1, iy, ix + 1, H, W, wx0, wy0, s_lo, s_hi, plane);      // tr
+  vote_cell(q2, iy + 1, ix, H, W, wx0, wy0, s_lo, s_hi, plane);      // bl
+  vote_cell(q3, iy + 1, ix + 1, H, W, wx0, wy0, s_lo, s_hi, plane);  // br
+}
+
+// splat into window cell c (no tests): low word with the returning add, carry + high word only when non-zero
+__device__ __forceinline__ void vote_fast(long long q, int c, unsigned* __restrict__ s_lo, unsigned* __restrict__ s_hi) {
+  const unsigned lo = (unsigned)q;
+  unsigned hi = (unsigned)((unsigned long long)q >> 32);
+  const unsigned old = atomicAdd(s_lo + c, lo);
+  hi += (old + lo < old) ? 1u : 0u;
+  if (hi != 0u) atomicAdd(s_hi + c, hi);
+}
+
+__device__ __forceinline__ void vote_one(float kpv, float sx, float sy, double xd, double yd, int H, int W, int wx0, int wy0,
                                          unsigned* __restrict__ s_lo, unsigned* __restrict__ s_hi,
                                          unsigned long long* __restrict__ plane) {
-  const double xs = (double)x + (double)sx;       // int64 + f32 -> f64 (:49)
-  const double ys = (double)y + (double)sy;
+  const double xs = xd + (double)sx;              // int64 + f32 -> f64 (:49)
+  const double ys = yd + (double)sy;
   const double fx = floor(xs), fy = floor(ys);
   // a vote can only land in the image if floor is in [-1, W): everything else (incl. NaN / inf offsets) is dropped like the
   // reference's good_inds mask does
@@ -77,55 +96,65 @@ __device__ __forceinline__ void vote_one(float kpv, float sx, float sy, int x, i
   const double p44 = (double)kpv * KG_FIX;
   const double a = p44 * omdx, b = p44 * dx, c = p44 * dy;     // (p*(1-dx)), (p*dx), (p*dy): the reference's left-to-right products (:27-30)
   const int ix = (int)fx, iy = (int)fy;
+  const long long q0 = __double2ll_rn(a * omdy), q1 = __double2ll_rn(b * omdy), q2 = __double2ll_rn(c * omdx), q3 = __double2ll_rn(c * dx);
   // ceil = floor + 1 whenever the fractional part is non-zero; when it is zero the splat's weight (dx or dy) is zero and
-  // the vote is skipped (q == 0), so floor + 1 can be used unconditionally
-  vote_cell(__double2ll_rn(a * omdy), iy, ix, H, W, wx0, wy0, s_lo, s_hi, plane);          // tl
-  vote_cell(__double2ll_rn(b * omdy), iy, ix + 1, H, W, wx0, wy0, s_lo, s_hi, plane);      // tr
-  vote_cell(__double2ll_rn(c * omdx), iy + 1, ix, H, W, wx0, wy0, s_lo, s_hi, plane);      // bl
-  vote_cell(__double2ll_rn(c * dx), iy + 1, ix + 1, H, W, wx0, wy0, s_lo, s_hi, plane);    // br
+  // the vote adds nothing, so floor + 1 can be used unconditionally
+  const int lx = ix - wx0, ly = iy - wy0;
+  if (ix >= 0 && ix + 1 < W && iy >= 0 && iy + 1 < H && (unsigned)lx < (unsigned)(VR_W - 1) && (unsigned)ly < (unsigned)(VR_H - 1)) {
+    const int cell = ly * VR_W + lx;                  // all four cells inside the image and inside the window
+    vote_fast(q0, cell, s_lo, s_hi);
+    vote_fast(q1, cell + 1, s_lo, s_hi);
+    vote_fast(q2, cell + VR_W, s_lo, s_hi);
+    vote_fast(q3, cell + VR_W + 1, s_lo, s_hi);
+  } else {
+    vote_slow(q0, q1, q2, q3, iy, ix, H, W, wx0, wy0, s_lo, s_hi, plane);
+  }
 }
 
-__global__ void __launch_bounds__(256) vote_kernel(const float* __restrict__ kp, const float* __restrict__ sh,
+__global__ void __launch_bounds__(256, 4) vote_kernel(const float* __restrict__ kp, const float* __restrict__ sh,
                                                    unsigned long long* __restrict__ acc, int H, int W) {
-  __shared__ unsigned s_lo[VR_H * VR_W], s_hi[VR_H * VR_W];     // 30 KiB
+  __shared__ unsigned s_lo[VR_H * VR_W], s_hi[VR_H * VR_W];
   const int plane_id = blockIdx.z;                      // n * 5 + i
   const int n = plane_id / 5, i = plane_id - n * 5;
   const size_t hw = (size_t)H * W;
   const int x0 = blockIdx.x * VT_W, y0 = blockIdx.y * VT_H;
   const int wx0 = x0 - VT_HALO, wy0 = y0 - VT_HALO;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < VR_H * VR_W; e += 256) { s_lo[e] = 0u; s_hi[e] = 0u; }
   __syncthreads();
   const float* kpp = kp + ((size_t)n * 5 + i) * hw;
   const float* sxp = sh + ((size_t)n * 10 + 2 * i) * hw;
   const float* syp = sxp + hw;
   unsigned long long* plane = acc + (size_t)plane_id * hw;
-  const int cx = (tid & 15) * 4, ry = tid >> 4;         // 16 threads x 4 pixels per tile row, 16 rows per pass
-  const bool vec = (W & 3) == 0;
+  // lane <-> consecutive x: the splats of one instruction go to consecutive cells (distinct banks); warp w owns 8 rows.
+  // All 24 loads of a half-row group are issued before the first vote (the kernel is otherwise bound by their latency).
+  constexpr int RPW = VT_H / 8;
 #pragma unroll
-  for (int pass = 0; pass < VT_H / 16; ++pass) {
-    const int y = y0 + ry + pass * 16, x = x0 + cx;
-    if (y >= H || x >= W) continue;
-    const size_t o = (size_t)y * W + x;
-    if (vec && x + 3 < W) {
-      const float4 k4 = __ldg(reinterpret_cast<const float4*>(kpp + o));
-      const float4 a4 = __ldg(reinterpret_cast<const float4*>(sxp + o));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(syp + o));
-      vote_one(k4.x, a4.x, b4.x, x, y, H, W, wx0, wy0, s_lo, s_hi, plane);
-      vote_one(k4.y, a4.y, b4.y, x + 1, y, H, W, wx0, wy0, s_lo, s_hi, plane);
-      vote_one(k4.z, a4.z, b4.z, x + 2, y, H, W, wx0, wy0, s_lo, s_hi, plane);
-      vote_one(k4.w, a4.w, b4.w, x + 3, y, H, W, wx0, wy0, s_lo, s_hi, plane);
-    } else {
-      for (int q = 0; q < 4 && x + q < W; ++q)
-        vote_one(__ldg(kpp + o + q), __ldg(sxp + o + q), __ldg(syp + o + q), x + q, y, H, W, wx0, wy0, s_lo, s_hi, plane);
+  for (int half = 0; half < VT_W / 32; ++half) {
+    const int x = x0 + half * 32 + lane;
+    if (x >= W) continue;
+    const double xd = (double)x;
+    const int yb = y0 + warp * RPW;
+    float kv[RPW], ax[RPW], ay[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const bool in = yb + r < H;
+      const size_t o = (size_t)(in ? yb + r : 0) * W + x;
+      kv[r] = in ? __ldg(kpp + o) : 0.f; ax[r] = in ? __ldg(sxp + o) : 0.f; ay[r] = in ? __ldg(syp + o) : 0.f;
     }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+      if (yb + r < H) vote_one(kv[r], ax[r], ay[r], xd, (double)(yb + r), H, W, wx0, wy0, s_lo, s_hi, plane);
   }
   __syncthreads();
-  for (int e = tid; e < VR_H * VR_W; e += 256) {
-    const unsigned long long v = ((unsigned long long)s_hi[e] << 32) + (unsigned long long)s_lo[e];
-    if (v == 0ull) continue;
-    const int ly = e / VR_W, lx = e - ly * VR_W;
-    atomicAdd(plane + (size_t)(wy0 + ly) * W + (wx0 + lx), v);   // in-image by construction (only in-image votes were accumulated)
+  // flush: one coalesced global reduction per non-zero cell (cells were only ever hit by in-image votes)
+  for (int ly = warp; ly < VR_H; ly += 8) {
+    unsigned long long* row = plane + (size_t)(wy0 + ly) * W + wx0;
+#pragma unroll
+    for (int lx = lane; lx < VR_W; lx += 32) {
+      const unsigned lo = s_lo[ly * VR_W + lx], hi = s_hi[ly * VR_W + lx];
+      if ((lo | hi) != 0u) atomicAdd(row + lx, ((unsigned long long)hi << 32) + (unsigned long long)lo);
+    }
   }
 }
 
@@ -341,7 +370,13 @@ __device__ __forceinline__ Blur32Row blur32_vstep(float (&win)[4][18], unsigned 
   return r;
 }
 
-__global__ void __launch_bounds__(128) blur32_candidates_kernel(const BlurParams p) {
+// scipy 'reflect' for a row / column index that is at most n outside [0, n): one reflection, no division
+__device__ __forceinline__ int reflect_near(int i, int n) {
+  i = i < 0 ? -1 - i : i;
+  return i >= n ? 2 * n - 1 - i : i;
+}
+
+__global__ void __launch_bounds__(128, 3) blur32_candidates_kernel(const BlurParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int plane_id = blockIdx.y;
   const int H = p.H, W = p.W;
@@ -353,18 +388,26 @@ __global__ void __launch_bounds__(128) blur32_candidates_kernel(const BlurParams
   if (ybeg >= H) return;
   const int yend = min(H, ybeg + p.RH);
   const int x0 = strip * B32_CW;
+  const bool small = H < 2 * BP_HALO + 4;                       // tiny maps: an index can be reflected more than once
   // this lane's columns: strip column c = 4 lane + k <-> image column x0 - 9 + c, reflected at the image border (so the four
   // cells are consecutive only in the interior: per-column offsets from the first one)
   const int g0 = reflect_index(x0 - BP_HALO + 4 * lane, W);
   int off[4];
+  bool col_in[4], col_out[4];                                  // inside the image / a column this strip reports candidates for
 #pragma unroll
-  for (int k = 0; k < 4; ++k) off[k] = reflect_index(x0 - BP_HALO + 4 * lane + k, W) - g0;
+  for (int k = 0; k < 4; ++k) {
+    const int c = 4 * lane + k, gx = x0 - BP_HALO + c;
+    off[k] = reflect_index(gx, W) - g0;
+    col_in[k] = gx >= 0 && gx < W;
+    col_out[k] = c >= BP_HALO && c < BP_HALO + B32_CW && gx < W;
+  }
   const unsigned long long* col0 = plane + g0;
   const float cscale = (float)(KG_UNFIX / KG_PI_R2);
   float win[4][18];
   unsigned long long raw[3][4];
+  auto row_ptr = [&](int gy) { return col0 + (size_t)(small ? reflect_index(gy, H) : reflect_near(gy, H)) * W; };
   auto load_row = [&](int gy, unsigned long long (&dst)[4]) {
-    const unsigned long long* rowp = col0 + (size_t)reflect_index(gy, H) * W;
+    const unsigned long long* rowp = row_ptr(gy);
 #pragma unroll
     for (int k = 0; k < 4; ++k) dst[k] = __ldg(rowp + off[k]);
   };
@@ -381,11 +424,12 @@ __global__ void __launch_bounds__(128) blur32_candidates_kernel(const BlurParams
     for (int k = 0; k < 4; ++k) { win[k][16] = 0.f; win[k][17] = 0.f; }
     load_row(yfirst + 8, raw[0]); load_row(yfirst + 9, raw[1]); load_row(yfirst + 10, raw[2]);
   }
+  // heat >= 0 everywhere, so a neighbour outside the image is represented by 0: it can never beat the centre
   float hu[4] = {0.f, 0.f, 0.f, 0.f}, hc[4] = {0.f, 0.f, 0.f, 0.f};
   const float thr = (float)p.peak_thresh;
   int phase = 0;
   for (int y = yfirst; y <= ylast; ++y) {
-    const unsigned long long* next_row = col0 + (size_t)reflect_index(y + GAUSS_R + 3, H) * W;
+    const unsigned long long* next_row = row_ptr(y + GAUSS_R + 3);
     Blur32Row r;
     switch (phase) {
 #define KG_V32(P) case P: r = blur32_vstep<P>(win, raw, next_row, off, cscale); break;
@@ -405,13 +449,14 @@ __global__ void __launch_bounds__(128) blur32_candidates_kernel(const BlurParams
       v[12 + k] = __shfl_sync(0xffffffffu, r.t[k], (lane + 1) & 31);
       v[16 + k] = __shfl_sync(0xffffffffu, r.t[k], (lane + 2) & 31);
     }
+    const bool row_in = y >= 0 && y < H;
     float hd[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float a = v[k + GAUSS_R] * c_gauss32[GAUSS_R];
 #pragma unroll
       for (int j = 0; j < GAUSS_R; ++j) a = fmaf(v[k + j] + v[k + 16 - j], c_gauss32[j], a);
-      hd[k] = a;
+      hd[k] = (row_in && col_in[k]) ? a : 0.f;
     }
     // ---- conservative peak test of row yr = y - 1 ----
     const int yr = y - 1;
@@ -420,18 +465,13 @@ __global__ void __launch_bounds__(128) blur32_candidates_kernel(const BlurParams
     if (yr >= ybeg && yr < yend) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int c = 4 * lane + k, gx = x0 - BP_HALO + c;
-        if (c < BP_HALO || c >= BP_HALO + B32_CW || gx >= W) continue;
         const float hF = hc[k] * KG_CAND_F;
-        bool cand = hF >= thr;
-        if (yr > 0) cand = cand && hF >= hu[k];
-        if (yr < H - 1) cand = cand && hF >= hd[k];
-        if (gx > 0) cand = cand && hF >= (k == 0 ? left_edge : hc[k - 1]);
-        if (gx < W - 1) cand = cand && hF >= (k == 3 ? right_edge : hc[k + 1]);
-        if (cand) {
+        const float m = fmaxf(fmaxf(hu[k], hd[k]), fmaxf(k == 0 ? left_edge : hc[k - 1], k == 3 ? right_edge : hc[k + 1]));
+        if (col_out[k] && hF >= m && hF >= thr) {
           const int slot = atomicAdd(p.cand_count, 1);
           if (slot < p.cand_cap)
-            p.cand[slot] = ((unsigned long long)p.scale << 56) | ((unsigned long long)plane_id << 32) | ((unsigned long long)yr << 16) | (unsigned long long)gx;
+            p.cand[slot] = ((unsigned long long)p.scale << 56) | ((unsigned long long)plane_id << 32) | ((unsigned long long)yr << 16) |
+                           (unsigned long long)(x0 - BP_HALO + 4 * lane + k);
           else
             atomicOr(p.status, 1);
         }

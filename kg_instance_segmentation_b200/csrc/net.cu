@@ -348,6 +348,20 @@ static void assign_tc(Plan* p, int precision) {
     // emulation (tools/precision_emulate.py, "<group>:w") puts the keypoint-map error at 6-7e-4 with them, 5.8e-4 without.
     if (precision == 1 && getenv("KG_NO_2PASS") == nullptr &&
         (w->name == "c0_conv.2" || w->name == "c1_up_conv.0" || w->name == "c2_up_conv.0")) op.tc_passes = 2;
+    // experiments: KG_2PASS_EXTRA = comma-separated name fragments of further layers to run 2-pass in "fast"
+    if (precision == 1 && op.tc_passes == 3) {
+      if (const char* extra = getenv("KG_2PASS_EXTRA")) {
+        std::string list(extra);
+        size_t pos = 0;
+        while (pos <= list.size()) {
+          const size_t e = list.find(',', pos);
+          const std::string frag = list.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+          if (!frag.empty() && w->name.find(frag) != std::string::npos) op.tc_passes = 2;
+          if (e == std::string::npos) break;
+          pos = e + 1;
+        }
+      }
+    }
   }
 }
 
@@ -501,7 +515,6 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
         p->shift_ops.push_back(t);
         continue;
       }
-      if (op.tc_passes == 2) op.tc_passes = 3;               // the plain implicit-GEMM kernel has no 2-pass variant
       TcConvOp t{};
       t.w = &op.w->tc; t.bias = op.w->d_b;
       t.N = p->N; t.H = op.Hout; t.W = op.Wout; t.R = op.w->R; t.S = op.w->S; t.pad = op.pad;
@@ -1055,8 +1068,8 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
 static int conv2d_nchw(const float* d_x, int N, int Cin, int H, int W, const float* h_w, const float* h_bias, int Cout, int R, int S,
                        int stride, int pad, int relu, const float* d_res, int mode, float* d_y, cudaStream_t stream) {
   KG_REQUIRE(d_x && h_w && d_y && N > 0 && Cin > 0 && Cout > 0, "kg_conv2d_nchw: bad arguments");
-  KG_REQUIRE(mode == 0 || mode == 1 || mode == 3 || mode == 11 || mode == 12 || mode == 13 || mode == 21,
-             "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 / 3 (tensor-core passes) or 11 / 12 / 13 (row-GEMM + shift-add kernel, 1 / 2 / 3 passes) or 21 (single pass, hi-plane output: CTA-pair kernel where eligible)");
+  KG_REQUIRE(mode == 0 || mode == 1 || mode == 2 || mode == 3 || mode == 11 || mode == 12 || mode == 13 || mode == 21,
+             "kg_conv2d_nchw: mode must be 0 (cuda cores), 1 / 2 / 3 (tensor-core passes) or 11 / 12 / 13 (row-GEMM + shift-add kernel, 1 / 2 / 3 passes) or 21 (single pass, hi-plane output: CTA-pair kernel where eligible)");
   Net tmp;
   KG_TRY(set_conv(&tmp, "c", h_w, Cout, Cin, R, S, h_bias, nullptr, nullptr, nullptr, nullptr, 0.0));
   ConvW& w = tmp.convs.at("c");

@@ -73,15 +73,16 @@ struct TcParams {
 // (s * 128 B), so the activations are fetched from L2 once per filter ROW instead of once per tap.
 template <int MT, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
-  constexpr int NPL = PASSES == 3 ? 2 : 1;
+  constexpr int NPA = PASSES >= 2 ? 2 : 1;      // activation planes (hi, lo)
+  constexpr int NPW = PASSES == 3 ? 2 : 1;      // weight planes: 2-pass = split activations x single-plane weights
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 128B swizzle atoms need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_tile = p.a_tile_bytes;                             // one plane of one pixel tile (or strip)
-  const uint32_t a_slot = (uint32_t)(MT * NPL) * a_tile;
+  const uint32_t a_slot = (uint32_t)(MT * NPA) * a_tile;
   const uint32_t w_tile = (uint32_t)p.BN * 128u;
   const uint32_t w_plane = (uint32_t)p.wg * w_tile;                   // one plane of one W slot: wg taps back to back
-  const uint32_t w_slot = (uint32_t)NPL * w_plane;
+  const uint32_t w_slot = (uint32_t)NPW * w_plane;
   const uint32_t stage0 = smem0;                                      // output staging (opt-in TMA-store epilogue): 8 epilogue warps x (hi 4 KiB + lo 4 KiB)
   const uint32_t a_ring = smem0 + (p.o_tma ? 65536u : 0u), w_ring = a_ring + (uint32_t)p.NA * a_slot;
   const uint32_t bars = w_ring + (uint32_t)p.NW * w_slot;
@@ -96,8 +97,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.a_map[0][0]); prefetch_tmap(&p.w_map[0]);
-    if (NPL == 2) { prefetch_tmap(&p.a_map[0][1]); prefetch_tmap(&p.w_map[1]); }
-    if (p.chunks1 > 0) { prefetch_tmap(&p.a_map[1][0]); if (NPL == 2) prefetch_tmap(&p.a_map[1][1]); }
+    if (NPA == 2) prefetch_tmap(&p.a_map[0][1]);
+    if (NPW == 2) prefetch_tmap(&p.w_map[1]);
+    if (p.chunks1 > 0) { prefetch_tmap(&p.a_map[1][0]); if (NPA == 2) prefetch_tmap(&p.a_map[1][1]); }
     if (p.o_tma) { prefetch_tmap(&p.o_map[0]); if (p.out_lo != nullptr) prefetch_tmap(&p.o_map[1]); }
   }
   if (warp == 1 && lane == 0) {
@@ -145,13 +147,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             if (!p.strip || s == 0) {
               mbar_wait(a_empty(ai), aph ^ 1u);
               if (leader) {
-                mbar_expect_tx(a_full(ai), (uint32_t)(MT * NPL) * p.a_tx_bytes);
+                mbar_expect_tx(a_full(ai), (uint32_t)(MT * NPA) * p.a_tx_bytes);
                 const uint32_t abase = a_ring + (uint32_t)ai * a_slot;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                  for (int pl = 0; pl < NPL; ++pl)
-                    tma_load_4d(abase + (uint32_t)(mt * NPL + pl) * a_tile, &p.a_map[src][pl], c,
+                  for (int pl = 0; pl < NPA; ++pl)
+                    tma_load_4d(abase + (uint32_t)(mt * NPA + pl) * a_tile, &p.a_map[src][pl], c,
                                 tx0[mt] * p.stride + (p.strip ? 0 : s) - p.pad, ty0[mt] * p.stride + r - p.pad, tn[mt], a_full(ai));
               }
               __syncwarp();
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 mbar_expect_tx(w_full(wi), w_slot);
                 const uint32_t wbase = w_ring + (uint32_t)wi * w_slot;
 #pragma unroll
-                for (int pl = 0; pl < NPL; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_plane, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
+                for (int pl = 0; pl < NPW; ++pl) tma_load_3d(wbase + (uint32_t)pl * w_plane, &p.w_map[pl], ch * TC_BK, n0, r * p.S + s, w_full(wi));
               }
               __syncwarp();
               if (++wi == p.NW) { wi = 0; wph ^= 1u; }
@@ -199,13 +201,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             const uint32_t abase = a_ring + (uint32_t)ai * a_slot + (p.strip ? (uint32_t)s * 128u : 0u);
             const uint32_t wbase = w_ring + (uint32_t)wi * w_slot + (p.wg > 1 ? (uint32_t)s * w_tile : 0u);
             const bool w_last = p.wg == 1 || s == p.S - 1;
-            uint64_t adesc[MT][NPL], bdesc[NPL];
+            uint64_t adesc[MT][NPA], bdesc[NPW];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-              for (int pl = 0; pl < NPL; ++pl) adesc[mt][pl] = umma_desc(abase + (uint32_t)(mt * NPL + pl) * a_tile);
+              for (int pl = 0; pl < NPA; ++pl) adesc[mt][pl] = umma_desc(abase + (uint32_t)(mt * NPA + pl) * a_tile);
 #pragma unroll
-            for (int pl = 0; pl < NPL; ++pl) bdesc[pl] = umma_desc(wbase + (uint32_t)pl * w_plane);
+            for (int pl = 0; pl < NPW; ++pl) bdesc[pl] = umma_desc(wbase + (uint32_t)pl * w_plane);
             if (leader) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
@@ -216,8 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 const uint32_t accum = cnt > ks_mask ? 1u : 0u;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)                              // innermost: consecutive MMAs hit different accumulators
-                  umma_f16(acc_base + ((uint32_t)mt * (uint32_t)p.KS + chain) * bn, adesc[mt][kAPl[ps] % NPL] + (uint64_t)(2 * k),
-                           bdesc[kWPl[ps] % NPL] + (uint64_t)(2 * k), idesc, accum);
+                  umma_f16(acc_base + ((uint32_t)mt * (uint32_t)p.KS + chain) * bn, adesc[mt][kAPl[ps] % NPA] + (uint64_t)(2 * k),
+                           bdesc[kWPl[ps] % NPW] + (uint64_t)(2 * k), idesc, accum);
                 ++cnt;
               }
             }
@@ -599,6 +601,8 @@ static void tc_init() {
       cudaFuncSetAttribute(tc_conv_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(tc_conv_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(tc_conv_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(tc_conv_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(tc_conv_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(tc_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_SMEM) != cudaSuccess) {
     g_tc_state = -1; snprintf(g_tc_msg, sizeof(g_tc_msg), "cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(cudaGetLastError()));
     return;
@@ -683,8 +687,8 @@ int tc_conv_prepare(TcConvOp* op) {
   KG_REQUIRE(op && op->w && op->w->valid, "tc_conv_prepare: weights not packed");
   KG_REQUIRE(op->C0 % TC_BK == 0 && op->C1 % TC_BK == 0 && op->C0 + op->C1 == op->w->cin, "tc_conv_prepare: channel split %d+%d vs cin %d",
              op->C0, op->C1, op->w->cin);
-  KG_REQUIRE(op->passes == 1 || op->passes == 3, "tc_conv_prepare: passes=%d", op->passes);
-  KG_REQUIRE(op->passes == 1 || (op->in0_lo != nullptr && (op->C1 == 0 || op->in1_lo != nullptr)), "tc_conv_prepare: 3-pass needs lo planes");
+  KG_REQUIRE(op->passes >= 1 && op->passes <= 3, "tc_conv_prepare: passes=%d", op->passes);
+  KG_REQUIRE(op->passes == 1 || (op->in0_lo != nullptr && (op->C1 == 0 || op->in1_lo != nullptr)), "tc_conv_prepare: 2- / 3-pass need lo planes");
   KG_REQUIRE(op->out_hi == nullptr || op->Cout % 16 == 0, "tc_conv_prepare: NHWC output needs Cout %% 16 == 0 (Cout=%d)", op->Cout);
   std::shared_ptr<TcParams> sp(new TcParams());
   TcParams& p = *sp;
@@ -700,7 +704,8 @@ int tc_conv_prepare(TcConvOp* op) {
   p.BW = bw; p.BH = TC_BM / bw;
   p.tiles_x = ceil_div(op->W, p.BW); p.tiles_y = ceil_div(op->H, p.BH);
   p.m_tiles = p.tiles_x * p.tiles_y * op->N;
-  p.passes = op->passes; p.NPL = op->passes == 3 ? 2 : 1;
+  p.passes = op->passes; p.NPL = op->passes >= 2 ? 2 : 1;      // NPL: activation planes; weight planes: npw below
+  const int npw = op->passes == 3 ? 2 : 1;
   // TMEM budget: acc_stages x MT x BN fp32 columns <= 512.  Two accumulator buffers let the epilogue of one tile overlap
   // the MMAs of the next; MT = 2 (two pixel tiles share each weight tile) only where that still fits.
   p.acc_stages = env_int("KG_TC_ACC", 2) >= 2 ? 2 : 1;
@@ -730,9 +735,9 @@ int tc_conv_prepare(TcConvOp* op) {
   const size_t budget = TC_MAX_SMEM - 2048 - (p.o_tma ? 65536 : 0);
   // weight tap group: all S taps of a filter row in one W slot when that slot stays small (narrow-N layers)
   p.wg = 1;
-  if (op->S > 1 && (size_t)op->S * p.NPL * p.BN * 128 <= (size_t)env_int("KG_TC_WG_MAXKB", 48) * 1024 && env_int("KG_TC_WG", 1) != 0) p.wg = op->S;
+  if (op->S > 1 && (size_t)op->S * npw * p.BN * 128 <= (size_t)env_int("KG_TC_WG_MAXKB", 48) * 1024 && env_int("KG_TC_WG", 1) != 0) p.wg = op->S;
   auto fit = [&](int mtv, int* na, int* nw) {
-    const size_t a_slot = (size_t)mtv * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.wg * p.NPL * p.BN * 128;
+    const size_t a_slot = (size_t)mtv * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.wg * npw * p.BN * 128;
     if (strip || p.wg > 1) {
       // A slots and W slots are consumed at different rates (one A strip per filter row / one W group per filter row)
       *na = strip ? 2 : 4;
@@ -758,7 +763,7 @@ int tc_conv_prepare(TcConvOp* op) {
   if (!fit(p.MT, &na, &nw) && p.MT == 2) { p.MT = 1; }
   if (!fit(p.MT, &na, &nw) && p.wg > 1) { p.wg = 1; }
   if (!fit(p.MT, &na, &nw)) {
-    const size_t a_slot = (size_t)p.MT * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.wg * p.NPL * p.BN * 128;
+    const size_t a_slot = (size_t)p.MT * p.NPL * p.a_tile_bytes, w_slot = (size_t)p.wg * npw * p.BN * 128;
     KG_REQUIRE(a_slot + w_slot <= budget, "tc_conv_prepare: tile does not fit in shared memory");
     na = nw = 1;
   }
@@ -807,7 +812,7 @@ int tc_conv_prepare(TcConvOp* op) {
     if (p.NPL == 2) KG_TRY(encode_act_map(&p.a_map[1][1], op->in1_lo, op->in1_C, op->W, op->H, op->N, box_w, p.BH));
   }
   KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.two_cta ? p.BN / 2 : p.BN, p.wg));
-  if (p.NPL == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
+  if (npw == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
   if (p.o_tma) {
     KG_TRY(encode_act_map(&p.o_map[0], op->out_hi, op->Cout, op->W, op->H, op->N, p.o_bw, 32 / p.o_bw));
     if (op->out_lo != nullptr) KG_TRY(encode_act_map(&p.o_map[1], op->out_lo, op->Cout, op->W, op->H, op->N, p.o_bw, 32 / p.o_bw));
@@ -816,7 +821,7 @@ int tc_conv_prepare(TcConvOp* op) {
   op->grid_x = (unsigned)std::min(p.num_work, std::max(1, persist));
   if (p.two_cta) op->grid_x = (unsigned)std::min(2 * p.num_work, std::max(2, persist & ~1));   // whole CTA pairs
   op->grid_y = 1;
-  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.wg * p.NPL * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024 + (p.o_tma ? 65536 : 0));
+  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.wg * npw * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024 + (p.o_tma ? 65536 : 0));
   if (p.two_cta) op->smem_bytes = (unsigned)((size_t)p.NA * p.a_tile_bytes + (size_t)p.NW * (p.BN / 2) * 128 + 16 * (p.NA + p.NW) + 128 + 1024);
   KG_REQUIRE(op->smem_bytes <= (unsigned)TC_MAX_SMEM, "tc_conv_prepare: smem %u > %d", op->smem_bytes, TC_MAX_SMEM);
   op->params = sp;
@@ -840,6 +845,8 @@ int tc_conv_launch(const TcConvOp* op, float* out32, cudaStream_t stream) {
   KG_REQUIRE(!p.two_cta, "tc_conv_launch: the CTA-pair kernel has no fp32 NCHW output");
   if (p.MT == 1 && p.passes == 1) tc_conv_kernel<1, 1><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
   else if (p.MT == 2 && p.passes == 1) tc_conv_kernel<2, 1><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
+  else if (p.MT == 1 && p.passes == 2) tc_conv_kernel<1, 2><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
+  else if (p.MT == 2 && p.passes == 2) tc_conv_kernel<2, 2><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
   else if (p.MT == 1 && p.passes == 3) tc_conv_kernel<1, 3><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
   else tc_conv_kernel<2, 3><<<grid, TC_THREADS, op->smem_bytes, stream>>>(p);
   KG_CUDA_CHECK(cudaGetLastError());

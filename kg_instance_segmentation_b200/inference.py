@@ -64,28 +64,32 @@ class InstanceHeat:
         self.model.to(self.device).eval()
         self._decoders = {}
         self.last_launches = 0
+        self.packed_k = 0        # > 0: the decode also writes the fixed-size per-image detection records (data-parallel all-gather)
 
     def load_weights(self, resume, dataset):
         """test.py:60-61."""
         self.model.load_state_dict(torch.load(os.path.join("weights_" + dataset, resume), map_location="cpu"))
 
     def _decoder(self, N, shapes, nms_thresh, max_peaks, max_boxes):
-        key = (N, tuple(shapes), float(nms_thresh), max_peaks, max_boxes)
+        key = (N, tuple(shapes), float(nms_thresh), max_peaks, max_boxes, self.packed_k)
         d = self._decoders.get(key)
         if d is None:
             self._decoders.clear()
             d = self._decoders[key] = postprocessing.Decoder(N, shapes, nms_thresh=nms_thresh, max_peaks=max_peaks,
-                                                             max_boxes=max_boxes, device=self.device)
+                                                             max_boxes=max_boxes, device=self.device, packed_k=self.packed_k)
         return d
 
-    def detect_batch(self, x, nms_thresh=0.5, with_masks=True, head_override=None, max_peaks=4096, max_boxes=4096, packed=False):
+    def detect_batch(self, x, nms_thresh=0.5, with_masks=True, head_override=None, max_peaks=4096, max_boxes=4096, packed=False,
+                     on_decoded=None):
         """x: [N,3,H,W] fp32 CUDA tensor in the reference's input convention (BGR/255 - 0.5, test.py:92), or a uint8
         [N,H,W,3] CUDA batch (normalised on the device).
         Returns (detections, seg): detections[i] = (M_i,5) float64 array or None (nms.py convention);
         seg = [mask_patches, mask_dets] of forward_seg, or the packed KGnet.SegResult when packed=True (None when
         with_masks is False).
         head_override: optional per-scale (kp, short, mid) CUDA tensors decoded INSTEAD of the network's own head
-        outputs (teacher-forced decode load for benchmarking; the network still computes all of its heads)."""
+        outputs (teacher-forced decode load for benchmarking; the network still computes all of its heads).
+        on_decoded(result): called right after the decode has been ENQUEUED (before any host sync), e.g. to issue the
+        data-parallel all-gather of result.packed on a side stream."""
         model = self.model
         launches = 0
         if x.dtype == torch.uint8:
@@ -103,6 +107,8 @@ class InstanceHeat:
         shapes = [tuple(h[0].shape[2:]) for h in heads]
         res = postprocessing.run_with_growth(lambda mp, mb: self._decoder(N, shapes, nms_thresh, mp, mb), heads, max_peaks, max_boxes)
         launches += res.n_launches
+        if on_decoded is not None:
+            on_decoded(res)
         dets = res.detections()                     # the one host sync of the pipeline: boxes are needed on the host
         self.last_result = res
         seg = None

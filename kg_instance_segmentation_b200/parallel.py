@@ -1,7 +1,11 @@
 """Data-parallel plumbing: images are independent end to end (no cross-image op in forward_dec, decode, NMS or
-forward_seg), so the batch is sharded across ranks in contiguous slices and the ONLY collective of the path is one
-all-gather of the fixed-size padded final detection list (torch.distributed: NCCL over NVLink on GPUs, gloo in the
-CPU tests).  The reference has no multi-GPU path (its DataParallel stub is never called, test.py:57-58)."""
+forward_seg), so the batch is sharded across ranks in contiguous slices and the ONLY collective of the path is ONE
+all-gather of the fixed-size per-image detection records (torch.distributed: NCCL over NVLink on GPUs, gloo in the
+CPU tests).  The reference has no multi-GPU path (its DataParallel stub is never called, test.py:57-58).
+
+Record layout (written on the device by nms_kernel, include/kgnet_b200.h `d_det_packed`): [B, K + 1, 5] f64 per rank;
+row 0 = (detection count, rows stored, 0, 0, 0) -- count < 0 marks a padding slot of a short shard --, rows 1.. = the
+detections [y1, x1, y2, x2, conf] in NMS keep order.  Counts travel inside the record: no second collective, no slicing."""
 from __future__ import annotations
 
 from typing import List, Optional, Tuple
@@ -19,46 +23,46 @@ def shard_range(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def pad_detections(dets: List[Optional[np.ndarray]], kmax: int, device=None):
-    """Per-image (M,5) float64 arrays (or None) -> padded tensor [B, kmax, 5] f64 and counts [B] i32."""
+def pack_detections(dets: List[Optional[np.ndarray]], kmax: int, device=None) -> torch.Tensor:
+    """Host-side builder of the record tensor (the device path gets it from the decode directly): per-image (M,5) float64
+    arrays (or None) -> [B, kmax + 1, 5] f64."""
     B = len(dets)
-    out = torch.zeros(B, kmax, 5, dtype=torch.float64)
-    cnt = torch.zeros(B, dtype=torch.int32)
+    out = torch.zeros(B, kmax + 1, 5, dtype=torch.float64)
     for i, d in enumerate(dets):
-        if d is None:
-            continue
-        if len(d) > kmax:
-            raise ValueError(f"image {i} has {len(d)} detections > kmax={kmax}")
-        out[i, :len(d)] = torch.from_numpy(np.ascontiguousarray(d))
-        cnt[i] = len(d)
-    if device is not None:
-        out, cnt = out.to(device), cnt.to(device)
-    return out, cnt
+        n = 0 if d is None else len(d)
+        k = min(n, kmax)
+        out[i, 0, 0], out[i, 0, 1] = n, k
+        if k:
+            out[i, 1:k + 1] = torch.from_numpy(np.ascontiguousarray(d[:k]))
+    return out.to(device) if device is not None else out
 
 
-def all_gather_detections(dets: torch.Tensor, counts: torch.Tensor, local_max: int, group=None):
-    """dets [B_local, K, 5] f64, counts [B_local] i32 (device tensors for NCCL, CPU tensors for gloo).
-    `local_max` = the largest per-rank batch (shards may differ by one image): shorter shards are padded so that every
-    rank contributes the same number of bytes.  Returns (dets [world*local_max, K, 5], counts [world*local_max])."""
+def all_gather_records(records: torch.Tensor, local_max: int, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """records [B_local, K + 1, 5] f64 (device tensor for NCCL, CPU tensor for gloo).  `local_max` = the largest per-rank
+    batch (shards may differ by one image): shorter shards are padded with count = -1 records so that every rank
+    contributes the same number of bytes.  ONE collective.  Returns [world * local_max, K + 1, 5]."""
     world = dist.get_world_size(group)
-    B, K, _ = dets.shape
+    B = records.shape[0]
     if B < local_max:
-        dets = torch.cat([dets, dets.new_zeros(local_max - B, K, 5)], 0)
-        counts = torch.cat([counts, counts.new_full((local_max - B,), -1)], 0)     # -1 marks padding slots
-    g_d = dets.new_empty(world * local_max, K, 5)
-    g_c = counts.new_empty(world * local_max)
-    dist.all_gather_into_tensor(g_d, dets.contiguous(), group=group)
-    dist.all_gather_into_tensor(g_c, counts.contiguous(), group=group)
-    return g_d, g_c
+        pad = records.new_zeros(local_max - B, *records.shape[1:])
+        pad[:, 0, 0] = -1
+        records = torch.cat([records, pad], 0)
+    if out is None:
+        out = records.new_empty(world * local_max, *records.shape[1:])
+    dist.all_gather_into_tensor(out, records.contiguous(), group=group)
+    return out
 
 
-def trim_gathered(g_dets: torch.Tensor, g_counts: torch.Tensor) -> List[Optional[np.ndarray]]:
-    """Gathered padded buffers -> ragged per-image list ordered by GLOBAL image index (padding slots dropped)."""
-    d = g_dets.cpu().numpy()
-    c = g_counts.cpu().numpy()
+def unpack_records(gathered: torch.Tensor) -> List[Optional[np.ndarray]]:
+    """Gathered records -> ragged per-image list ordered by GLOBAL image index (padding slots dropped); an image whose count
+    exceeds the rows stored raises (the record was truncated: raise K)."""
+    g = gathered.cpu().numpy()
     out = []
-    for i in range(len(c)):
-        if c[i] < 0:
+    for rec in g:
+        n, k = int(rec[0, 0]), int(rec[0, 1])
+        if n < 0:
             continue
-        out.append(d[i, :c[i]].copy() if c[i] > 0 else None)
+        if k < n:
+            raise ValueError(f"detection record truncated: {n} detections, {k} stored")
+        out.append(rec[1:k + 1].copy() if k > 0 else None)
     return out

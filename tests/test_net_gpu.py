@@ -103,7 +103,7 @@ def test_conv_tensor_core_stride2(case):
 
 
 @pytest.mark.parametrize("case", TC_CASES)
-@pytest.mark.parametrize("mode", [3, 1])
+@pytest.mark.parametrize("mode", [3, 2, 1])
 def test_conv_tensor_core_path(case, mode):
     from kg_instance_segmentation_b200 import _cabi
     if not _cabi.lib().kg_tc_available():
@@ -111,7 +111,7 @@ def test_conv_tensor_core_path(case, mode):
     x, w, b, pad, r, y = _case(2, *case)
     got = _conv(x, w, b, 1, pad, case[7], r, mode)
     scale = float(y.abs().max())
-    tol = (2e-4 if mode == 3 else 3e-3) * scale + 1e-5
+    tol = (2e-4 if mode == 3 else 3e-3) * scale + 1e-5      # 2-pass: split activations x fp16 weights (11-bit weight rounding)
     err = float((got - y).abs().max())
     assert err <= tol, f"max err {err} > {tol}"
 

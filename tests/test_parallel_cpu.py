@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the data-parallel plumbing (host logic; the per-image results are stand-ins produced by
-the oracle NMS so that the test needs no GPU): all-gather of the padded per-shard detection lists == the single-process
+the oracle NMS so that the test needs no GPU): ONE all-gather of the fixed-size per-shard detection records == the single-process
 result of the same global batch, ordered by global image index."""
 import os
 import sys
@@ -32,9 +32,8 @@ def _worker(rank, world, port, global_batch, q):
         lo, hi = parallel.shard_range(global_batch, rank, world)
         local_max = max(parallel.shard_range(global_batch, r, world)[1] - parallel.shard_range(global_batch, r, world)[0]
                         for r in range(world))
-        d, c = parallel.pad_detections(full[lo:hi], kmax=8)
-        gd, gc = parallel.all_gather_detections(d, c, local_max)
-        got = parallel.trim_gathered(gd, gc)
+        rec = parallel.pack_detections(full[lo:hi], kmax=8)
+        got = parallel.unpack_records(parallel.all_gather_records(rec, local_max))
         ok = len(got) == global_batch and all((a is None and b is None) or (a is not None and b is not None and np.array_equal(a, b))
                                               for a, b in zip(got, full))
         q.put((rank, ok, len(got)))

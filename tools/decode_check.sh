@@ -11,7 +11,7 @@ d=json.load(open('gpurun_out/${tag}_bench_decode.json'))
 print('decode', d['value'], d['ms_per_step'], json.dumps(d['roofline']['stages']))
 PY
 if [ "${FULL:-1}" = "1" ]; then
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'vote_kernel|blur_peak' -s 24 -c 8 -f -o gpurun_out/${tag}_decode \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'vote_kernel|blur32|exact_peaks|blur_peak' -s 27 -c 9 -f -o gpurun_out/${tag}_decode \
       python bench.py --workload decode --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu.log 2>&1
   ncu -i gpurun_out/${tag}_decode.ncu-rep --page raw --csv > gpurun_out/${tag}_decode_raw.csv 2>/dev/null
 fi
