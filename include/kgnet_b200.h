@@ -212,6 +212,25 @@ int kg_paste_masks(const float* d_masks, const long long* d_mask_off, const int*
                    const float* d_dets, int n, int input_h, int input_w, int image_h, int image_w, float seg_thresh,
                    uint8_t* d_out_masks, float* d_out_dets, void* stream);
 
+/* preprocessing.get_ground_truth (preprocessing.py:105-118) + the channel concat of dataset_base.py:99-102 for a batch:
+ * d_boxes [sum n_b, 5, 2] fp32 keypoints (x, y) in the order tl, tr, bl, br, centre (dataset_base.masks_to_bboxes),
+ * image b owns rows d_box_offsets[b] .. d_box_offsets[b+1] (B + 1 ints).  d_gt: [B, 55, H, W] fp32 =
+ * concat(kp heat [5], short offsets [10], mid offsets [40]) -- the gt_c* tensors DetectionLossAll consumes. */
+int kg_encode_ground_truth(const float* d_boxes, const int* d_box_offsets, int B, int H, int W, float* d_gt, void* stream);
+
+/* Loss forward passes (the reference's validation loop, train.py:165-177; no backward pass in this library).
+ * DetectionLossAll.forward (loss.py:40-49) of one scale: predictions [N,5|10|40,H,W] fp32, target d_gt [N,55,H,W] fp32.
+ * d_scratch5: 5 doubles of device scratch (cleared here); d_out4 = (kp BCE, short, mid, kp + short + 0.25 * mid) fp32. */
+int kg_detection_loss(const float* d_pr_kp, const float* d_pr_short, const float* d_pr_mid, const float* d_gt, int N, int H, int W,
+                      float kp_radius, double* d_scratch5, float* d_out4, void* stream);
+
+/* SEG_loss.forward's per-object term (seg_loss.py:62-86) for n_pairs matched (prediction, ground-truth object) pairs:
+ * mean BCE between mask patch and the ground-truth mask cropped to the rounded box and resized (INTER_NEAREST) to the patch.
+ * d_pairs: n_pairs records { int64 patch_off; int32 pitch, h, w, gt_index, y1, x1, y2, x2; } (40 bytes, 8-byte aligned);
+ * d_gt_masks: [n_gt, H, W] fp32; d_pair_loss: [n_pairs] fp32. */
+int kg_seg_loss_pairs(const float* d_masks, const void* d_pairs, int n_pairs, const float* d_gt_masks, int H, int W,
+                      float* d_pair_loss, void* stream);
+
 /* 1 when the tcgen05/TMA path initialised on the current device; kg_tc_status() says why not otherwise. */
 int kg_tc_available(void);
 const char* kg_tc_status(void);

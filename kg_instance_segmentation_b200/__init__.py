@@ -9,5 +9,6 @@ from . import config  # noqa: F401
 from . import _cabi  # noqa: F401
 from . import nms, postprocessing  # noqa: F401
 from . import KGnet  # noqa: F401
+from . import preprocessing, loss, seg_loss  # noqa: F401
 
-__all__ = ["config", "nms", "postprocessing", "KGnet"]
+__all__ = ["config", "nms", "postprocessing", "KGnet", "preprocessing", "loss", "seg_loss"]

@@ -129,22 +129,27 @@ __global__ void __launch_bounds__(256, 4) vote_kernel(const float* __restrict__ 
   // lane <-> consecutive x: the splats of one instruction go to consecutive cells (distinct banks); warp w owns 8 rows.
   // All 24 loads of a half-row group are issued before the first vote (the kernel is otherwise bound by their latency).
   constexpr int RPW = VT_H / 8;
+  const int yb = y0 + warp * RPW;
+  const int rows = min(RPW, H - yb);                      // uniform per warp
 #pragma unroll
   for (int half = 0; half < VT_W / 32; ++half) {
     const int x = x0 + half * 32 + lane;
-    if (x >= W) continue;
+    if (x >= W || rows <= 0) continue;
     const double xd = (double)x;
-    const int yb = y0 + warp * RPW;
+    const int o = yb * W + x;                               // 32-bit indexing: a plane has < 2^31 cells (checked by the launcher)
+    const float* kq = kpp + o; const float* xq = sxp + o; const float* yq = syp + o;
     float kv[RPW], ax[RPW], ay[RPW];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-      const bool in = yb + r < H;
-      const size_t o = (size_t)(in ? yb + r : 0) * W + x;
-      kv[r] = in ? __ldg(kpp + o) : 0.f; ax[r] = in ? __ldg(sxp + o) : 0.f; ay[r] = in ? __ldg(syp + o) : 0.f;
+      const int ro = r < rows ? r * W : 0;
+      kv[r] = __ldg(kq + ro); ax[r] = __ldg(xq + ro); ay[r] = __ldg(yq + ro);
     }
+    double yd = (double)yb;
 #pragma unroll
-    for (int r = 0; r < RPW; ++r)
-      if (yb + r < H) vote_one(kv[r], ax[r], ay[r], xd, (double)(yb + r), H, W, wx0, wy0, s_lo, s_hi, plane);
+    for (int r = 0; r < RPW; ++r) {
+      if (r < rows) vote_one(kv[r], ax[r], ay[r], xd, yd, H, W, wx0, wy0, s_lo, s_hi, plane);
+      yd += 1.0;
+    }
   }
   __syncthreads();
   // flush: one coalesced global reduction per non-zero cell (cells were only ever hit by in-image votes)
@@ -352,16 +357,16 @@ __constant__ float c_gauss32[9] = {(float)0x1.18aad19e4159bp-14, (float)0x1.c98b
 struct Blur32Row { float t[4]; };
 
 // one row of the vertical pass for window phase PH (18-slot circular window: slot (PH + i) % 18 = input row y - 8 + i);
-// the raw accumulator rows y + 8 .. y + 10 wait in a 3-deep queue (index = phase % 3) so that three rows of loads are in flight
+// the raw accumulator row y + 8 was loaded one iteration earlier (a row iteration of a warp takes longer than the load latency)
 template <int PH>
-__device__ __forceinline__ Blur32Row blur32_vstep(float (&win)[4][18], unsigned long long (&raw)[3][4],
+__device__ __forceinline__ Blur32Row blur32_vstep(float (&win)[4][18], unsigned long long (&raw)[4],
                                                   const unsigned long long* __restrict__ next_row, const int (&off)[4], float cscale) {
-  constexpr int s_new = (PH + 16) % 18, qi = PH % 3;
+  constexpr int s_new = (PH + 16) % 18;
   Blur32Row r;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    win[k][s_new] = (float)(long long)raw[qi][k] * cscale;
-    raw[qi][k] = __ldg(next_row + off[k]);
+    win[k][s_new] = (float)(long long)raw[k] * cscale;
+    raw[k] = __ldg(next_row + off[k]);
     float t = win[k][(PH + 8) % 18] * c_gauss32[GAUSS_R];
 #pragma unroll
     for (int j = 0; j < GAUSS_R; ++j) t = fmaf(win[k][(PH + j) % 18] + win[k][(PH + 16 - j) % 18], c_gauss32[j], t);
@@ -376,7 +381,7 @@ __device__ __forceinline__ int reflect_near(int i, int n) {
   return i >= n ? 2 * n - 1 - i : i;
 }
 
-__global__ void __launch_bounds__(128, 3) blur32_candidates_kernel(const BlurParams p) {
+__global__ void __launch_bounds__(128, 4) blur32_candidates_kernel(const BlurParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int plane_id = blockIdx.y;
   const int H = p.H, W = p.W;
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(128, 3) blur32_candidates_kernel(const BlurPar
   const unsigned long long* col0 = plane + g0;
   const float cscale = (float)(KG_UNFIX / KG_PI_R2);
   float win[4][18];
-  unsigned long long raw[3][4];
+  unsigned long long raw[4];
   auto row_ptr = [&](int gy) { return col0 + (size_t)(small ? reflect_index(gy, H) : reflect_near(gy, H)) * W; };
   auto load_row = [&](int gy, unsigned long long (&dst)[4]) {
     const unsigned long long* rowp = row_ptr(gy);
@@ -422,14 +427,14 @@ __global__ void __launch_bounds__(128, 3) blur32_candidates_kernel(const BlurPar
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { win[k][16] = 0.f; win[k][17] = 0.f; }
-    load_row(yfirst + 8, raw[0]); load_row(yfirst + 9, raw[1]); load_row(yfirst + 10, raw[2]);
+    load_row(yfirst + 8, raw);
   }
   // heat >= 0 everywhere, so a neighbour outside the image is represented by 0: it can never beat the centre
   float hu[4] = {0.f, 0.f, 0.f, 0.f}, hc[4] = {0.f, 0.f, 0.f, 0.f};
   const float thr = (float)p.peak_thresh;
   int phase = 0;
   for (int y = yfirst; y <= ylast; ++y) {
-    const unsigned long long* next_row = row_ptr(y + GAUSS_R + 3);
+    const unsigned long long* next_row = row_ptr(y + GAUSS_R + 1);
     Blur32Row r;
     switch (phase) {
 #define KG_V32(P) case P: r = blur32_vstep<P>(win, raw, next_row, off, cscale); break;
@@ -972,10 +977,10 @@ static int launch_blur_peak(BlurParams bp, int N, cudaStream_t stream) {
   return KG_OK;
 }
 
-// fp32 prefilter (blur32_candidates_kernel): warp-private strips of 110 output columns, 4 warps per CTA, ~12 warps per SM
+// fp32 prefilter (blur32_candidates_kernel): warp-private strips of 110 output columns, 4 warps per CTA, 16 warps per SM at 128 registers
 static int launch_blur32(BlurParams bp, int N, cudaStream_t stream) {
   bp.n_strips = ceil_div(bp.W, B32_CW);
-  bp.RH = pick_rows(bp.H, (long long)N * 5 * bp.n_strips, (long long)num_sms() * 12);
+  bp.RH = pick_rows(bp.H, (long long)N * 5 * bp.n_strips, (long long)num_sms() * 16);
   const int items = bp.n_strips * ceil_div(bp.H, bp.RH);
   dim3 grid(ceil_div(items, 4), N * 5, 1);
   KG_REQUIRE(grid.y <= 65535, "blur32: grid too large");

@@ -459,6 +459,101 @@ def test_inference(sd, image, input_h, input_w, nms_thresh=0.5, seg_thresh=0.5, 
 
 
 # ---------------------------------------------------------------------------------------------
+# Ground-truth encoder restated: preprocessing.py:45-118 (+ the channel concat of dataset_base.py:99-102)
+
+def encode_ground_truth(bboxes, height, width):
+    """bboxes [n,5,2] keypoints (x,y) -> gt [55,H,W] f32 = concat(kp heat [5], short offsets [10], mid offsets [40]).
+
+    load_disc_masks (:62-77): nearest instance by fp64 Euclidean distance (np.argmin: first minimum), inside when <= KP_RADIUS.
+    compute_short_offsets / copy_with_border_check (:12-60): every instance pastes its WHOLE clipped (2R+1)^2 window -- integer
+    offsets int(centre) - pixel inside the radius-R circle, zeros in the corners; the mask line `temp_map[np.where(mask)==0,:] = 0.`
+    is a no-op (a tuple compared with 0), so later instances overwrite earlier ones.
+    compute_mid_offsets (:88-103): inside the disc of the edge's source keypoint: target keypoint of the same instance - pixel."""
+    R = KP_RADIUS
+    b = np.asarray(bboxes, np.float32).reshape(-1, NUM_KPS, 2)
+    n = len(b)
+    gt = np.zeros((5 + 2 * NUM_KPS + 4 * len(EDGES), height, width), np.float64)
+    if n == 0:
+        return gt.astype(np.float32)
+    yy, xx = np.meshgrid(np.arange(height, dtype=np.int64), np.arange(width, dtype=np.int64), indexing="ij")
+    owner = np.full((NUM_KPS, height, width), -1, np.int64)
+    for i in range(NUM_KPS):
+        d = np.sqrt((b[:, i, 0].astype(np.float64)[:, None, None] - xx[None]) ** 2 + (b[:, i, 1].astype(np.float64)[:, None, None] - yy[None]) ** 2)
+        j = d.argmin(0)
+        inside = np.take_along_axis(d, j[None], 0)[0] <= R
+        owner[i] = np.where(inside, j, -1)
+        gt[i] = inside
+        for k in range(n):                                   # short offsets: window paste in instance order
+            cx, cy = int(b[k, i, 0]), int(b[k, i, 1])
+            y1, y2 = max(cy - R, 0), min(cy + R, height - 1) + 1
+            x1, x2 = max(cx - R, 0), min(cx + R, width - 1) + 1
+            if y2 <= y1 or x2 <= x1:
+                continue
+            ox = cx - xx[y1:y2, x1:x2]; oy = cy - yy[y1:y2, x1:x2]
+            circ = ox * ox + oy * oy <= R * R
+            gt[5 + 2 * i, y1:y2, x1:x2] = ox * circ
+            gt[5 + 2 * i + 1, y1:y2, x1:x2] = oy * circ
+    for m, (a, t) in enumerate(DIR_EDGES):
+        inside = owner[a] >= 0
+        jj = np.clip(owner[a], 0, n - 1)
+        gt[15 + 2 * m] = np.where(inside, b[jj, t, 0].astype(np.float64) - xx, 0.0)
+        gt[15 + 2 * m + 1] = np.where(inside, b[jj, t, 1].astype(np.float64) - yy, 0.0)
+    return gt.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Losses restated (forward): loss.py:6-49, seg_loss.py:8-97
+
+def detection_loss(prediction, groundtruth, kp_radius=KP_RADIUS):
+    """DetectionLossAll.forward (loss.py:40-49) -> (total, kp, short, mid) torch scalars."""
+    torch, F = _t()
+    pr_kp, pr_short, pr_mid = prediction
+    gt_kp, gt_short, gt_mid = groundtruth[:, :5], groundtruth[:, 5:15], groundtruth[:, 15:]
+    kp = F.binary_cross_entropy(pr_kp, gt_kp)                                                 # :12-14
+    m2 = gt_kp.repeat_interleave(2, dim=1)                                                   # :18-23
+    short = (torch.abs(pr_short - gt_short) / kp_radius * m2).sum() / (m2.sum() + 1e-10)    # :17,24-25
+    src = [e[0] for e in DIR_EDGES]
+    m4 = gt_kp[:, src].repeat_interleave(2, dim=1)                                           # :30-35
+    mid = (torch.abs(pr_mid - gt_mid) / kp_radius * m4).sum() / (m4.sum() + 1e-10)          # :29,36-37
+    return kp + short + 0.25 * mid, kp, short, mid
+
+
+def seg_loss(predictions, gt_masks, gt_boxes, height, width):
+    """SEG_loss.forward (seg_loss.py:31-97) -> torch scalar or None."""
+    import cv2
+    torch, F = _t()
+    f = np.float32
+
+    def jaccard(a, b):                                                                        # :14-29
+        area_a = (a[2] - a[0]) * (a[3] - a[1]); area_b = (b[2] - b[0]) * (b[3] - b[1])
+        ih = max(min(a[2], b[2]) - max(a[0], b[0]), f(0.)); iw = max(min(a[3], b[3]) - max(a[1], b[1]), f(0.))
+        inter = ih * iw
+        union = area_a + area_b - inter
+        return f(0.) if union <= 2 else np.divide(inter, union)
+
+    mask_patches, mask_dets = predictions
+    total, any_match = 0., False
+    for i in range(len(mask_patches)):
+        loss_batch, num_obj = 0., 0
+        for j in range(len(mask_patches[i])):
+            patch = mask_patches[i][j].detach().cpu().to(torch.float32)
+            pbox = np.asarray(mask_dets[i][j], np.float32)[:4]
+            for k in range(len(gt_boxes[i])):
+                if jaccard(pbox, np.asarray(gt_boxes[i][k], np.float32)) >= 0.5:
+                    y1 = np.maximum(0, np.int32(np.round(pbox[0]))); x1 = np.maximum(0, np.int32(np.round(pbox[1])))
+                    y2 = np.minimum(np.int32(np.round(pbox[2])), height - 1); x2 = np.minimum(np.int32(np.round(pbox[3])), width - 1)
+                    crop = np.asarray(gt_masks[i][k], np.float32)[y1:y2, x1:x2]
+                    h1, w1 = patch.shape
+                    crop = cv2.resize(crop, (w1, h1), interpolation=cv2.INTER_NEAREST)        # :76
+                    loss_batch = loss_batch + F.binary_cross_entropy(patch, torch.from_numpy(crop))
+                    num_obj += 1
+                    any_match = True
+        if num_obj:
+            total = total + loss_batch / num_obj
+    return total / len(mask_patches) if any_match else None
+
+
+# ---------------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY.md §8d) live in the product package (they are data generators, not the algorithm);
 # re-exported here because the tests and golden generator historically call them through the oracle.
 from kg_instance_segmentation_b200.synthetic import make_state_dict, planted_scene  # noqa: E402,F401

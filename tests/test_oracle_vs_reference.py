@@ -148,3 +148,48 @@ def test_preprocess_restatement_matches_reference_lines(reference):
     img_input = cv2.resize(image, (64, 48))
     ref = torch.FloatTensor(np.transpose(img_input.copy(), (2, 0, 1))).unsqueeze(0) / 255 - 0.5
     assert torch.equal(ref, O.preprocess_image(image, 48, 64))
+
+
+def _random_instances(rs, n, H, W):
+    bb = []
+    for _ in range(n):
+        x1 = rs.randint(0, W - 14); y1 = rs.randint(0, H - 14)
+        x2 = min(x1 + rs.randint(12, 31), W - 1); y2 = min(y1 + rs.randint(12, 31), H - 1)
+        bb.append([(x1, y1), (x2, y1), (x1, y2), (x2, y2), ((x1 + x2) / 2, (y1 + y2) / 2)])
+    return np.asarray(bb, np.float32).reshape(-1, 5, 2)
+
+
+def test_ground_truth_encoder_restatement_matches_reference(reference):
+    """oracle.encode_ground_truth against preprocessing.get_ground_truth + the concat of dataset_base.py:99-102 (bit-exact,
+    including overlapping instance windows and keypoints at the image border)."""
+    import preprocessing as P        # the reference's (conftest put /root/reference on sys.path)
+    rs = np.random.RandomState(0)
+    for trial in range(8):
+        H, W = (48, 64) if trial < 5 else (40, 40)
+        bb = _random_instances(rs, int(rs.randint(0, 8)), H, W)
+        kp, sh, mid = P.get_ground_truth(bb, H, W, 5)
+        ref = np.concatenate((kp, np.transpose(sh, (2, 0, 1)), np.transpose(mid, (2, 0, 1))), 0).astype(np.float32)
+        assert np.array_equal(ref, O.encode_ground_truth(bb, H, W)), trial
+
+
+def test_loss_restatements_match_reference_modules(reference):
+    """oracle.detection_loss / seg_loss against loss.DetectionLossAll and seg_loss.SEG_loss (bit-exact on CPU)."""
+    import warnings
+    import loss as RL
+    import seg_loss as RS
+    torch.manual_seed(0)
+    N, H, W = 2, 24, 32
+    pr = [torch.rand(N, 5, H, W), torch.randn(N, 10, H, W), torch.randn(N, 40, H, W)]
+    gt = torch.zeros(N, 55, H, W)
+    gt[:, :5] = (torch.rand(N, 5, H, W) > 0.8).float(); gt[:, 5:] = torch.randn(N, 50, H, W)
+    assert torch.equal(RL.DetectionLossAll(5)(pr, gt), O.detection_loss(pr, gt)[0])
+    rs = np.random.RandomState(0)
+    gt_masks = [rs.rand(3, H, W).round().astype(np.float32), rs.rand(2, H, W).round().astype(np.float32)]
+    gt_boxes = [np.array([[2, 3, 14, 20, 1], [10, 10, 22, 30, 1], [0, 0, 5, 5, 1]], np.float32), np.array([[4, 4, 20, 28, 1], [1, 1, 3, 3, 1]], np.float32)]
+    patches = [[torch.rand(12, 17) * 0.98 + 0.01, torch.rand(11, 19) * 0.98 + 0.01], [torch.rand(16, 24) * 0.98 + 0.01]]
+    dets = [[torch.Tensor([2.2, 3.1, 14.4, 20.3, 0.9]), torch.Tensor([10.6, 10.2, 21.7, 29.9, 0.8])], [torch.Tensor([4, 4, 20, 28, 0.7])]]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = RS.SEG_loss(H, W)([patches, dets], gt_masks, gt_boxes)
+    assert torch.equal(ref, O.seg_loss([patches, dets], gt_masks, gt_boxes, H, W))
+    assert O.seg_loss([[[]], [[]]], [gt_masks[0]], [gt_boxes[0]], H, W) is None

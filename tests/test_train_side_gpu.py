@@ -1,0 +1,123 @@
+"""GPU parity of the callers either side of the inference path that SURVEY.md 8f ranks "next": the ground-truth encoder
+(preprocessing.py:45-118) and the loss forward passes of the validation loop (loss.py, seg_loss.py; train.py:165-177)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _instances(rs, n, H, W, lo=12, hi=31):
+    bb = []
+    for _ in range(n):
+        x1 = rs.randint(0, W - lo - 2); y1 = rs.randint(0, H - lo - 2)
+        x2 = min(x1 + rs.randint(lo, hi), W - 1); y2 = min(y1 + rs.randint(lo, hi), H - 1)
+        bb.append([(x1, y1), (x2, y1), (x1, y2), (x2, y2), ((x1 + x2) / 2, (y1 + y2) / 2)])
+    return np.asarray(bb, np.float32).reshape(-1, 5, 2)
+
+
+def test_ground_truth_encoder_bit_exact():
+    """Batched device encoder against the oracle (itself pinned bit-exact against preprocessing.get_ground_truth): empty
+    images, overlapping windows, keypoints on the border, 4 scales like dataset_base.py:90-97."""
+    from kg_instance_segmentation_b200 import preprocessing
+    rs = np.random.RandomState(1)
+    for H, W in ((64, 96), (128, 128), (40, 40)):
+        boxes = [_instances(rs, n, H, W) for n in (0, 1, 5, 17)]
+        boxes[2][0, :, :] = [(0, 0), (W - 1, 0), (0, H - 1), (W - 1, H - 1), ((W - 1) / 2, (H - 1) / 2)]      # image-sized instance
+        gt = preprocessing.encode_ground_truth_batch(boxes, H, W).cpu().numpy()
+        for b, bb in enumerate(boxes):
+            assert np.array_equal(gt[b], O.encode_ground_truth(bb, H, W)), (H, W, b)
+    kp, sh, mid = preprocessing.get_ground_truth(boxes[1], 40, 40, 5)          # the reference's per-image return convention
+    ref = O.encode_ground_truth(boxes[1], 40, 40)
+    assert kp.shape == (5, 40, 40) and sh.shape == (40, 40, 10) and mid.shape == (40, 40, 40)
+    assert np.array_equal(kp, ref[:5]) and np.array_equal(sh.transpose(2, 0, 1), ref[5:15]) and np.array_equal(mid.transpose(2, 0, 1), ref[15:])
+
+
+def test_ground_truth_encoder_dense_1024():
+    """cfg-4 sized input: 500 instances on a 1024x1024 map in one launch."""
+    from kg_instance_segmentation_b200 import preprocessing
+    rs = np.random.RandomState(2)
+    bb = _instances(rs, 500, 1024, 1024, 16, 41)
+    gt = preprocessing.encode_ground_truth_batch([bb], 1024, 1024)[0].cpu().numpy()
+    assert np.array_equal(gt, O.encode_ground_truth(bb, 1024, 1024))
+
+
+def test_detection_loss_matches_oracle():
+    """DetectionLossAll.forward: fp32 torch reductions on the oracle side, fp64 accumulation here: rtol 2e-6."""
+    from kg_instance_segmentation_b200 import loss
+    torch.manual_seed(0)
+    for N, H, W in ((2, 64, 96), (1, 128, 128), (3, 16, 16)):
+        pr = [torch.rand(N, 5, H, W) * 0.98 + 0.01, torch.randn(N, 10, H, W) * 3, torch.randn(N, 40, H, W) * 20]
+        gt = torch.zeros(N, 55, H, W)
+        gt[:, :5] = (torch.rand(N, 5, H, W) > 0.9).float(); gt[:, 5:] = torch.randn(N, 50, H, W) * 5
+        crit = loss.DetectionLossAll(5)
+        got = crit([t.cuda() for t in pr], gt.cuda())
+        ref, kp, sh, mid = O.detection_loss(pr, gt)
+        assert got.shape == () and got.is_cuda
+        np.testing.assert_allclose(float(got), float(ref), rtol=2e-6)
+        np.testing.assert_allclose(crit.last_terms.cpu().numpy(), [float(kp), float(sh), float(mid)], rtol=2e-6)
+    # saturated predictions: the -100 clamp of F.binary_cross_entropy, and an all-zero target (denominator 1e-10)
+    pr = [torch.zeros(1, 5, 8, 8), torch.ones(1, 10, 8, 8), torch.ones(1, 40, 8, 8)]
+    gt = torch.zeros(1, 55, 8, 8); gt[0, 0, 0, 0] = 1.0
+    got = loss.DetectionLossAll(5)([t.cuda() for t in pr], gt.cuda())
+    np.testing.assert_allclose(float(got), float(O.detection_loss(pr, gt)[0]), rtol=2e-6)
+    gt.zero_()
+    got = loss.DetectionLossAll(5)([t.cuda() for t in pr], gt.cuda())
+    np.testing.assert_allclose(float(got), float(O.detection_loss(pr, gt)[0]), rtol=2e-6, atol=1e-12)
+
+
+def test_seg_loss_matches_oracle_on_forward_seg_output():
+    """SEG_loss.forward on the real forward_seg output (patches are windows of the packed atlas) and on loose tensors."""
+    from kg_instance_segmentation_b200 import KGnet, seg_loss
+    sd = O.make_state_dict(seed=0)
+    sd["seg_head.2.weight"] = sd["seg_head.2.weight"] * 0.05
+    m = KGnet.resnet50(pretrained=False, precision="exact")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    torch.manual_seed(3)
+    H = W = 96
+    x = torch.rand(2, 3, H, W) - 0.5
+    gt_boxes = [np.array([[4., 6., 50., 60., 1.], [40., 30., 90., 88., 1.]], np.float32), np.array([[10., 12., 70., 64., 1.]], np.float32)]
+    rs = np.random.RandomState(0)
+    gt_masks = [rs.rand(2, H, W).round().astype(np.float32), rs.rand(1, H, W).round().astype(np.float32)]
+    det_boxes = [np.array([[5., 7., 49., 61., 0.9], [42., 31., 88., 86., 0.8], [0., 0., 10., 10., 0.3]]), np.array([[11., 12., 69., 66., 0.7]])]
+    out = m.forward_dec(x.cuda())
+    preds = m.forward_seg(out[4], det_boxes)
+    got = seg_loss.SEG_loss(H, W)(preds, gt_masks, gt_boxes)
+    ref = O.seg_loss(preds, gt_masks, gt_boxes, H, W)
+    assert got is not None and ref is not None
+    np.testing.assert_allclose(float(got), float(ref), rtol=5e-6)
+    loose = [[[p.clone() for p in per] for per in preds[0]], preds[1]]        # plain list: patches are gathered into one buffer
+    np.testing.assert_allclose(float(seg_loss.SEG_loss(H, W)(loose, gt_masks, gt_boxes)), float(ref), rtol=5e-6)
+    far = [np.array([[60., 60., 90., 90., 1.]], np.float32), np.array([[80., 80., 95., 95., 1.]], np.float32)]
+    assert seg_loss.SEG_loss(H, W)(preds, [gt_masks[0][:1], gt_masks[1]], far) is None and O.seg_loss(preds, [gt_masks[0][:1], gt_masks[1]], far, H, W) is None
+
+
+def test_validation_step_flow():
+    """train.py:165-177 `validating` with the three imports swapped: forward(x, boxes) -> 4 x DetectionLossAll + SEG_loss."""
+    from kg_instance_segmentation_b200 import KGnet, loss, preprocessing, seg_loss
+    sd = O.make_state_dict(seed=0)
+    m = KGnet.resnet50(pretrained=False, precision="exact")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    H = W = 64
+    torch.manual_seed(5)
+    x = torch.rand(1, 3, H, W) - 0.5
+    rs = np.random.RandomState(4)
+    inst = _instances(rs, 2, H, W, 14, 30)
+    gts = [preprocessing.encode_ground_truth_batch([np.floor(inst / s)], H // s, W // s) for s in (1, 2, 4, 8)]
+    bboxes_c0 = [np.array([[b[0, 1], b[0, 0], b[3, 1], b[3, 0], 1.] for b in inst], np.float32)]
+    masks = [np.stack([np.pad(np.ones((int(b[3, 1] - b[0, 1]), int(b[3, 0] - b[0, 0])), np.float32),
+                              ((int(b[0, 1]), H - int(b[3, 1])), (int(b[0, 0]), W - int(b[3, 0])))) for b in inst])]
+    pr_c0, pr_c1, pr_c2, pr_c3, predictions = m(x.cuda(), bboxes_c0)
+    loss_dec, loss_seg = loss.DetectionLossAll(5), seg_loss.SEG_loss(H, W)
+    loss1 = loss_dec(pr_c0, gts[0]) + loss_dec(pr_c1, gts[1]) + loss_dec(pr_c2, gts[2]) + loss_dec(pr_c3, gts[3])
+    loss2 = loss_seg(predictions, masks, bboxes_c0)
+    total = float((loss1 + loss2).item())
+    ref_out = O.forward_dec(sd, x)
+    ref1 = sum(O.detection_loss(ref_out[s], torch.from_numpy(O.encode_ground_truth(np.floor(inst / sc), H // sc, W // sc))[None])[0]
+               for s, sc in enumerate((1, 2, 4, 8)))
+    ref2 = O.seg_loss(O.forward_seg(sd, ref_out[4], bboxes_c0), masks, bboxes_c0, H, W)
+    np.testing.assert_allclose(total, float(ref1 + ref2), rtol=2e-3)
