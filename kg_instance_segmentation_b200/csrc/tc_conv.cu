@@ -264,10 +264,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const bool valid = oy < p.H && ox < p.W;
       const long long pix = (long long)n * HW + (long long)oy * p.W + ox;
       const bool keep = valid && (p.mask == nullptr || p.mask[pix] != 0);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        if (((c0 >> cgran) & 1) != half) continue;
+      // this warp's 16-column chunks: c0 with ((c0 >> cgran) & 1) == half.  The residual of chunk i + 1 is requested before chunk i is
+      // processed: a lane-per-pixel 32-byte load per plane waits ~1 us on HBM, and with one chunk in flight per warp the residual
+      // stream of the wide-N 1x1 convs (conv3 / downsample of every bottleneck) was latency-bound at ~28 % of DRAM peak
+      auto next_chunk = [&](int c) { c += 16; while (c < p.BN && ((c >> cgran) & 1) != half) c += 16; return c; };
+      const bool has_res = p.res_hi != nullptr && valid;
+      uint4 rh_next[2], rl_next[2];
+      auto fetch_res = [&](int c) {
+        if (has_res && c < p.BN && n0 + c + 16 <= p.Cout) {
+          ld_global_nc_v8(p.res_hi + pix * p.Cout + n0 + c, rh_next[0], rh_next[1]);
+          ld_global_nc_v8(p.res_lo + pix * p.Cout + n0 + c, rl_next[0], rl_next[1]);
+        }
+      };
+      const int c_first = next_chunk(-16);
+      fetch_res(c_first);
+      for (int c0 = c_first; c0 < p.BN; c0 = next_chunk(c0)) {
         uint32_t raw[16];
         float v[16];
+        uint4 rhv[2] = {rh_next[0], rh_next[1]}, rlv[2] = {rl_next[0], rl_next[1]};
+        fetch_res(next_chunk(c0));
         tmem_ld16(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.KS * p.BN + c0), raw);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
@@ -285,10 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             v[j] = fmaf(v[j], p.inv_scale, b.x); v[j + 1] = fmaf(v[j + 1], p.inv_scale, b.y);
             v[j + 2] = fmaf(v[j + 2], p.inv_scale, b.z); v[j + 3] = fmaf(v[j + 3], p.inv_scale, b.w);
           }
-          if (p.res_hi != nullptr && valid) {
-            uint4 rhv[2], rlv[2];
-            ld_global_nc_v8(p.res_hi + pix * p.Cout + co0, rhv[0], rhv[1]);
-            ld_global_nc_v8(p.res_lo + pix * p.Cout + co0, rlv[0], rlv[1]);
+          if (has_res) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               const uint4 a = rhv[q], b = rlv[q];
@@ -312,16 +324,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           }
           if (p.out_hi != nullptr) {
             uint4 hi4[2], lo4[2];
-            __half2* hh = reinterpret_cast<__half2*>(hi4);
-            __half2* ll = reinterpret_cast<__half2*>(lo4);
+            uint32_t* hh = reinterpret_cast<uint32_t*>(hi4);
+            uint32_t* ll = reinterpret_cast<uint32_t*>(lo4);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float a = fminf(fmaxf(v[2 * e], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * e + 1], -65504.f), 65504.f);
-              const __half2 h = __floats2half2_rn(a, b);
-              const float2 hf = __half22float2(h);
-              hh[e] = h;
-              ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
-            }
+            for (int e = 0; e < 8; ++e) split_f16x2(v[2 * e], v[2 * e + 1], hh[e], ll[e]);
             if (p.o_tma) {
               // staging rows are 128 B (64 channels) with the 128-byte swizzle of the store's tensor map: 16-byte chunk j of
               // row r sits at chunk (j ^ (r & 7)); a 64-channel group is complete after four 16-channel pieces
@@ -545,15 +551,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_co
           const int co0 = n0 + c0;
           if (!valid || co0 >= p.Cout) continue;
           uint4 hi4[2];
-          __half2* hh = reinterpret_cast<__half2*>(hi4);
+          uint32_t* hh = reinterpret_cast<uint32_t*>(hi4);
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
-            float v0 = fmaf(__uint_as_float(raw[j]), p.inv_scale, b.x), v1 = fmaf(__uint_as_float(raw[j + 1]), p.inv_scale, b.y);
-            float v2 = fmaf(__uint_as_float(raw[j + 2]), p.inv_scale, b.z), v3 = fmaf(__uint_as_float(raw[j + 3]), p.inv_scale, b.w);
-            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-            hh[j / 2] = __floats2half2_rn(fminf(fmaxf(v0, -65504.f), 65504.f), fminf(fmaxf(v1, -65504.f), 65504.f));
-            hh[j / 2 + 1] = __floats2half2_rn(fminf(fmaxf(v2, -65504.f), 65504.f), fminf(fmaxf(v3, -65504.f), 65504.f));
+            const float v0 = fmaf(__uint_as_float(raw[j]), p.inv_scale, b.x), v1 = fmaf(__uint_as_float(raw[j + 1]), p.inv_scale, b.y);
+            const float v2 = fmaf(__uint_as_float(raw[j + 2]), p.inv_scale, b.z), v3 = fmaf(__uint_as_float(raw[j + 3]), p.inv_scale, b.w);
+            // ReLU + clamp to the finite fp16 range + convert: one F2FP per pair
+            hh[j / 2] = p.relu ? f16x2_relu_sat(v0, v1) : f16x2_sat(v0, v1);
+            hh[j / 2 + 1] = p.relu ? f16x2_relu_sat(v2, v3) : f16x2_sat(v2, v3);
           }
           st_global_v8(p.out_hi + pix * p.Cout + co0, hi4[0], hi4[1]);
         }

@@ -2,6 +2,7 @@
 // tcgen05.mma / commit / ld, UMMA shared-memory descriptors.  sm_100a only.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace kg {
@@ -146,6 +147,26 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint
 __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint4& a, uint4& b) {
   asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y),
                "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
+// Two fp32 -> packed fp16x2 (low half = a), round to nearest, SATURATED to the finite fp16 range: one F2FP.SATFINITE instruction
+// instead of two clamps per value and the convert (a value that would round to +-inf becomes +-65504, like the explicit clamp).
+__device__ __forceinline__ uint32_t f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// same with ReLU fused (F2FP.SATFINITE.RELU): max(x, 0) before the conversion
+__device__ __forceinline__ uint32_t f16x2_relu_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// split fp16 of a pair: hi = fp16(v), lo = fp16(v - hi)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = f16x2_sat(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = f16x2_sat(a - hf.x, b - hf.y);
 }
 
 // 8 consecutive fp32 columns of this warp's 32 TMEM lanes (no wait: pair with tmem_ld_wait)

@@ -280,6 +280,14 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
     const long long cs = (long long)p.H * p.W;
     uint32_t tile_it = 0;
     int off = 0;                                           // ring offset of logical buffer row 0
+    // register-shuffle epilogue (64-channel 3x3, whole-row tiles): this warp's 32 biases live in registers for the whole kernel
+    // (one shared-memory load per output value otherwise)
+    constexpr bool kRegEpi = OUTMODE == 1 && TAPS == 3 && O0 == 64 && NG == 1;
+    float r_bias[kRegEpi ? 32 : 1];
+    if constexpr (kRegEpi) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) r_bias[c] = s_bias[half * 32 + c];
+    }
     for (int work = blockIdx.x; work < p.num_work; work += gridDim.x) {
       const int n = work / p.rows_y, y0 = (work - n * p.rows_y) * p.BH;
       for (int tx = 0; tx < p.tiles_x; ++tx, ++tile_it) {
@@ -313,19 +321,16 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 uint4 h4, l4;
-                __half2* hh = reinterpret_cast<__half2*>(&h4);
-                __half2* ll = reinterpret_cast<__half2*>(&l4);
+                uint32_t* hh = reinterpret_cast<uint32_t*>(&h4);
+                uint32_t* ll = reinterpret_cast<uint32_t*>(&l4);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  float a = fmaf(v[8 * k + 2 * e], G.inv_scale, s_bias[cb + 8 * k + 2 * e]);
-                  float bq = fmaf(v[8 * k + 2 * e + 1], G.inv_scale, s_bias[cb + 8 * k + 2 * e + 1]);
+                  float a = fmaf(v[8 * k + 2 * e], G.inv_scale, r_bias[8 * k + 2 * e]);
+                  float bq = fmaf(v[8 * k + 2 * e + 1], G.inv_scale, r_bias[8 * k + 2 * e + 1]);
                   if (p.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
                   if (!keep) { a = 0.f; bq = 0.f; }
-                  a = fminf(fmaxf(a, -65504.f), 65504.f); bq = fminf(fmaxf(bq, -65504.f), 65504.f);
-                  const __half2 h = __floats2half2_rn(a, bq);
-                  const float2 hf = __half22float2(h);
-                  hh[e] = h;
-                  ll[e] = __floats2half2_rn(a - hf.x, bq - hf.y);
+                  if (p.out_lo != nullptr) split_f16x2(a, bq, hh[e], ll[e]);
+                  else hh[e] = f16x2_sat(a, bq);
                 }
                 if (srow >= 0) {                               // 128-byte swizzle of the store's tensor map: 16-byte piece j of row r at (j ^ (r & 7))
                   const uint32_t a0 = stage + (uint32_t)srow * 128u + ((((uint32_t)(half * 4 + k)) ^ ((uint32_t)srow & 7u)) << 4);
@@ -481,19 +486,15 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                   static_for<0, c_n / 8>([&](auto Cx) __attribute__((always_inline)) {
                     constexpr int c0 = decltype(Cx)::value * 8;
                     uint4 h4, l4;
-                    __half2* hh = reinterpret_cast<__half2*>(&h4);
-                    __half2* ll = reinterpret_cast<__half2*>(&l4);
+                    uint32_t* hh = reinterpret_cast<uint32_t*>(&h4);
+                    uint32_t* ll = reinterpret_cast<uint32_t*>(&l4);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                       float a = fmaf(v[c0 + 2 * e], G.inv_scale, s_bias[b0 + c_lo + c0 + 2 * e]);
                       float bq = fmaf(v[c0 + 2 * e + 1], G.inv_scale, s_bias[b0 + c_lo + c0 + 2 * e + 1]);
                       if (p.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
                       if (!keep) { a = 0.f; bq = 0.f; }
-                      a = fminf(fmaxf(a, -65504.f), 65504.f); bq = fminf(fmaxf(bq, -65504.f), 65504.f);
-                      const __half2 h = __floats2half2_rn(a, bq);
-                      const float2 hf = __half22float2(h);
-                      hh[e] = h;
-                      ll[e] = __floats2half2_rn(a - hf.x, bq - hf.y);
+                      split_f16x2(a, bq, hh[e], ll[e]);
                     }
                     *reinterpret_cast<uint4*>(p.out_hi + pix * no + c_lo + c0) = h4;
                     if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * no + c_lo + c0) = l4;
