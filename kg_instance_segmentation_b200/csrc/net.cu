@@ -595,6 +595,12 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
       }
       case OP_BILINEAR: {
         const Tensor& ti = p->tensors[op.in0]; const Tensor& to = p->tensors[op.out];
+        static const bool no2x = getenv("KG_NO_BILINEAR2X") != nullptr;
+        if (!no2x && to.H == 2 * ti.H && to.W == 2 * ti.W && to.C == ti.C) {          // the decoder's exact x2 steps (KGnet.py:288-297)
+          KG_TRY(launch_bilinear2x(P.hi(ti), P.lo(ti), P.hi(to), P.lo(to), p->N, ti.H, ti.W, ti.C, stream));
+          ++launches;
+          break;
+        }
         KG_TRY(launch_bilinear(P.hi(ti), P.lo(ti), ti.C, P.hi(to), P.lo(to), to.C, ti.C, p->d_resize_probs + op.prob_off, op.nprob,
                                op.max_pix, stream));
         ++launches;

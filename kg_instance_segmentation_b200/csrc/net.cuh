@@ -46,6 +46,7 @@ int launch_stem_conv(const float* x, const float* w, const float* bias, __half* 
                      int stride, cudaStream_t s);
 int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
                     const ResizeProb* probs, int nprob, int max_pix, cudaStream_t s);
+int launch_bilinear2x(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int N, int Hin, int Win, int C, cudaStream_t s);
 int launch_maxpool3x3s2(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int N, int Hin, int Win,
                         int C, cudaStream_t s);
 // NHWC split fp16 -> fp32 NCHW and back

@@ -284,6 +284,72 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict_
   if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + o) = l4;
 }
 
+// Exact x2 upsampling of a dense NHWC tensor (the four F.interpolate calls of the decoder, KGnet.py:288-297).  One thread owns one
+// INPUT pixel x 8 channels and produces its 2 x 2 output pixels from the 3 x 3 input neighbourhood: 9 loads per plane for 4 outputs
+// where the generic kernel issues 16, and the weights are the constants 0.25 / 0.75 (align_corners=False at scale 2: source
+// coordinate (o + 0.5) / 2 - 0.5, clamped at 0 like the generic kernel / ATen).  Same expression per output as bilinear_kernel.
+__global__ void __launch_bounds__(256) bilinear2x_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                                                         __half* __restrict__ out_hi, __half* __restrict__ out_lo, int Hin, int Win, int C,
+                                                         unsigned total) {
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int cg = C >> 3;
+  const int c = (int)(e % (unsigned)cg) * 8;
+  unsigned q = e / (unsigned)cg;
+  const int j = (int)(q % (unsigned)Win); q /= (unsigned)Win;
+  const int i = (int)(q % (unsigned)Hin);
+  const int n = (int)(q / (unsigned)Hin);
+  // neighbourhood rows / columns (i-1, i, i+1) clamped to the image: a clamped entry repeats the edge value, which is exactly what
+  // the generic kernel reads there (index clamp at the far edge, source coordinate clamp at 0 with weights (1, 0) at the near edge)
+  const int r[3] = {max(i - 1, 0), i, min(i + 1, Hin - 1)}, cc[3] = {max(j - 1, 0), j, min(j + 1, Win - 1)};
+  const long long img = (long long)n * Hin * Win;
+  float v[3][3][8];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) ld8_split(in_hi, in_lo, (img + (long long)r[a] * Win + cc[b]) * C + c, v[a][b]);
+  // output parity 0 blends (i-1, i) with (0.25, 0.75) -- (1, 0) at i == 0 --, parity 1 blends (i, i+1) with (0.75, 0.25)
+  const float wy[2][2] = {{i > 0 ? 0.25f : 1.f, i > 0 ? 0.75f : 0.f}, {0.75f, 0.25f}};
+  const float wx[2][2] = {{j > 0 ? 0.25f : 1.f, j > 0 ? 0.75f : 0.f}, {0.75f, 0.25f}};
+  const int Wout = 2 * Win;
+  const long long oimg = (long long)n * (2 * Hin) * Wout;
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      uint4 h4, l4;
+      __half2* hh = reinterpret_cast<__half2*>(&h4);
+      __half2* ll = reinterpret_cast<__half2*>(&l4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float o[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int ch = 2 * k + t;
+          const float val = wy[py][0] * (wx[px][0] * v[py][px][ch] + wx[px][1] * v[py][px + 1][ch]) +
+                            wy[py][1] * (wx[px][0] * v[py + 1][px][ch] + wx[px][1] * v[py + 1][px + 1][ch]);
+          o[t] = fminf(fmaxf(val, -65504.f), 65504.f);
+        }
+        const __half2 h = __floats2half2_rn(o[0], o[1]);
+        const float2 hf = __half22float2(h);
+        hh[k] = h;
+        ll[k] = __floats2half2_rn(o[0] - hf.x, o[1] - hf.y);
+      }
+      const long long op = (oimg + (long long)(2 * i + py) * Wout + (2 * j + px)) * C + c;
+      *reinterpret_cast<uint4*>(out_hi + op) = h4;
+      if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + op) = l4;
+    }
+}
+
+int launch_bilinear2x(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int N, int Hin, int Win, int C, cudaStream_t s) {
+  KG_REQUIRE((C & 7) == 0, "bilinear2x: channel count must be a multiple of 8 (C=%d)", C);
+  const long long total = (long long)N * Hin * Win * (C >> 3);
+  KG_REQUIRE(total < (1ll << 32), "bilinear2x: problem too large");
+  bilinear2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in_hi, in_lo, out_hi, out_lo, Hin, Win, C, (unsigned)total);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
 int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
                     const ResizeProb* probs, int nprob, int max_pix, cudaStream_t s) {
   if (nprob <= 0 || max_pix <= 0) return KG_OK;
