@@ -657,6 +657,19 @@ __device__ void boxes_from_skeletons(const double* __restrict__ skel, int nskel,
   if (tid == 0) *n_boxes = base;
 }
 
+// Spatial hash of the peaks of one list: cells of 8 x 8 pixels per keypoint type, chained through s_next.  Both neighbourhood
+// queries of the greedy loop are radius searches around a point -- partner within KP_RADIUS + 1 = 6 px of the proposal (:113-114),
+// skeleton keypoint of the seed's type within 10 px of the seed (:100) -- so they only have to visit 3 x 3 resp. 5 x 5 cells
+// instead of every peak of the list (the first version scanned all K peaks per seed and target: O(K^2) with three block-wide
+// barriers per scan, 30 ms for a 2 500-peak list).  With the scans gone the loop is latency-bound and runs on ONE warp
+// (__syncwarp instead of __syncthreads).
+constexpr int GH_CELL_SHIFT = 3;
+
+__device__ __forceinline__ unsigned group_hash(int id, int cy, int cx, unsigned mask) {
+  const unsigned key = ((unsigned)id * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cx * 83492791u);
+  return (key ^ (key >> 15)) & mask;
+}
+
 __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __restrict__ peak_conf_g,
                                                     int* __restrict__ peak_key_g, int* __restrict__ peak_count_g,
                                                     double* __restrict__ skel_g, int* __restrict__ skel_xy_g,
@@ -668,10 +681,10 @@ __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __re
   int* s_key = reinterpret_cast<int*>(s_conf + P);
   unsigned short* s_px = reinterpret_cast<unsigned short*>(s_key + P);
   unsigned short* s_py = s_px + P;
-  unsigned char* s_id = reinterpret_cast<unsigned char*>(s_py + P);
-  unsigned char* s_alive = s_id + P;
-  __shared__ double s_best[8];
-  __shared__ int s_bestj[8];
+  unsigned short* s_next = s_py + P;                   // hash chain: next peak of the same bucket (0xffff = end)
+  unsigned short* s_head = s_next + P;                 // [2 * P] bucket heads
+  unsigned char* s_id = reinterpret_cast<unsigned char*>(s_head + 2 * P);
+  unsigned char* s_state = s_id + P;                   // bit0: alive (not yet consumed), bit1: keypoint of an existing skeleton
 
   const int list = blockIdx.x;
   const int n = list / gp.n_scales, s = list - n * gp.n_scales;
@@ -703,91 +716,130 @@ __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __re
       __syncthreads();
     }
   }
+  unsigned hmask = 1;
+  while ((int)hmask < 2 * max(K, 1)) hmask <<= 1;
+  hmask = min(hmask, (unsigned)(2 * P)) - 1u;
+  for (int e = tid; e <= (int)hmask; e += blockDim.x) s_head[e] = 0xffffu;
   for (int e = tid; e < K; e += blockDim.x) {
     const int key = s_key[e];
     const int id = key / hw, rem = key - id * hw;
     const int y = rem / W;
     s_id[e] = (unsigned char)id; s_py[e] = (unsigned short)y; s_px[e] = (unsigned short)(rem - y * W);
-    s_alive[e] = 1;
+    s_state[e] = 1;
     gconf[e] = s_conf[e];     // export the sorted order (doubles as the caller-visible peak list)
     gkey[e] = key;
   }
   __syncthreads();
-
-  // ---- greedy grouping (postprocessing.py:98-124) ----
-  double* skel = skel_g + (size_t)list * P * 15;
-  int* skel_xy = skel_xy_g + (size_t)list * P * 5;
-  const float* mid = gp.mid[s] + (size_t)n * 40 * hw;
-  int nskel = 0;
-  for (int i = 0; i < K; ++i) {
-    if (!s_alive[i]) continue;                       // consumed earlier (keypoints.pop(matches[0][0]))
-    const int sid = s_id[i], sx = s_px[i], sy = s_py[i];
-    int hit = 0;
-    for (int q = tid; q < nskel; q += blockDim.x) {  // any(norm(kp.xy - s[kp.id,:2]) <= 10) (:100); exact in integers
-      const unsigned xy = (unsigned)skel_xy[q * 5 + sid];
-      const int ddx = sx - (int)(xy & 0xffffu), ddy = sy - (int)(xy >> 16);
-      hit |= (ddx * ddx + ddy * ddy <= 100);
+  // chains are built by one thread per BUCKET-independent insertion order: a serial pass keeps them deterministic (rank-ascending
+  // from the head is not required: every query applies its own explicit tie-break)
+  if (tid == 0) {
+    for (int e = K - 1; e >= 0; --e) {
+      const unsigned b = group_hash(s_id[e], s_py[e] >> GH_CELL_SHIFT, s_px[e] >> GH_CELL_SHIFT, hmask);
+      s_next[e] = s_head[b];
+      s_head[b] = (unsigned short)e;
     }
-    if (__syncthreads_or(hit)) continue;
-    double sk[15];
-#pragma unroll
-    for (int k = 0; k < 15; ++k) sk[k] = 0.;
-    int sk_xy[5] = {0, 0, 0, 0, 0};
-    sk[3 * sid] = (double)sx; sk[3 * sid + 1] = (double)sy; sk[3 * sid + 2] = s_conf[i];
-    sk_xy[sid] = sx | (sy << 16);
-    for (int kk = 0; kk < 4; ++kk) {
-      const int t = kk + (kk >= sid ? 1 : 0);         // BFS order over K5: ascending target id (:103)
-      const int m = c_mid_index[sid][t];
-      const double prx = (double)sx + (double)__ldg(mid + (size_t)(2 * m) * hw + sy * W + sx);       // (:110-112)
-      const double pry = (double)sy + (double)__ldg(mid + (size_t)(2 * m + 1) * hw + sy * W + sx);
-      double best = DBL_MAX;
-      int bestj = INT_MAX;
-      for (int j = i + 1 + tid; j < K; j += blockDim.x) {
-        if (s_alive[j] && s_id[j] == t) {
-          const double ddx = prx - (double)s_px[j], ddy = pry - (double)s_py[j];
-          const double d = sqrt(ddx * ddx + ddy * ddy);                                             // np.linalg.norm (:114,117)
-          if (d <= 6.0 && d < best) { best = d; bestj = j; }                                        // KP_RADIUS + 1
+  }
+  __syncthreads();
+
+  // ---- greedy grouping (postprocessing.py:98-124), one warp ----
+  double* skel = skel_g + (size_t)list * P * 15;
+  int* skel_xy = skel_xy_g + (size_t)list * P * 5;      // kept for the debug export of integer skeletons
+  const float* mid = gp.mid[s] + (size_t)n * 40 * hw;
+  __shared__ int s_nskel;
+  if (warp == 0) {
+    int nskel = 0;
+    int n_missing[5] = {0, 0, 0, 0, 0};                  // skeletons without a keypoint of type t: their s[t] sits at (0, 0) (:100 quirk)
+    for (int i = 0; i < K; ++i) {
+      if (!(s_state[i] & 1)) continue;                   // consumed earlier (keypoints.pop(matches[0][0]))
+      const int sid = s_id[i], sx = s_px[i], sy = s_py[i];
+      // -- any(norm(kp.xy - s[kp.id,:2]) <= 10) over the existing skeletons: exact in integers --
+      int hit = (n_missing[sid] > 0 && sx * sx + sy * sy <= 100) ? 1 : 0;
+      if (lane < 25) {
+        const int cy = (sy >> GH_CELL_SHIFT) + lane / 5 - 2, cx = (sx >> GH_CELL_SHIFT) + lane % 5 - 2;
+        if (cy >= 0 && cx >= 0 && (cy << GH_CELL_SHIFT) < H && (cx << GH_CELL_SHIFT) < W) {
+          for (unsigned j = s_head[group_hash(sid, cy, cx, hmask)]; j != 0xffffu; j = s_next[j]) {
+            if ((s_state[j] & 2) && s_id[j] == sid) {
+              const int ddx = sx - (int)s_px[j], ddy = sy - (int)s_py[j];
+              hit |= (ddx * ddx + ddy * ddy <= 100);
+            }
+          }
         }
       }
+      if (__any_sync(0xffffffffu, hit)) { if (lane == 0) s_state[i] = 0; __syncwarp(); continue; }   // keypoints.pop(0) happened (:99)
+      // -- the four partner searches (targets in ascending id, BFS order over K5): 4 x 9 (target, cell) tasks over the lanes --
+      double best[2] = {DBL_MAX, DBL_MAX};
+      int bestj[2] = {INT_MAX, INT_MAX};
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
-        if (ob < best || (ob == best && oj < bestj)) { best = ob; bestj = oj; }
+      for (int round = 0; round < 2; ++round) {
+        const int task = round * 32 + lane;                // task = kk * 9 + cell
+        if (task < 36) {
+          const int kk = task / 9, cell = task - kk * 9;
+          const int t = kk + (kk >= sid ? 1 : 0);
+          const int m = c_mid_index[sid][t];
+          const double prx = (double)sx + (double)__ldg(mid + (size_t)(2 * m) * hw + sy * W + sx);       // (:110-112)
+          const double pry = (double)sy + (double)__ldg(mid + (size_t)(2 * m + 1) * hw + sy * W + sx);
+          // candidates lie within 6 px of the proposal: cells floor(pr / 8) - 1 .. + 1 cover them
+          const double fcx = floor(prx * 0.125), fcy = floor(pry * 0.125);
+          if (fcx >= -1. && fcy >= -1. && fcx <= 8192. && fcy <= 8192.) {
+            const int cy = (int)fcy + cell / 3 - 1, cx = (int)fcx + cell % 3 - 1;
+            if (cy >= 0 && cx >= 0 && (cy << GH_CELL_SHIFT) < H && (cx << GH_CELL_SHIFT) < W) {
+              for (unsigned j = s_head[group_hash(t, cy, cx, hmask)]; j != 0xffffu; j = s_next[j]) {
+                if ((int)j > i && (s_state[j] & 1) && s_id[j] == t && (s_py[j] >> GH_CELL_SHIFT) == cy && (s_px[j] >> GH_CELL_SHIFT) == cx) {
+                  const double ddx = prx - (double)s_px[j], ddy = pry - (double)s_py[j];
+                  const double d = sqrt(ddx * ddx + ddy * ddy);                                       // np.linalg.norm (:114,117)
+                  if (d <= 6.0 && (d < best[round] || (d == best[round] && (int)j < bestj[round]))) { best[round] = d; bestj[round] = (int)j; }
+                }
+              }
+            }
+          }
+        }
       }
-      if (lane == 0) { s_best[warp] = best; s_bestj[warp] = bestj; }
-      __syncthreads();
-      best = s_best[0]; bestj = s_bestj[0];
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-        const double ob = s_best[w];
-        const int oj = s_bestj[w];
-        if (ob < best || (ob == best && oj < bestj)) { best = ob; bestj = oj; }
-      }
-      if (bestj != INT_MAX) {                                                                       // stable sort by distance -> first minimum
-        sk[3 * t] = (double)s_px[bestj]; sk[3 * t + 1] = (double)s_py[bestj]; sk[3 * t + 2] = s_conf[bestj];
-        sk_xy[t] = (int)s_px[bestj] | ((int)s_py[bestj] << 16);
-        if (tid == 0) s_alive[bestj] = 0;                                                           // keypoints.pop(matches[0][0]) (:120)
-      }
-      __syncthreads();
-    }
-    if (tid < 15) {
-      double v = 0.;
+      // reduce per target: tasks of target kk are lanes 9 kk .. 9 kk + 8 of the flattened 36 -> gather with shuffles
+      double sk[15];
 #pragma unroll
-      for (int k = 0; k < 15; ++k) if (k == tid) v = sk[k];
-      skel[(size_t)nskel * 15 + tid] = v;
-    }
-    if (tid >= 32 && tid < 37) {
-      int v = 0;
+      for (int k = 0; k < 15; ++k) sk[k] = 0.;
+      int sk_xy[5] = {0, 0, 0, 0, 0};
+      sk[3 * sid] = (double)sx; sk[3 * sid + 1] = (double)sy; sk[3 * sid + 2] = s_conf[i];
+      sk_xy[sid] = sx | (sy << 16);
 #pragma unroll
-      for (int k = 0; k < 5; ++k) if (k == tid - 32) v = sk_xy[k];
-      skel_xy[nskel * 5 + (tid - 32)] = v;
+      for (int kk = 0; kk < 4; ++kk) {
+        const int t = kk + (kk >= sid ? 1 : 0);
+        double b = DBL_MAX; int bj = INT_MAX;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          const int task = kk * 9 + c;
+          const double ob = __shfl_sync(0xffffffffu, best[task >> 5], task & 31);
+          const int oj = __shfl_sync(0xffffffffu, bestj[task >> 5], task & 31);
+          if (ob < b || (ob == b && oj < bj)) { b = ob; bj = oj; }
+        }
+        if (bj != INT_MAX) {                                                                             // stable sort by distance -> first minimum
+          sk[3 * t] = (double)s_px[bj]; sk[3 * t + 1] = (double)s_py[bj]; sk[3 * t + 2] = s_conf[bj];
+          sk_xy[t] = (int)s_px[bj] | ((int)s_py[bj] << 16);
+          if (lane == 0) s_state[bj] = 2;                                                                // popped (:120), now a skeleton keypoint
+        } else {
+          ++n_missing[t];
+        }
+      }
+      if (lane == 0) s_state[i] = 2;
+      if (lane < 15) {
+        double v = 0.;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) if (k == lane) v = sk[k];
+        skel[(size_t)nskel * 15 + lane] = v;
+      }
+      if (lane >= 16 && lane < 21) {
+        int v = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) if (k == lane - 16) v = sk_xy[k];
+        skel_xy[nskel * 5 + (lane - 16)] = v;
+      }
+      ++nskel;
+      __syncwarp();
     }
-    ++nskel;
-    __syncthreads();                                  // skel_xy visible to the next seed test
+    if (lane == 0) { skel_count_g[list] = nskel; s_nskel = nskel; }
   }
-  if (tid == 0) skel_count_g[list] = nskel;
   __syncthreads();
-  boxes_from_skeletons(skel, nskel, (double)gp.box_scale[s], true, sbox_g + (size_t)list * P * 5, sbox_count_g + list,
+  boxes_from_skeletons(skel, s_nskel, (double)gp.box_scale[s], true, sbox_g + (size_t)list * P * 5, sbox_count_g + list,
                        skel_keep_g ? skel_keep_g + (size_t)list * P : nullptr);
 }
 
@@ -1053,7 +1105,7 @@ size_t decode_workspace_bytes(const kg_decode_config* cfg, const kg_decode_scale
   return carve(*cfg, sc, nullptr).total;
 }
 
-static size_t group_smem(int P) { return (size_t)P * 18; }
+static size_t group_smem(int P) { return (size_t)P * 24 + 16; }
 static size_t nms_smem(int B) { return (size_t)B * 13; }
 
 int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const kg_decode_outputs* out, void* workspace,
