@@ -748,12 +748,24 @@ __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __re
   __shared__ int s_nskel;
   if (warp == 0) {
     int nskel = 0;
-    int n_missing[5] = {0, 0, 0, 0, 0};                  // skeletons without a keypoint of type t: their s[t] sits at (0, 0) (:100 quirk)
+    int n_missing = 0;                                   // lane t: skeletons without a keypoint of type t -- their s[t] sits at (0, 0) (:100 quirk)
+    // The seed's four mid offsets (8 floats, scattered over 8 channel planes) are on the critical path of the sequential loop:
+    // they are fetched four ranks AHEAD, one value per lane (lane = 8 * (peak - base) + 2 * kk + component), and handed out by
+    // shuffle when their peak becomes the seed.
+    auto fetch_mid = [&](int base) -> float {
+      const int pk = base + (lane >> 3);
+      if (pk >= K) return 0.f;
+      const int id = s_id[pk], kk = (lane >> 1) & 3, t = kk + (kk >= id ? 1 : 0);
+      const int m = c_mid_index[id][t];
+      return __ldg(mid + (size_t)(2 * m + (lane & 1)) * hw + (int)s_py[pk] * W + (int)s_px[pk]);          // (:110-112)
+    };
+    float mid_cur = fetch_mid(0), mid_next = fetch_mid(4);
     for (int i = 0; i < K; ++i) {
+      if (i > 0 && (i & 3) == 0) { mid_cur = mid_next; mid_next = fetch_mid(i + 4); }
       if (!(s_state[i] & 1)) continue;                   // consumed earlier (keypoints.pop(matches[0][0]))
       const int sid = s_id[i], sx = s_px[i], sy = s_py[i];
       // -- any(norm(kp.xy - s[kp.id,:2]) <= 10) over the existing skeletons: exact in integers --
-      int hit = (n_missing[sid] > 0 && sx * sx + sy * sy <= 100) ? 1 : 0;
+      int hit = (__shfl_sync(0xffffffffu, n_missing, sid) > 0 && sx * sx + sy * sy <= 100) ? 1 : 0;
       if (lane < 25) {
         const int cy = (sy >> GH_CELL_SHIFT) + lane / 5 - 2, cx = (sx >> GH_CELL_SHIFT) + lane % 5 - 2;
         if (cy >= 0 && cx >= 0 && (cy << GH_CELL_SHIFT) < H && (cx << GH_CELL_SHIFT) < W) {
@@ -772,12 +784,13 @@ __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __re
 #pragma unroll
       for (int round = 0; round < 2; ++round) {
         const int task = round * 32 + lane;                // task = kk * 9 + cell
+        const int kk_s = min(task / 9, 3);
+        const float mox = __shfl_sync(0xffffffffu, mid_cur, 8 * (i & 3) + 2 * kk_s);
+        const float moy = __shfl_sync(0xffffffffu, mid_cur, 8 * (i & 3) + 2 * kk_s + 1);
         if (task < 36) {
           const int kk = task / 9, cell = task - kk * 9;
           const int t = kk + (kk >= sid ? 1 : 0);
-          const int m = c_mid_index[sid][t];
-          const double prx = (double)sx + (double)__ldg(mid + (size_t)(2 * m) * hw + sy * W + sx);       // (:110-112)
-          const double pry = (double)sy + (double)__ldg(mid + (size_t)(2 * m + 1) * hw + sy * W + sx);
+          const double prx = (double)sx + (double)mox, pry = (double)sy + (double)moy;
           // candidates lie within 6 px of the proposal: cells floor(pr / 8) - 1 .. + 1 cover them
           const double fcx = floor(prx * 0.125), fcy = floor(pry * 0.125);
           if (fcx >= -1. && fcy >= -1. && fcx <= 8192. && fcy <= 8192.) {
@@ -794,13 +807,10 @@ __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __re
           }
         }
       }
-      // reduce per target: tasks of target kk are lanes 9 kk .. 9 kk + 8 of the flattened 36 -> gather with shuffles
-      double sk[15];
-#pragma unroll
-      for (int k = 0; k < 15; ++k) sk[k] = 0.;
-      int sk_xy[5] = {0, 0, 0, 0, 0};
-      sk[3 * sid] = (double)sx; sk[3 * sid + 1] = (double)sy; sk[3 * sid + 2] = s_conf[i];
-      sk_xy[sid] = sx | (sy << 16);
+      // reduce per target: tasks of target kk are lanes 9 kk .. 9 kk + 8 of the flattened 36 -> gather with shuffles.
+      // Lane t (0..4) owns keypoint type t of the new skeleton: (x, y, conf), all zero when missing.
+      double kx = 0., ky = 0., kc = 0.;
+      if (lane == sid) { kx = (double)sx; ky = (double)sy; kc = s_conf[i]; }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const int t = kk + (kk >= sid ? 1 : 0);
@@ -813,25 +823,17 @@ __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __re
           if (ob < b || (ob == b && oj < bj)) { b = ob; bj = oj; }
         }
         if (bj != INT_MAX) {                                                                             // stable sort by distance -> first minimum
-          sk[3 * t] = (double)s_px[bj]; sk[3 * t + 1] = (double)s_py[bj]; sk[3 * t + 2] = s_conf[bj];
-          sk_xy[t] = (int)s_px[bj] | ((int)s_py[bj] << 16);
+          if (lane == t) { kx = (double)s_px[bj]; ky = (double)s_py[bj]; kc = s_conf[bj]; }
           if (lane == 0) s_state[bj] = 2;                                                                // popped (:120), now a skeleton keypoint
-        } else {
-          ++n_missing[t];
+        } else if (lane == t) {
+          ++n_missing;
         }
       }
       if (lane == 0) s_state[i] = 2;
-      if (lane < 15) {
-        double v = 0.;
-#pragma unroll
-        for (int k = 0; k < 15; ++k) if (k == lane) v = sk[k];
-        skel[(size_t)nskel * 15 + lane] = v;
-      }
-      if (lane >= 16 && lane < 21) {
-        int v = 0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) if (k == lane - 16) v = sk_xy[k];
-        skel_xy[nskel * 5 + (lane - 16)] = v;
+      if (lane < 5) {
+        double* dst = skel + (size_t)nskel * 15 + 3 * lane;
+        dst[0] = kx; dst[1] = ky; dst[2] = kc;
+        skel_xy[nskel * 5 + lane] = (int)kx | ((int)ky << 16);
       }
       ++nskel;
       __syncwarp();
