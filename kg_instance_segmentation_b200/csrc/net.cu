@@ -56,8 +56,7 @@ struct Op {
   int tc_passes = 0;                             // 0: CUDA-core kernel; 1 or 3: tensor-core kernel passes
   int tc_index = -1;                             // index into Plan::tc_ops (OP_CONV) / Plan::shift_ops (OP_HEADS2)
   bool use_shift = false;                        // OP_CONV through the row-GEMM + shift-add kernel (64-channel 3x3 convs)
-  int head_scale = -1;                           // OP_HEADS2: the three second-layer head convs of this scale
-  int n_shift = 1;                               // OP_HEADS2: consecutive Plan::shift_ops launches (1 fused, or 3: kp+short, mid[0:20], mid[20:40])
+  int head_scale = -1;                           // OP_HEADS2: the three second-layer head convs of this scale in one launch
 };
 
 struct Plan {
@@ -490,37 +489,16 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
     for (auto& op : p->ops) {
       if (op.type == OP_HEADS2) {
         const Tensor& t0 = p->tensors[op.in0];
-        auto base = [&]() {
-          TcShiftOp t{};
-          t.N = p->N; t.H = t0.H; t.W = t0.W; t.R = 7; t.S = 7; t.pad = 3; t.Cin = op.C0; t.in_hi = P.hi(t0); t.in_C = t0.C;
-          return t;
-        };
-        auto head = [&](int h) -> const ConvW& { return net->convs.at(std::string(kHeadNames[h]) + "_c" + std::to_string(op.head_scale) + ".2"); };
-        auto group = [&](TcShiftGroup& g, int h, int ch_off, int n_ch) {
-          const ConvW& w = head(h);
-          g.h_w = w.h_w.data(); g.d_bias = w.d_b + ch_off; g.n_out = n_ch; g.in_coff = h * op.C0; g.sigmoid = h == 0;
-          g.w_stride = w.Cout; g.w_off = ch_off; g.out_ch_total = w.Cout; g.out_ch_off = ch_off;
-        };
-        if (getenv("KG_TC_DEBUG")) fprintf(stderr, "[op %d heads_l2_c%d] ", (int)(&op - p->ops.data()), op.head_scale);
-        op.tc_index = (int)p->shift_ops.size();
-        static const bool split = !(getenv("KG_HEADS_SPLIT") && getenv("KG_HEADS_SPLIT")[0] == '0');
-        if (split) {
-          // three launches whose accumulators fit TMEM twice (176 / 168 / 168 columns): the shift-add epilogue of tile i overlaps
-          // the MMAs of tile i + 1.  The fused launch (464 columns, one accumulator set) ran at 35 % tensor pipe with the tensor
-          // core idle during the epilogue.
-          TcShiftOp a = base(); a.n_groups = 2; group(a.g[0], 0, 0, kHeadOut[0]); group(a.g[1], 1, 0, kHeadOut[1]);
-          KG_TRY(tc_shift_prepare(&a)); p->shift_ops.push_back(a);
-          for (int half = 0; half < 2; ++half) {
-            TcShiftOp b = base(); b.n_groups = 1; group(b.g[0], 2, half * 20, 20);
-            KG_TRY(tc_shift_prepare(&b)); p->shift_ops.push_back(b);
-          }
-          op.n_shift = 3;
-        } else {
-          TcShiftOp t = base(); t.n_groups = 3;
-          for (int h = 0; h < 3; ++h) group(t.g[h], h, 0, kHeadOut[h]);
-          KG_TRY(tc_shift_prepare(&t)); p->shift_ops.push_back(t);
-          op.n_shift = 1;
+        TcShiftOp t{};
+        t.N = p->N; t.H = t0.H; t.W = t0.W; t.R = 7; t.S = 7; t.pad = 3; t.Cin = op.C0; t.in_hi = P.hi(t0); t.in_C = t0.C; t.n_groups = 3;
+        for (int h = 0; h < 3; ++h) {
+          const ConvW& w = net->convs.at(std::string(kHeadNames[h]) + "_c" + std::to_string(op.head_scale) + ".2");
+          t.g[h].h_w = w.h_w.data(); t.g[h].d_bias = w.d_b; t.g[h].n_out = w.Cout; t.g[h].in_coff = h * op.C0; t.g[h].sigmoid = h == 0;
         }
+        if (getenv("KG_TC_DEBUG")) fprintf(stderr, "[op %d heads_l2_c%d] ", (int)(&op - p->ops.data()), op.head_scale);
+        KG_TRY(tc_shift_prepare(&t));
+        op.tc_index = (int)p->shift_ops.size();
+        p->shift_ops.push_back(t);
         continue;
       }
       if (op.type != OP_CONV || op.tc_passes == 0) continue;
@@ -611,16 +589,8 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
       }
       case OP_HEADS2: {
         float* outs[3] = {ext[3 * op.head_scale], ext[3 * op.head_scale + 1], ext[3 * op.head_scale + 2]};
-        if (op.n_shift == 3) {
-          float* mid_only[1] = {outs[2]};
-          KG_TRY(tc_shift_launch(&p->shift_ops[op.tc_index], outs, stream));              // kp, short
-          KG_TRY(tc_shift_launch(&p->shift_ops[op.tc_index + 1], mid_only, stream));      // mid channels 0..19
-          KG_TRY(tc_shift_launch(&p->shift_ops[op.tc_index + 2], mid_only, stream));      // mid channels 20..39
-          launches += 3;
-        } else {
-          KG_TRY(tc_shift_launch(&p->shift_ops[op.tc_index], outs, stream));
-          ++launches;
-        }
+        KG_TRY(tc_shift_launch(&p->shift_ops[op.tc_index], outs, stream));
+        ++launches;
         break;
       }
       case OP_BILINEAR: {
@@ -1191,41 +1161,18 @@ static int heads_l2_nchw(const float* d_x, int N, int Cin, int H, int W, const f
   do {
     if (cudaMalloc(&xh, in_e * 2)) { rc = KG_ERR_CUDA; break; }
     if ((rc = launch_import_nchw(d_x, xh, nullptr, N, H * W, 3 * Cin, stream)) != KG_OK) break;
-    ConvW* ws[3] = {nullptr, nullptr, nullptr};
+    TcShiftOp t{};
+    t.N = N; t.H = H; t.W = W; t.R = 7; t.S = 7; t.pad = 3; t.Cin = Cin; t.in_hi = xh; t.in_C = 3 * Cin; t.n_groups = 3;
     for (int h = 0; h < 3; ++h) {
       const std::string nme = "h" + std::to_string(h);
       if ((rc = set_conv(&tmp, nme.c_str(), h_w[h], kHeadOut[h], Cin, 7, 7, h_bias[h], nullptr, nullptr, nullptr, nullptr, 0.0)) != KG_OK) break;
-      ws[h] = &tmp.convs.at(nme);
-      if ((rc = upload_conv(*ws[h])) != KG_OK) break;
+      ConvW& w = tmp.convs.at(nme);
+      if ((rc = upload_conv(w)) != KG_OK) break;
+      t.g[h].h_w = w.h_w.data(); t.g[h].d_bias = w.d_b; t.g[h].n_out = kHeadOut[h]; t.g[h].in_coff = h * Cin; t.g[h].sigmoid = h == 0;
     }
     if (rc != KG_OK) break;
-    auto base = [&]() {
-      TcShiftOp t{};
-      t.N = N; t.H = H; t.W = W; t.R = 7; t.S = 7; t.pad = 3; t.Cin = Cin; t.in_hi = xh; t.in_C = 3 * Cin;
-      return t;
-    };
-    auto group = [&](TcShiftGroup& g, int h, int ch_off, int n_ch) {
-      g.h_w = ws[h]->h_w.data(); g.d_bias = ws[h]->d_b + ch_off; g.n_out = n_ch; g.in_coff = h * Cin; g.sigmoid = h == 0;
-      g.w_stride = kHeadOut[h]; g.w_off = ch_off; g.out_ch_total = kHeadOut[h]; g.out_ch_off = ch_off;
-    };
-    const bool split = !(getenv("KG_HEADS_SPLIT") && getenv("KG_HEADS_SPLIT")[0] == '0');
-    if (split) {       // the production configuration: kp + short, then the two halves of the mid-offset conv
-      TcShiftOp a = base(); a.n_groups = 2; group(a.g[0], 0, 0, kHeadOut[0]); group(a.g[1], 1, 0, kHeadOut[1]);
-      if ((rc = tc_shift_prepare(&a)) != KG_OK) break;
-      if ((rc = tc_shift_launch(&a, d_y, stream)) != KG_OK) break;
-      float* mid_only[1] = {d_y[2]};
-      for (int half = 0; half < 2 && rc == KG_OK; ++half) {
-        TcShiftOp b = base(); b.n_groups = 1; group(b.g[0], 2, half * 20, 20);
-        if ((rc = tc_shift_prepare(&b)) != KG_OK) break;
-        rc = tc_shift_launch(&b, mid_only, stream);
-      }
-      if (rc != KG_OK) break;
-    } else {
-      TcShiftOp t = base(); t.n_groups = 3;
-      for (int h = 0; h < 3; ++h) group(t.g[h], h, 0, kHeadOut[h]);
-      if ((rc = tc_shift_prepare(&t)) != KG_OK) break;
-      if ((rc = tc_shift_launch(&t, d_y, stream)) != KG_OK) break;
-    }
+    if ((rc = tc_shift_prepare(&t)) != KG_OK) break;
+    if ((rc = tc_shift_launch(&t, d_y, stream)) != KG_OK) break;
     if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("kg_heads_l2_nchw: %s", cudaGetErrorString(cudaGetLastError())); rc = KG_ERR_CUDA; }
   } while (0);
   if (rc == KG_ERR_CUDA && cudaPeekAtLastError() != cudaSuccess) set_error("kg_heads_l2_nchw: CUDA error %s", cudaGetErrorString(cudaGetLastError()));

@@ -39,7 +39,7 @@ constexpr int SH_A_TILE = 128 * SH_BK * 2;   // 16 KiB
 constexpr int SH_MAX_N = 192;                // rows of one weight slab (N of one MMA)
 constexpr int SH_MAX_SMEM = 227 * 1024;
 
-struct ShGroup { const float* bias; float* out32; int in_coff; float inv_scale; int sigmoid; int out_ch_total, out_ch_off; };
+struct ShGroup { const float* bias; float* out32; int in_coff; float inv_scale; int sigmoid; };
 struct ShParams {
   CUtensorMap a_map[2];                       // activation planes (hi, lo)
   CUtensorMap w_map[SH_MAX_UNITS][2];         // weight slab of each unit, planes (hi, lo)
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               const ShGroup& G = p.grp[g];
               if (inside) {
                 if (OUTMODE == 0) {
-                  float* dst = G.out32 + (((long long)n * G.out_ch_total + G.out_ch_off + c_lo) * p.H + y) * p.W + x;
+                  float* dst = G.out32 + (((long long)n * no + c_lo) * p.H + y) * p.W + x;
 #pragma unroll
                   for (int e = 0; e < c_n; ++e) {
                     float o = fmaf(v[e], G.inv_scale, s_bias[b0 + c_lo + e]);
@@ -526,19 +526,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // the instantiated configurations
-using HeadsCfg = ShCfg<5, 10, 40, 7>;   // KGnet's second-layer heads: kp 5 (sigmoid), short offsets 10, mid offsets 40; 7x7 (464 TMEM columns: one accumulator set)
-// The same three convs as THREE launches whose accumulators fit TMEM twice (epilogue of tile i overlaps the MMAs of tile i + 1):
-using HeadsACfg = ShCfg<5, 10, 0, 7>;   // kp + short offsets: 176 columns
-using HeadsBCfg = ShCfg<20, 0, 0, 7>;   // one half of the 40 mid-offset channels: 168 columns
+using HeadsCfg = ShCfg<5, 10, 40, 7>;   // KGnet's second-layer heads: kp 5 (sigmoid), short offsets 10, mid offsets 40; 7x7
 using C64Cfg = ShCfg<64, 0, 0, 3>;      // one 3x3 conv with 64 output channels (c0_conv.2, c1/c2_up_conv, layer1 conv2, mask branch)
 using C1Cfg = ShCfg<1, 0, 0, 3>;        // seg_head.2: 3x3, one output channel
-enum ShKernel { SHK_NONE = -1, SHK_HEADS = 0, SHK_C64, SHK_C1, SHK_HEADS_A, SHK_HEADS_B };
+enum ShKernel { SHK_NONE = -1, SHK_HEADS = 0, SHK_C64, SHK_C1 };
 
 static ShKernel pick_kernel(int R, int S, int n_groups, const int* n_out, bool nhwc_out) {
   if (R != S) return SHK_NONE;
   if (S == 7 && n_groups == 3 && n_out[0] == 5 && n_out[1] == 10 && n_out[2] == 40 && !nhwc_out) return SHK_HEADS;
-  if (S == 7 && n_groups == 2 && n_out[0] == 5 && n_out[1] == 10 && !nhwc_out) return SHK_HEADS_A;
-  if (S == 7 && n_groups == 1 && n_out[0] == 20 && !nhwc_out) return SHK_HEADS_B;
   if (S == 3 && n_groups == 1 && n_out[0] == 64 && nhwc_out) return SHK_C64;
   if (S == 3 && n_groups == 1 && n_out[0] == 1 && !nhwc_out) return SHK_C1;
   return SHK_NONE;
@@ -566,9 +561,8 @@ static int shift_pack_t(const TcShiftOp* op, TcShiftPacked* out) {
   for (int g = 0; g < Cfg::NG; ++g) {
     const TcShiftGroup& G = op->g[g];
     KG_REQUIRE(G.h_w && G.n_out == Cfg::n_out(g), "tc_shift_pack: conv %d: null weights or unexpected Cout", g);
-    const int wst = G.w_stride > 0 ? G.w_stride : G.n_out;       // channels per (tap, cin) row of h_w; this launch takes [w_off, w_off + n_out)
     float mx = 0.f;
-    const size_t nw = (size_t)R * S * op->Cin * wst;               // the scale is a property of the WHOLE conv: all slices share it
+    const size_t nw = (size_t)R * S * op->Cin * G.n_out;
     for (size_t i = 0; i < nw; ++i) mx = fmaxf(mx, fabsf(G.h_w[i]));
     int e = 0;
     if (mx > 0.f && std::isfinite(mx)) { int ex; frexpf(mx, &ex); e = 10 - ex; }
@@ -579,7 +573,7 @@ static int shift_pack_t(const TcShiftOp* op, TcShiftPacked* out) {
       for (int t = 0; t < S; ++t)
         for (int ci = 0; ci < op->Cin; ++ci)
           for (int co = 0; co < G.n_out; ++co) {
-            const float v = G.h_w[(((size_t)r * S + t) * op->Cin + ci) * wst + G.w_off + co] * scale;
+            const float v = G.h_w[(((size_t)r * S + t) * op->Cin + ci) * G.n_out + co] * scale;
             const size_t o = ((size_t)r * rows + Cfg::col0(g) + t * Cfg::stride(g) + co) * op->Cin + ci;
             const __half h = __float2half_rn(v);
             hi[o] = h;
@@ -625,7 +619,6 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
     KG_REQUIRE(G.d_bias && G.n_out == Cfg::n_out(g), "tc_shift_prepare: conv %d: null bias or unexpected Cout", g);
     ShGroup& D = p.grp[g];
     D.bias = G.d_bias; D.in_coff = G.in_coff; D.sigmoid = G.sigmoid ? 1 : 0; D.inv_scale = op->packed.inv_scale[g];
-    D.out_ch_total = G.out_ch_total > 0 ? G.out_ch_total : G.n_out; D.out_ch_off = G.out_ch_off;
   }
   for (int pl = 0; pl < NPA; ++pl) {
     const __half* base = pl == 0 ? op->in_hi : op->in_lo;
@@ -702,8 +695,6 @@ int tc_shift_pack(const TcShiftOp* op, TcShiftPacked* out) {
   KG_REQUIRE(op && out, "tc_shift_pack: null argument");
   switch (kernel_of(op)) {
     case SHK_HEADS: return shift_pack_t<HeadsCfg>(op, out);
-    case SHK_HEADS_A: return shift_pack_t<HeadsACfg>(op, out);
-    case SHK_HEADS_B: return shift_pack_t<HeadsBCfg>(op, out);
     case SHK_C64: return shift_pack_t<C64Cfg>(op, out);
     case SHK_C1: return shift_pack_t<C1Cfg>(op, out);
     default: set_error("tc_shift_pack: unsupported shape"); return KG_ERR_INVALID;
@@ -715,13 +706,13 @@ int tc_shift_prepare(TcShiftOp* op) {
   KG_REQUIRE(op->passes >= 1 && op->passes <= 3, "tc_shift_prepare: passes=%d", op->passes);
   const ShKernel k = kernel_of(op);
   KG_REQUIRE(k != SHK_NONE, "tc_shift_prepare: unsupported shape");
-  KG_REQUIRE((k != SHK_HEADS && k != SHK_HEADS_A && k != SHK_HEADS_B) || op->passes == 1, "tc_shift_prepare: the head kernels are single-pass only");
+  KG_REQUIRE(k != SHK_HEADS || op->passes == 1, "tc_shift_prepare: the fused head kernel is single-pass only");
   EncodeTiledFn encode = (EncodeTiledFn)tc_encode_tiled_fn();
   KG_REQUIRE(encode != nullptr, "tc_shift_prepare: cuTensorMapEncodeTiled unavailable");
   static bool attr_set = false;
   if (!attr_set) {
 #define KG_SH_ATTR(...) KG_CUDA_CHECK(cudaFuncSetAttribute(tc_shift_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_MAX_SMEM))
-    KG_SH_ATTR(5, 10, 40, 7, 1, 0, false); KG_SH_ATTR(5, 10, 0, 7, 1, 0, false); KG_SH_ATTR(20, 0, 0, 7, 1, 0, false);
+    KG_SH_ATTR(5, 10, 40, 7, 1, 0, false);
     KG_SH_ATTR(64, 0, 0, 3, 1, 1, false); KG_SH_ATTR(64, 0, 0, 3, 2, 1, false); KG_SH_ATTR(64, 0, 0, 3, 3, 1, false);
     KG_SH_ATTR(64, 0, 0, 3, 1, 1, true); KG_SH_ATTR(64, 0, 0, 3, 2, 1, true); KG_SH_ATTR(64, 0, 0, 3, 3, 1, true);
     KG_SH_ATTR(1, 0, 0, 3, 1, 0, false); KG_SH_ATTR(1, 0, 0, 3, 3, 0, false);
@@ -731,8 +722,6 @@ int tc_shift_prepare(TcShiftOp* op) {
   }
   switch (k) {
     case SHK_HEADS: return shift_prepare_t<HeadsCfg>(op, encode);
-    case SHK_HEADS_A: return shift_prepare_t<HeadsACfg>(op, encode);
-    case SHK_HEADS_B: return shift_prepare_t<HeadsBCfg>(op, encode);
     case SHK_C64: return shift_prepare_t<C64Cfg>(op, encode);
     default: return shift_prepare_t<C1Cfg>(op, encode);
   }
@@ -752,8 +741,6 @@ int tc_shift_launch(const TcShiftOp* op, float* const* out32, cudaStream_t strea
 #define KG_SH_LAUNCH(...) tc_shift_kernel<__VA_ARGS__><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p)
   switch (kernel_of(op)) {
     case SHK_HEADS: KG_SH_LAUNCH(5, 10, 40, 7, 1, 0, false); break;
-    case SHK_HEADS_A: KG_SH_LAUNCH(5, 10, 0, 7, 1, 0, false); break;
-    case SHK_HEADS_B: KG_SH_LAUNCH(20, 0, 0, 7, 1, 0, false); break;
     case SHK_C64:
       if (op->wres) { if (op->passes == 3) KG_SH_LAUNCH(64, 0, 0, 3, 3, 1, true); else if (op->passes == 2) KG_SH_LAUNCH(64, 0, 0, 3, 2, 1, true); else KG_SH_LAUNCH(64, 0, 0, 3, 1, 1, true); }
       else { if (op->passes == 3) KG_SH_LAUNCH(64, 0, 0, 3, 3, 1, false); else if (op->passes == 2) KG_SH_LAUNCH(64, 0, 0, 3, 2, 1, false); else KG_SH_LAUNCH(64, 0, 0, 3, 1, 1, false); }

@@ -20,10 +20,6 @@ struct TcShiftGroup {
   const float* d_bias = nullptr;  // device, [n_out]
   int n_out = 0, in_coff = 0;
   bool sigmoid = false;
-  // a launch may compute a SLICE [w_off, w_off + n_out) of a conv's output channels: h_w then has w_stride (>= n_out) channels
-  // per (tap, cin) row, and the fp32 NCHW output tensor has out_ch_total channels of which this launch writes those from out_ch_off
-  int w_stride = 0, w_off = 0;        // 0 = the conv has exactly n_out channels
-  int out_ch_total = 0, out_ch_off = 0;
 };
 
 // Packed device weights of one launch configuration (fp16 hi / lo planes, [R][rows][Cin]) + the per-conv 1/scale.
