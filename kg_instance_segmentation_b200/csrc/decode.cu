@@ -778,55 +778,49 @@ __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __re
         }
       }
       if (__any_sync(0xffffffffu, hit)) { if (lane == 0) s_state[i] = 0; __syncwarp(); continue; }   // keypoints.pop(0) happened (:99)
-      // -- the four partner searches (targets in ascending id, BFS order over K5): 4 x 9 (target, cell) tasks over the lanes --
-      double best[2] = {DBL_MAX, DBL_MAX};
-      int bestj[2] = {INT_MAX, INT_MAX};
-#pragma unroll
-      for (int round = 0; round < 2; ++round) {
-        const int task = round * 32 + lane;                // task = kk * 9 + cell
-        const int kk_s = min(task / 9, 3);
-        const float mox = __shfl_sync(0xffffffffu, mid_cur, 8 * (i & 3) + 2 * kk_s);
-        const float moy = __shfl_sync(0xffffffffu, mid_cur, 8 * (i & 3) + 2 * kk_s + 1);
-        if (task < 36) {
-          const int kk = task / 9, cell = task - kk * 9;
-          const int t = kk + (kk >= sid ? 1 : 0);
-          const double prx = (double)sx + (double)mox, pry = (double)sy + (double)moy;
-          // candidates lie within 6 px of the proposal: cells floor(pr / 8) - 1 .. + 1 cover them
-          const double fcx = floor(prx * 0.125), fcy = floor(pry * 0.125);
-          if (fcx >= -1. && fcy >= -1. && fcx <= 8192. && fcy <= 8192.) {
+      // -- the four partner searches (targets in ascending id, BFS order over K5): lane = 8 * kk + c handles target kk, cell c of the
+      //    3 x 3 neighbourhood of the proposal (lane c == 0 also takes the ninth cell); an 8-lane butterfly picks the nearest --
+      const int kk = lane >> 3, tt = kk + (kk >= sid ? 1 : 0);
+      const float mox = __shfl_sync(0xffffffffu, mid_cur, 8 * (i & 3) + 2 * kk);
+      const float moy = __shfl_sync(0xffffffffu, mid_cur, 8 * (i & 3) + 2 * kk + 1);
+      const double prx = (double)sx + (double)mox, pry = (double)sy + (double)moy;
+      double best = DBL_MAX;
+      int bestj = INT_MAX;
+      {
+        // candidates lie within 6 px of the proposal: cells floor(pr / 8) - 1 .. + 1 cover them
+        const double fcx = floor(prx * 0.125), fcy = floor(pry * 0.125);
+        if (fcx >= -1. && fcy >= -1. && fcx <= 8192. && fcy <= 8192.) {
+          const int ncell = (lane & 7) == 0 ? 2 : 1;
+          for (int q = 0; q < ncell; ++q) {
+            const int cell = q == 0 ? (lane & 7) : 8;
             const int cy = (int)fcy + cell / 3 - 1, cx = (int)fcx + cell % 3 - 1;
             if (cy >= 0 && cx >= 0 && (cy << GH_CELL_SHIFT) < H && (cx << GH_CELL_SHIFT) < W) {
-              for (unsigned j = s_head[group_hash(t, cy, cx, hmask)]; j != 0xffffu; j = s_next[j]) {
-                if ((int)j > i && (s_state[j] & 1) && s_id[j] == t && (s_py[j] >> GH_CELL_SHIFT) == cy && (s_px[j] >> GH_CELL_SHIFT) == cx) {
+              for (unsigned j = s_head[group_hash(tt, cy, cx, hmask)]; j != 0xffffu; j = s_next[j]) {
+                if ((int)j > i && (s_state[j] & 1) && s_id[j] == tt && (s_py[j] >> GH_CELL_SHIFT) == cy && (s_px[j] >> GH_CELL_SHIFT) == cx) {
                   const double ddx = prx - (double)s_px[j], ddy = pry - (double)s_py[j];
                   const double d = sqrt(ddx * ddx + ddy * ddy);                                       // np.linalg.norm (:114,117)
-                  if (d <= 6.0 && (d < best[round] || (d == best[round] && (int)j < bestj[round]))) { best[round] = d; bestj[round] = (int)j; }
+                  if (d <= 6.0 && (d < best || (d == best && (int)j < bestj))) { best = d; bestj = (int)j; }
                 }
               }
             }
           }
         }
       }
-      // reduce per target: tasks of target kk are lanes 9 kk .. 9 kk + 8 of the flattened 36 -> gather with shuffles.
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {                      // min over the 8 lanes of the target: distance, then rank (stable sort -> first minimum)
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+        if (ob < best || (ob == best && oj < bestj)) { best = ob; bestj = oj; }
+      }
       // Lane t (0..4) owns keypoint type t of the new skeleton: (x, y, conf), all zero when missing.
       double kx = 0., ky = 0., kc = 0.;
       if (lane == sid) { kx = (double)sx; ky = (double)sy; kc = s_conf[i]; }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int t = kk + (kk >= sid ? 1 : 0);
-        double b = DBL_MAX; int bj = INT_MAX;
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-          const int task = kk * 9 + c;
-          const double ob = __shfl_sync(0xffffffffu, best[task >> 5], task & 31);
-          const int oj = __shfl_sync(0xffffffffu, bestj[task >> 5], task & 31);
-          if (ob < b || (ob == b && oj < bj)) { b = ob; bj = oj; }
-        }
-        if (bj != INT_MAX) {                                                                             // stable sort by distance -> first minimum
-          if (lane == t) { kx = (double)s_px[bj]; ky = (double)s_py[bj]; kc = s_conf[bj]; }
-          if (lane == 0) s_state[bj] = 2;                                                                // popped (:120), now a skeleton keypoint
-        } else if (lane == t) {
-          ++n_missing;
+      {
+        const int my_kk = lane - (lane > sid ? 1 : 0);        // lane t != sid <-> target index kk(t)
+        const int bj = __shfl_sync(0xffffffffu, bestj, 8 * (my_kk & 3));
+        if (lane < 5 && lane != sid) {
+          if (bj != INT_MAX) { kx = (double)s_px[bj]; ky = (double)s_py[bj]; kc = s_conf[bj]; s_state[bj] = 2; }   // popped (:120), now a skeleton keypoint
+          else ++n_missing;
         }
       }
       if (lane == 0) s_state[i] = 2;
@@ -846,13 +840,16 @@ __global__ void __launch_bounds__(256) group_kernel(GroupParams gp, double* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int NMS_MASK_CAP = 2048;     // lists up to this length use the all-pairs bit-matrix path (512 KiB of workspace per image)
+
 // K4: per image: gather_skeleton (postprocessing.py:255-261: scale 0..3 concatenated) and
 // non_maximum_suppression_numpy (nms.py:4-53).  argsort ties: (conf, index) ascending.
 __global__ void __launch_bounds__(256) nms_kernel(const double* __restrict__ sbox_g, const int* __restrict__ sbox_count_g,
                                                   int n_lists, int list_cap, int max_boxes, double nms_thresh,
                                                   double* __restrict__ boxes_g, int* __restrict__ box_count_g,
                                                   double* __restrict__ dets_g, int* __restrict__ det_count_g,
-                                                  int* __restrict__ status, double* __restrict__ packed_g, int packed_k) {
+                                                  int* __restrict__ status, double* __restrict__ packed_g, int packed_k,
+                                                  unsigned* __restrict__ mask_g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_conf = reinterpret_cast<double*>(smem_raw);
   int* s_idx = reinterpret_cast<int*>(s_conf + max_boxes);
@@ -897,6 +894,60 @@ __global__ void __launch_bounds__(256) nms_kernel(const double* __restrict__ sbo
     }
   }
   int nkeep = 0;
+  if (mask_g != nullptr && B > 64 && B <= NMS_MASK_CAP) {
+    // Dense lists: the suppression relation of ALL pairs first (bit b of row a: IoU(a, b) > thresh, b after a in the sorted order;
+    // same fp64 expression as below, every pair independent), then one warp walks the sorted list with the removed-set in
+    // registers.  The greedy loop below spends a block-wide scan + barrier per KEPT box: 0.7 ms for a 700-box image.
+    const int words = (B + 31) >> 5;
+    unsigned* mask = mask_g + (size_t)n * NMS_MASK_CAP * (NMS_MASK_CAP / 32);
+    for (int e = tid; e < B * words; e += blockDim.x) {
+      const int a = e / words, w = e - a * words;
+      unsigned bits = 0u;
+      if (w * 32 + 31 > a) {
+        const double* ca = boxes + (size_t)s_idx[a] * 5;
+        const double cy1 = ca[0], cx1 = ca[1], cy2 = ca[2], cx2 = ca[3];
+        const double carea = (cx2 - cx1) * (cy2 - cy1);
+        for (int k = 0; k < 32; ++k) {
+          const int b = w * 32 + k;
+          if (b <= a || b >= B) continue;
+          const double* o = boxes + (size_t)s_idx[b] * 5;
+          const double yy1 = fmax(o[0], cy1), xx1 = fmax(o[1], cx1), yy2 = fmin(o[2], cy2), xx2 = fmin(o[3], cx2);
+          const double iw = fmax(0., xx2 - xx1), ih = fmax(0., yy2 - yy1);
+          const double inter = iw * ih;
+          const double oarea = (o[3] - o[1]) * (o[2] - o[0]);
+          const double iou = inter / ((oarea - inter) + carea);
+          if (!(iou <= nms_thresh)) bits |= 1u << k;
+        }
+      }
+      mask[(size_t)a * words + w] = bits;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      unsigned removed[NMS_MASK_CAP / 1024];               // lane l owns words l, l + 32, ...
+#pragma unroll
+      for (int q = 0; q < NMS_MASK_CAP / 1024; ++q) removed[q] = 0u;
+      for (int a = 0; a < B; ++a) {
+        const int w = a >> 5;
+        unsigned mine = 0u;
+#pragma unroll
+        for (int q = 0; q < NMS_MASK_CAP / 1024; ++q) if (q == (w >> 5)) mine = removed[q];
+        const unsigned word = __shfl_sync(0xffffffffu, mine, w & 31);
+        if ((word >> (a & 31)) & 1u) continue;
+        if (tid < 5) dets[(size_t)nkeep * 5 + tid] = boxes[(size_t)s_idx[a] * 5 + tid];
+        ++nkeep;
+#pragma unroll
+        for (int q = 0; q < NMS_MASK_CAP / 1024; ++q) {
+          const int ww = q * 32 + tid;
+          if (ww < words) removed[q] |= mask[(size_t)a * words + ww];
+        }
+      }
+    }
+    nkeep = __shfl_sync(0xffffffffu, nkeep, 0);            // (warp 0 only has the count)
+    __shared__ int s_nkeep;
+    if (tid == 0) s_nkeep = nkeep;
+    __syncthreads();
+    nkeep = s_nkeep;
+  } else
   for (int a = 0; a < B; ++a) {
     if (s_supp[a]) continue;
     const int c = s_idx[a];
@@ -1053,6 +1104,7 @@ struct DecodeWorkspace {
   double* sbox; int* sbox_count;
   double* boxes; int* box_count;
   double* dets; int* det_count;
+  unsigned* nms_mask;                      // [N, NMS_MASK_CAP, NMS_MASK_CAP / 32] suppression bit matrix of the dense-list NMS path
   char* zero_begin; size_t zero_bytes;     // region cleared at the start of every call
   size_t total;
 };
@@ -1081,6 +1133,7 @@ static DecodeWorkspace carve(const kg_decode_config& cfg, const kg_decode_scale*
   w.box_count = a.take<int>(cfg.N);
   w.dets = a.take<double>((size_t)cfg.N * cfg.max_boxes * 5);
   w.det_count = a.take<int>(cfg.N);
+  w.nms_mask = a.take<unsigned>((size_t)cfg.N * NMS_MASK_CAP * (NMS_MASK_CAP / 32));
   w.total = align_up(a.off, 256);
   return w;
 }
@@ -1180,7 +1233,7 @@ int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const 
                                                              out->d_box_count ? out->d_box_count : w.box_count,
                                                              out->d_dets ? out->d_dets : w.dets,
                                                              out->d_det_count ? out->d_det_count : w.det_count, out->d_status,
-                                                             out->d_det_packed, out->det_packed_k);
+                                                             out->d_det_packed, out->det_packed_k, w.nms_mask);
   }
   launches += 2;
   if (out->d_peak_count != nullptr) {
@@ -1252,9 +1305,13 @@ int nms_host(const double* h_boxes, int n, double nms_thresh, double* h_out, int
   KG_CUDA_CHECK(cudaMemcpyAsync(in.p, h_boxes, sizeof(double) * 5 * n, cudaMemcpyHostToDevice, st.s));
   int* d_ints = ints.as<int>();
   if (cap <= 8192) {
+    DevBuf maskb;                                        // dense lists take the bit-matrix path, like kg_decode
+    if (n <= NMS_MASK_CAP) KG_CUDA_CHECK(cudaMalloc(&maskb.p, (size_t)NMS_MASK_CAP * (NMS_MASK_CAP / 32) * sizeof(unsigned)));
     KG_CUDA_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem(8192)));
     nms_kernel<<<1, 256, nms_smem(cap), st.s>>>(in.as<double>(), d_ints, 1, cap, cap, nms_thresh, boxes.as<double>(), d_ints + 1,
-                                                dets.as<double>(), d_ints + 2, d_ints + 3, nullptr, 0);
+                                                dets.as<double>(), d_ints + 2, d_ints + 3, nullptr, 0, maskb.as<unsigned>());
+    KG_CUDA_CHECK(cudaGetLastError());
+    KG_CUDA_CHECK(cudaStreamSynchronize(st.s));          // maskb is released at the end of this scope
   } else {
     KG_CUDA_CHECK(cudaMalloc(&scratch.p, (size_t)cap * 13));
     nms_big_kernel<<<1, 1024, 0, st.s>>>(in.as<double>(), n, cap, nms_thresh, scratch.as<unsigned char>(), dets.as<double>(), d_ints + 2);

@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
             const bool staged = p.stage_bytes != 0;
             auto emit32 = [&](const float* v, long long pix, int srow) __attribute__((always_inline)) {
               if (p.noemit) return;
-              const bool keep = p.mask == nullptr || p.mask[pix] != 0;
+              const bool has_mask = p.mask != nullptr;                    // uniform: the forward_seg atlases only
+              const bool keep = !has_mask || p.mask[pix] != 0;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 uint4 h4, l4;
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                   float a = fmaf(v[8 * k + 2 * e], G.inv_scale, r_bias[8 * k + 2 * e]);
                   float bq = fmaf(v[8 * k + 2 * e + 1], G.inv_scale, r_bias[8 * k + 2 * e + 1]);
                   if (p.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
-                  if (!keep) { a = 0.f; bq = 0.f; }
+                  if (has_mask) { a = keep ? a : 0.f; bq = keep ? bq : 0.f; }
                   if (p.out_lo != nullptr) split_f16x2(a, bq, hh[e], ll[e]);
                   else hh[e] = f16x2_sat(a, bq);
                 }
@@ -352,13 +353,17 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               tmem_ld8_nowait(lane_addr + (uint32_t)(128 + cb + 8 * c), reinterpret_cast<uint32_t*>(&z2[8 * c]));
             }
             tmem_ld_wait();
+            // edge exchange with the neighbouring quadrants: 128-bit shared stores / loads (one lane is active, the instruction count
+            // is what matters)
             if (lane == 31) {
+              float4* d4 = reinterpret_cast<float4*>(e0 + quad * 64 + cb);
 #pragma unroll
-              for (int c = 0; c < 32; ++c) e0[quad * 64 + cb + c] = z0[c];
+              for (int c = 0; c < 8; ++c) d4[c] = make_float4(z0[4 * c], z0[4 * c + 1], z0[4 * c + 2], z0[4 * c + 3]);
             }
             if (lane == 0) {
+              float4* d4 = reinterpret_cast<float4*>(e2 + quad * 64 + cb);
 #pragma unroll
-              for (int c = 0; c < 32; ++c) e2[quad * 64 + cb + c] = z2[c];
+              for (int c = 0; c < 8; ++c) d4[c] = make_float4(z2[4 * c], z2[4 * c + 1], z2[4 * c + 2], z2[4 * c + 3]);
             }
             epi_bar();                                       // (also orders the staging writes below after bulk_wait_read0 above)
             if (lane == 0 && !first && quad == 0) {          // the previous tile's last pixel is complete now
@@ -374,12 +379,21 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               z2[c] = __shfl_down_sync(0xffffffffu, z2[c], 1);     // right neighbour's tap 2
             }
             if (lane == 0) {
+              const float4* s4 = reinterpret_cast<const float4*>(quad == 0 ? e0_prev + 3 * 64 + cb : e0 + (quad - 1) * 64 + cb);
+              const bool zero = quad == 0 && first;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) z0[c] = quad == 0 ? (first ? 0.f : e0_prev[3 * 64 + cb + c]) : e0[(quad - 1) * 64 + cb + c];
+              for (int c = 0; c < 8; ++c) {
+                const float4 f = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : s4[c];
+                z0[4 * c] = f.x; z0[4 * c + 1] = f.y; z0[4 * c + 2] = f.z; z0[4 * c + 3] = f.w;
+              }
             }
             if (lane == 31) {
+              const float4* s4 = reinterpret_cast<const float4*>(e2 + (quad == 3 ? 0 : quad + 1) * 64 + cb);
 #pragma unroll
-              for (int c = 0; c < 32; ++c) z2[c] = quad == 3 ? 0.f : e2[(quad + 1) * 64 + cb + c];
+              for (int c = 0; c < 8; ++c) {
+                const float4 f = quad == 3 ? make_float4(0.f, 0.f, 0.f, 0.f) : s4[c];
+                z2[4 * c] = f.x; z2[4 * c + 1] = f.y; z2[4 * c + 2] = f.z; z2[4 * c + 3] = f.w;
+              }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
