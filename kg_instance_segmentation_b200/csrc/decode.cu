@@ -900,17 +900,21 @@ __global__ void __launch_bounds__(256) nms_kernel(const double* __restrict__ sbo
     // registers.  The greedy loop below spends a block-wide scan + barrier per KEPT box: 0.7 ms for a 700-box image.
     const int words = (B + 31) >> 5;
     unsigned* mask = mask_g + (size_t)n * NMS_MASK_CAP * (NMS_MASK_CAP / 32);
+    // the sorted boxes are staged in shared memory: the pair loop is latency-bound on the box loads otherwise
+    double* s_box = reinterpret_cast<double*>(smem_raw + (((size_t)max_boxes * 13 + 15) & ~(size_t)15));
+    for (int e = tid; e < B * 4; e += blockDim.x) s_box[e] = boxes[(size_t)s_idx[e >> 2] * 5 + (e & 3)];
+    __syncthreads();
     for (int e = tid; e < B * words; e += blockDim.x) {
       const int a = e / words, w = e - a * words;
       unsigned bits = 0u;
       if (w * 32 + 31 > a) {
-        const double* ca = boxes + (size_t)s_idx[a] * 5;
+        const double* ca = s_box + 4 * a;
         const double cy1 = ca[0], cx1 = ca[1], cy2 = ca[2], cx2 = ca[3];
         const double carea = (cx2 - cx1) * (cy2 - cy1);
         for (int k = 0; k < 32; ++k) {
           const int b = w * 32 + k;
           if (b <= a || b >= B) continue;
-          const double* o = boxes + (size_t)s_idx[b] * 5;
+          const double* o = s_box + 4 * b;
           const double yy1 = fmax(o[0], cy1), xx1 = fmax(o[1], cx1), yy2 = fmin(o[2], cy2), xx2 = fmin(o[3], cx2);
           const double iw = fmax(0., xx2 - xx1), ih = fmax(0., yy2 - yy1);
           const double inter = iw * ih;
@@ -1161,7 +1165,7 @@ size_t decode_workspace_bytes(const kg_decode_config* cfg, const kg_decode_scale
 }
 
 static size_t group_smem(int P) { return (size_t)P * 24 + 16; }
-static size_t nms_smem(int B) { return (size_t)B * 13; }
+static size_t nms_smem(int B) { return (((size_t)B * 13 + 15) & ~(size_t)15) + (size_t)std::min(B, NMS_MASK_CAP) * 32; }   // + staged boxes of the bit-matrix path
 
 int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const kg_decode_outputs* out, void* workspace,
                   size_t workspace_bytes, cudaStream_t stream, int* n_launches) {
