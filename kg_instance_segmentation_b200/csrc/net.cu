@@ -351,20 +351,23 @@ static void assign_tc(Plan* p, int precision) {
     if (precision == 1 && getenv("KG_NO_2PASS") == nullptr &&
         (w->name == "c0_conv.2" || w->name == "c1_up_conv.0" || w->name == "c2_up_conv.0" || w->name == "c3_up_conv.0" ||
          w->name == "c4_up_conv.0")) op.tc_passes = 2;
-    // experiments: KG_2PASS_EXTRA = comma-separated name fragments of further layers to run 2-pass in "fast"
-    if (precision == 1 && op.tc_passes == 3) {
-      if (const char* extra = getenv("KG_2PASS_EXTRA")) {
-        std::string list(extra);
-        size_t pos = 0;
-        while (pos <= list.size()) {
-          const size_t e = list.find(',', pos);
-          const std::string frag = list.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
-          if (!frag.empty() && w->name.find(frag) != std::string::npos) op.tc_passes = 2;
-          if (e == std::string::npos) break;
-          pos = e + 1;
-        }
+    // experiments: KG_2PASS_EXTRA / KG_1PASS_EXTRA = comma-separated name fragments of further layers to run 2-pass / single-pass in "fast"
+    auto listed = [&](const char* var) {
+      const char* extra = getenv(var);
+      if (extra == nullptr) return false;
+      const std::string list(extra);
+      size_t pos = 0;
+      while (pos <= list.size()) {
+        const size_t e = list.find(',', pos);
+        const std::string frag = list.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+        if (!frag.empty() && w->name.find(frag) != std::string::npos) return true;
+        if (e == std::string::npos) break;
+        pos = e + 1;
       }
-    }
+      return false;
+    };
+    if (precision == 1 && op.tc_passes == 3 && listed("KG_2PASS_EXTRA")) op.tc_passes = 2;
+    if (precision == 1 && op.tc_passes != 1 && listed("KG_1PASS_EXTRA")) op.tc_passes = 1;
   }
 }
 

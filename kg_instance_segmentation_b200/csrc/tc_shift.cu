@@ -82,8 +82,6 @@ struct ShCfg {
   static constexpr int b_lo(int b) { int g = 0; while (b >= nbatch(g)) { b -= nbatch(g); ++g; } return b * 16; }
   static constexpr int b_n(int b) { return n_out(b_group(b)) - b_lo(b) < 16 ? n_out(b_group(b)) - b_lo(b) : 16; }
   static constexpr int last_batch_of_half(int h) { int l = -1; for (int b = 0; b < NBT; ++b) if ((b & 1) == h) l = b; return l; }
-  // channels handled by the same epilogue half before batch b (register index of the batch's first channel)
-  static constexpr int half_off(int b) { int o = 0; for (int i = (b & 1); i < b; i += 2) o += b_n(i); return o; }
   static constexpr int NU = (O0 > 0 ? units_of(0) : 0) + (O1 > 0 ? units_of(1) : 0) + (O2 > 0 ? units_of(2) : 0);
   static constexpr int COLS = col0(NG);
   static constexpr int NOUT = bufcol(NG);
@@ -425,126 +423,6 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
             continue;
           }
         }
-        if constexpr (OUTMODE == 0 && TAPS == 7) {
-          if (p.row_mode && p.RB == 0) {
-            // ---- 7x7 heads, whole-row tiles: shift-add in REGISTERS.  out[u] = sum_s Z[u + s - 3][s]: lane u takes tap s from lane
-            // u + s - 3 by warp shuffle.  The three pixels at either end of a quadrant need taps from the neighbouring quadrant: every
-            // warp exports the six (lane, tap) values its neighbours are missing (lanes 0..2: taps 4..6 to the left, lanes 29..31:
-            // taps 0..2 to the right), ONE barrier per tile makes them visible, and the edge lanes add what they lack.  The last
-            // three pixels of a tile wait in `pend` for the next tile of the row.  (The generic path below adds every tap into a
-            // shared-memory row buffer: 2 x 464 x 128 shared accesses and 8 barriers per tile, 35 % tensor pipe.)
-            constexpr int NOUT = Cfg::NOUT;
-            constexpr int XSZ = 4 * NOUT * 6;
-            const bool first = tx == 0, last = tx == p.tiles_x - 1;
-            const uint32_t par = tile_it & 1u;
-            // Buffer lifetimes with ONE barrier per tile: a warp that passed barrier i + 1 implies every warp finished tile i.  XL and
-            // pend are read in the tile after their barrier only (two buffers); the right exports are ALSO read one tile later by
-            // quadrant 0 (three buffers).
-            const uint32_t tri = tile_it % 3u;
-            float* XL = s_edge + par * XSZ;                  // [quad][channel][6]: lane 0: taps 4,5,6 | lane 1: taps 5,6 | lane 2: tap 6
-            float* XR = s_edge + 2 * XSZ + tri * XSZ;        // [quad][channel][6]: lane 31: taps 0,1,2 | lane 30: taps 0,1 | lane 29: tap 0
-            const float* XR_prev = s_edge + 2 * XSZ + ((tile_it + 2u) % 3u) * XSZ;
-            float* pend = s_edge + 5 * XSZ + par * (3 * NOUT);
-            const float* pend_prev = s_edge + 5 * XSZ + (par ^ 1u) * (3 * NOUT);
-            constexpr int NCH_MAX = 29;                      // channels of one epilogue half (kp 5 + mid 16 + mid 8, or short 10 + mid 16)
-            float osum[NCH_MAX];
-            static_for<0, Cfg::NBT>([&](auto Bx) __attribute__((always_inline)) {
-              constexpr int b = decltype(Bx)::value;
-              constexpr int g = Cfg::b_group(b), c_lo = Cfg::b_lo(b), c_n = Cfg::b_n(b), b0 = Cfg::bufcol(g), nch = (c_n + 7) / 8;
-              if ((b & 1) == half) {
-                float z[TAPS][nch * 8];
-                static_for<0, TAPS>([&](auto Sx) __attribute__((always_inline)) {
-                  constexpr int s = decltype(Sx)::value;
-                  static_for<0, nch>([&](auto Cx) __attribute__((always_inline)) {
-                    constexpr int c = decltype(Cx)::value;
-                    constexpr uint32_t col = (uint32_t)(Cfg::col0(g) + Cfg::stride(g) * s + c_lo + 8 * c);
-                    tmem_ld8_nowait(lane_addr + col, reinterpret_cast<uint32_t*>(&z[s][8 * c]));
-                  });
-                });
-                tmem_ld_wait();
-                if (b == Cfg::last_batch_of_half(b & 1)) {     // this warp has read all of its columns of Z
-                  tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
-                }
-#pragma unroll
-                for (int e = 0; e < c_n; ++e) {
-                  const int ch = b0 + c_lo + e;
-                  float* xl = XL + (quad * NOUT + ch) * 6;
-                  float* xr = XR + (quad * NOUT + ch) * 6;
-                  if (lane == 0) { xl[0] = z[4][e]; xl[1] = z[5][e]; xl[2] = z[6][e]; }
-                  if (lane == 1) { xl[3] = z[5][e]; xl[4] = z[6][e]; }
-                  if (lane == 2) { xl[5] = z[6][e]; }
-                  if (lane == 31) { xr[0] = z[0][e]; xr[1] = z[1][e]; xr[2] = z[2][e]; }
-                  if (lane == 30) { xr[3] = z[0][e]; xr[4] = z[1][e]; }
-                  if (lane == 29) { xr[5] = z[0][e]; }
-                  float a = z[3][e];
-#pragma unroll
-                  for (int d = 1; d <= 3; ++d) {
-                    const float up = __shfl_up_sync(0xffffffffu, z[3 - d][e], d);       // tap 3 - d of lane u - d
-                    const float dn = __shfl_down_sync(0xffffffffu, z[3 + d][e], d);     // tap 3 + d of lane u + d
-                    a += (lane >= d ? up : 0.f) + (lane + d <= 31 ? dn : 0.f);
-                  }
-                  osum[Cfg::half_off(b) + e] = a;
-                }
-              }
-            });
-            if (Cfg::last_batch_of_half(1) < 0 && half == 1) {   // a half without work still releases the accumulators
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
-            }
-            epi_bar();                                           // exports of this tile (and pend / XR of the previous one) are visible
-            const int y = y0;
-            const int x = tx * 128 + t;
-            static_for<0, Cfg::NBT>([&](auto Bx) __attribute__((always_inline)) {
-              constexpr int b = decltype(Bx)::value;
-              constexpr int g = Cfg::b_group(b), c_lo = Cfg::b_lo(b), c_n = Cfg::b_n(b), b0 = Cfg::bufcol(g), no = Cfg::n_out(g);
-              if ((b & 1) == half) {
-                const ShGroup& G = p.grp[g];
-#pragma unroll
-                for (int e = 0; e < c_n; ++e) {
-                  const int ch = b0 + c_lo + e;
-                  float a = osum[Cfg::half_off(b) + e];
-                  // left neighbours' taps 0..2 (lanes 0..2), right neighbours' taps 4..6 (lanes 29..31)
-                  if (lane < 3 && !(quad == 0 && first)) {
-                    const float* xr = (quad == 0 ? XR_prev + (3 * NOUT + ch) * 6 : XR + ((quad - 1) * NOUT + ch) * 6);
-                    if (lane == 0) a += xr[2] + xr[4] + xr[5];
-                    if (lane == 1) a += xr[1] + xr[3];
-                    if (lane == 2) a += xr[0];
-                  }
-                  if (lane > 28 && quad < 3) {
-                    const float* xl = XL + ((quad + 1) * NOUT + ch) * 6;
-                    if (lane == 31) a += xl[0] + xl[3] + xl[5];
-                    if (lane == 30) a += xl[1] + xl[4];
-                    if (lane == 29) a += xl[2];
-                  }
-                  float* plane = G.out32 + (((long long)n * no + c_lo + e) * p.H + y) * p.W;
-                  const float bias = s_bias[ch];
-                  if (quad == 3 && lane > 28 && !last) {
-                    pend[(lane - 29) * NOUT + ch] = a;           // finished by the next tile of this row
-                  } else {
-                    float o = fmaf(a, G.inv_scale, bias);
-                    if (G.sigmoid) o = 1.f / (1.f + expf(-o));
-                    plane[x] = o;
-                  }
-                  if (quad == 0 && lane < 3 && !first) {
-                    // the previous tile's last three pixels: pending sum + this tile's first lanes' taps 4..6 (this quadrant's own exports)
-                    const float* xl = XL + ch * 6;
-                    float v = pend_prev[lane * NOUT + ch];
-                    if (lane == 2) v += xl[0] + xl[3] + xl[5];
-                    if (lane == 1) v += xl[1] + xl[4];
-                    if (lane == 0) v += xl[2];
-                    float o = fmaf(v, G.inv_scale, bias);
-                    if (G.sigmoid) o = 1.f / (1.f + expf(-o));
-                    plane[tx * 128 - 3 + lane] = o;
-                  }
-                }
-              }
-            });
-            continue;
-          }
-        }
         // ---- shift-add: tap s of position q goes to output pixel q - s + pad (everything below is compile-time unrolled) ----
         static_for<0, TAPS>([&](auto Sx) __attribute__((always_inline)) {
           constexpr int s = decltype(Sx)::value;
@@ -743,7 +621,6 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   p.num_work = op->N * p.rows_y;
   p.RB = p.row_mode ? 128 + 2 * op->pad : 128;
   if (std::is_same<Cfg, C64Cfg>::value && p.row_mode && op->out_hi != nullptr) p.RB = 0;   // register-shuffle epilogue: no row buffer
-  { const char* e = getenv("KG_SH_HEADS_REG"); if (std::is_same<Cfg, HeadsCfg>::value && p.row_mode && !(e && e[0] == '0')) p.RB = 0; }
   p.out_hi = op->out_hi; p.out_lo = op->out_lo; p.mask = op->mask; p.relu = op->relu ? 1 : 0;
   const int rows = Cfg::COLS, R = op->R;
   const int acc_sets = 2 * Cfg::COLS <= 512 ? 2 : 1;
@@ -783,10 +660,7 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
     }
   }
   p.w_slab = (unsigned)align_up((size_t)maxN * 128, 1024);
-  // edge-exchange region of the register-shuffle epilogues: 832 floats (3x3, 64 channels) / (2 left + 3 right) export buffers of
-  // 4 quadrants x NOUT channels x 6 + 2 x 3 pending pixels (7x7 heads)
-  const size_t edge_floats = std::is_same<Cfg, HeadsCfg>::value ? (size_t)(5 * 4 * Cfg::NOUT * 6 + 2 * 3 * Cfg::NOUT + 16) : 832;
-  const size_t buf_bytes = ((size_t)p.RB * Cfg::RS + Cfg::NOUT + 4 + edge_floats) * sizeof(float);
+  const size_t buf_bytes = ((size_t)p.RB * Cfg::RS + Cfg::NOUT + 4 + 832) * sizeof(float);
   // TMA-store epilogue of the register-shuffle path (64-channel NHWC output, whole-row tiles)
   { const char* e = getenv("KG_SH_STAGE"); p.stage_bytes = (std::is_same<Cfg, C64Cfg>::value && p.row_mode && op->out_hi != nullptr && !(e && e[0] == '0')) ? 32768u : 0u; }
   if (p.stage_bytes) {
