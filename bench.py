@@ -111,11 +111,15 @@ def profiled_traffic(key=None):
     if not files:
         return None, None
     d = json.load(open(files[-1]))
+    state = d.get("code_state")
     if key is not None:
         d = d.get(key)
         if d is None:
             return None, None
-    return d.get("dram_bytes_per_launch"), os.path.basename(files[-1])
+    # the capture is a separate ncu run of the same command (a number taken under a profiler is never a bench value): the source
+    # says which code state and how many launches it covers, so that a stale capture is visible in the line
+    src = os.path.basename(files[-1]) + (f" ({d.get('launches')} launches" + (f", code {state}" if state else "") + ")")
+    return d.get("dram_bytes_per_launch"), src
 
 
 def planted_batch(n_distinct=4):

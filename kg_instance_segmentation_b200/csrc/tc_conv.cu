@@ -278,18 +278,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       };
       const int c_first = next_chunk(-16);
       fetch_res(c_first);
+      uint32_t raw_next[16];
+      if (p.KS == 1 && c_first < p.BN) tmem_ld16_nowait(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.BN + c_first), raw_next);
       for (int c0 = c_first; c0 < p.BN; c0 = next_chunk(c0)) {
         uint32_t raw[16];
         float v[16];
         uint4 rhv[2] = {rh_next[0], rh_next[1]}, rlv[2] = {rl_next[0], rl_next[1]};
         fetch_res(next_chunk(c0));
-        tmem_ld16(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.KS * p.BN + c0), raw);
+        if (p.KS == 1) {
+          // software-pipelined: the load of THIS chunk was issued one iteration ago; the next chunk's load goes out before this one
+          // is processed (the TMEM round trip of every 16-column chunk was exposed otherwise)
+          tmem_ld_wait16(raw_next);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-        for (int ks = 1; ks < p.KS; ++ks) {
-          tmem_ld16(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((mt * p.KS + ks) * p.BN + c0), raw);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw_next[j]);
+          const int cn = next_chunk(c0);
+          if (cn < p.BN) tmem_ld16_nowait(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.BN + cn), raw_next);
+        } else {
+          // the KS partial accumulators of a narrow-N tile: all loads are issued before the single wait (one TMEM round trip per
+          // chunk instead of KS serialised ones)
+          uint32_t part[3][16];
+          tmem_ld16_nowait(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.KS * p.BN + c0), raw);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(raw[j]);
+          for (int ks = 1; ks < 4; ++ks)
+            if (ks < p.KS) tmem_ld16_nowait(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((mt * p.KS + ks) * p.BN + c0), part[ks - 1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+#pragma unroll
+          for (int ks = 1; ks < 4; ++ks)
+            if (ks < p.KS) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(part[ks - 1][j]);
+            }
         }
         const int co0 = n0 + c0;
         if ((!valid && !p.o_tma) || co0 >= p.Cout) continue;
@@ -787,6 +807,7 @@ int tc_conv_prepare(TcConvOp* op) {
     const int total_mmas = op->R * op->S * (p.chunks0 + p.chunks1) * 4 * p.passes;
     while (ks > 1 && total_mmas < ks) --ks;                               // every chain must receive at least one MMA
     while (ks & (ks - 1)) --ks;                                           // power of two (chain = counter & (KS - 1))
+    if (ks > 4) ks = 4;                                                   // the epilogue sums at most four partial accumulators
     p.KS = ks;
   }
   // CTA-pair kernel (tc_conv2_kernel): single-pass, hi-plane NHWC output, no residual / mask / second source, N = 192 or 256

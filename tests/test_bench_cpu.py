@@ -27,6 +27,6 @@ def test_roofline_traffic_comes_from_the_committed_capture():
     sys.path.insert(0, ROOT)
     import bench
     per_launch, src = bench.profiled_traffic()
-    assert src is not None and src.endswith("_traffic.json") and per_launch > 1e8
+    assert src is not None and "_traffic.json" in src and per_launch > 1e8
     blur, _ = bench.profiled_traffic("decode")
     assert 5e7 < blur < 5e8        # ~446 MB of accumulators per step over four launches

@@ -1,21 +1,22 @@
 #!/bin/bash
 # usage (on the GPU box, via gpurun): tools/gpu_profile.sh <tag>   -> gpurun_out/<tag>_*
-# pytest -m gpu, the default bench line, the ncu launch list of one step and one `--set full` capture of the tensor-core
-# launches (tc_conv / tc_shift) of that step.
-tag=${1:-r1}
+# pytest -m gpu, the default bench line (with CPU and cuDNN baselines), the decode / cfg4 / free-running lines, the ncu launch list of
+# one step and `--set full` captures of (a) the tensor-core launches and (b) the decode kernels of that step.
+tag=${1:-r2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv,noheader > gpurun_out/${tag}_gpu.txt
 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/${tag}_pytest.log
 tail -2 gpurun_out/${tag}_pytest.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
-tail -c 400 gpurun_out/${tag}_bench.json
-python bench.py --workload decode --steps 10 --warmup 3 > gpurun_out/${tag}_bench_decode.json 2>> gpurun_out/${tag}_bench.err
+python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+tail -c 300 gpurun_out/${tag}_bench.json; echo
+python bench.py --workload decode --steps 20 --warmup 3 > gpurun_out/${tag}_bench_decode.json 2>> gpurun_out/${tag}_bench.err
+python bench.py --config cfg4 --steps 8 --warmup 3 --no-gpu-baseline > gpurun_out/${tag}_bench_cfg4.json 2>> gpurun_out/${tag}_bench.err
+python bench.py --free-running --steps 8 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_bench_free_running.json 2>> gpurun_out/${tag}_bench.err
 # launches per step are printed by bench (gpu_launches / steps); warm-up = 3 steps
 L=$(python -c "import json;d=json.load(open('gpurun_out/${tag}_bench.json'));print(d['gpu_launches']//d['steps'])")
 echo "launches/step=$L"
-SKIP=${SKIP:-$((3*L))}
-ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $L --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'kg::|tc_|vote|blur|exact_peaks|group_kernel|nms_kernel|bilinear|maxpool|preprocess' -s $((3*L)) -c $L --csv \
+    --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1
 if [ "${FULL:-1}" = "1" ]; then
   TC=$(python - <<PY
 import csv
@@ -26,10 +27,14 @@ print(sum(1 for r in rows[hi+1:] if len(r)>k and ('tc_conv' in r[k] or 'tc_shift
 PY
 )
   echo "tensor-core launches/step=$TC"
-  timeout 800 ncu --set full --clock-control none -k regex:'tc_conv|tc_shift' -s $((3*TC)) -c $TC -f -o gpurun_out/${tag}_tc \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
+  timeout 900 ncu --set full --clock-control none -k regex:'tc_conv|tc_shift' -s $((3*TC)) -c $TC -f -o gpurun_out/${tag}_tc \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
   ncu -i gpurun_out/${tag}_tc.ncu-rep --page raw --csv > gpurun_out/${tag}_tc_raw.csv 2>/dev/null
-  sz=$(stat -c %s gpurun_out/${tag}_tc.ncu-rep)
-  if [ "$sz" -gt 40000000 ]; then rm -f gpurun_out/${tag}_tc.ncu-rep; fi
-  ls -la gpurun_out/
+  timeout 600 ncu --set full --clock-control none -k regex:'vote_kernel|blur32|exact_peaks' -s 27 -c 9 -f -o gpurun_out/${tag}_decode \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_ncu_decode.log 2>&1
+  ncu -i gpurun_out/${tag}_decode.ncu-rep --page raw --csv > gpurun_out/${tag}_decode_raw.csv 2>/dev/null
+  for f in gpurun_out/${tag}_tc.ncu-rep gpurun_out/${tag}_decode.ncu-rep; do
+    sz=$(stat -c %s $f 2>/dev/null || echo 0); if [ "$sz" -gt 30000000 ]; then rm -f $f; fi
+  done
+  ls -la gpurun_out/ | grep ${tag}
 fi
