@@ -38,8 +38,6 @@ constexpr int TC_MAX_SMEM = 227 * 1024;
 struct TcParams {
   CUtensorMap a_map[2][2];          // [source][plane hi/lo]
   CUtensorMap w_map[2];             // [plane hi/lo]
-  CUtensorMap o_map[2];             // NHWC output planes (TMA-store epilogue), boxes of 64 channels x 32 pixels
-  int o_tma, o_bw;                  // o_tma: outputs leave through smem staging + TMA stores; o_bw: box width in pixels (32 / o_bw rows)
   const float* bias;
   __half* out_hi; __half* out_lo;
   float* out32;
@@ -83,8 +81,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const uint32_t w_tile = (uint32_t)p.BN * 128u;
   const uint32_t w_plane = (uint32_t)p.wg * w_tile;                   // one plane of one W slot: wg taps back to back
   const uint32_t w_slot = (uint32_t)NPW * w_plane;
-  const uint32_t stage0 = smem0;                                      // output staging (opt-in TMA-store epilogue): 8 epilogue warps x (hi 4 KiB + lo 4 KiB)
-  const uint32_t a_ring = smem0 + (p.o_tma ? 65536u : 0u), w_ring = a_ring + (uint32_t)p.NA * a_slot;
+  const uint32_t a_ring = smem0, w_ring = a_ring + (uint32_t)p.NA * a_slot;
   const uint32_t bars = w_ring + (uint32_t)p.NW * w_slot;
   auto a_full = [&](int s) { return bars + 8u * s; };
   auto a_empty = [&](int s) { return bars + 8u * (p.NA + s); };
@@ -100,7 +97,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     if (NPA == 2) prefetch_tmap(&p.a_map[0][1]);
     if (NPW == 2) prefetch_tmap(&p.w_map[1]);
     if (p.chunks1 > 0) { prefetch_tmap(&p.a_map[1][0]); if (NPA == 2) prefetch_tmap(&p.a_map[1][1]); }
-    if (p.o_tma) { prefetch_tmap(&p.o_map[0]); if (p.out_lo != nullptr) prefetch_tmap(&p.o_map[1]); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
@@ -237,95 +233,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       }   // work loop
     }
   } else {
-    // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4; the two warps of a quadrant take alternate 16-column chunks
-    // (the epilogue is instruction-bound: bias / residual / ReLU / split-fp16 conversion of 128 x BN values per tile) =====
+    // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4; the two warps of a quadrant take alternate 16-column chunks.
+    // The epilogue is instruction-bound (ncu source view, c0_cat_refine: 9 100 warp-instructions per 128-pixel tile, a third of
+    // them parameter reloads, index arithmetic and branches), so every launch parameter it needs is hoisted into registers here,
+    // per-tile addresses are formed once, and the chunk loop steps by a constant. =====
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int cgran = p.o_tma ? 6 : 4;                               // log2 of the column granule one warp owns (64 with TMA staging)
     const int row = quad * 32 + lane;
-    const int HW = p.H * p.W;
-    const uint32_t stg = stage0 + (uint32_t)(warp - 2) * 8192u;      // this warp's staging: 32 pixels x 128 B, hi then lo
-    const uint32_t stg_row = stg + (uint32_t)lane * 128u;
+    const int H = p.H, W = p.W, HW = H * W, Cout = p.Cout, BN = p.BN, KS = p.KS, BW = p.BW, BH = p.BH, tiles_x = p.tiles_x;
+    const int m_tiles = p.m_tiles, n_tiles = p.n_tiles, num_work = p.num_work;
+    const bool two_acc = p.acc_stages == 2, relu = p.relu != 0, sigm = p.sigmoid != 0;
+    const float inv_scale = p.inv_scale;
+    const float* __restrict__ bias = p.bias;
+    __half* const out_hi = p.out_hi; __half* const out_lo = p.out_lo;
+    float* const out32 = p.out32;
+    const __half* const res_hi = p.res_hi; const __half* const res_lo = p.res_lo;
+    const uint8_t* const mask = p.mask;
+    const int ry = row / BW, rx = row - ry * BW;                       // this lane's pixel inside the tile
+    const uint32_t lane_base = ((uint32_t)(quad * 32) << 16);
     int it = 0;
-    for (int work = blockIdx.x; work < p.num_work; work += gridDim.x, ++it) {
-    const int m_first = (work / p.n_tiles) * MT;
-    const int n0 = (work % p.n_tiles) * p.BN;
-    const int acc = p.acc_stages == 2 ? (it & 1) : 0;
-    const uint32_t acc_phase = p.acc_stages == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++it) {
+    const int m_first = (work / n_tiles) * MT;
+    const int n0 = (work % n_tiles) * BN;
+    const int acc = two_acc ? (it & 1) : 0;
+    const uint32_t acc_phase = two_acc ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
     mbar_wait(tmem_full(acc), acc_phase);
     tc_fence_after();
-    const uint32_t acc_base = tmem_base + (uint32_t)acc * acc_cols;
+    const uint32_t acc_base = tmem_base + (uint32_t)acc * acc_cols + lane_base;
     for (int mt = 0; mt < MT; ++mt) {
       const int m = m_first + mt;
-      if (m >= p.m_tiles) break;
+      if (m >= m_tiles) break;
       const int n = m / tiles_per_img, rem = m - n * tiles_per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int oy = ty * p.BH + row / p.BW, ox = tx * p.BW + row % p.BW;
-      const bool valid = oy < p.H && ox < p.W;
-      const long long pix = (long long)n * HW + (long long)oy * p.W + ox;
-      const bool keep = valid && (p.mask == nullptr || p.mask[pix] != 0);
-      // this warp's 16-column chunks: c0 with ((c0 >> cgran) & 1) == half.  The residual of chunk i + 1 is requested before chunk i is
-      // processed: a lane-per-pixel 32-byte load per plane waits ~1 us on HBM, and with one chunk in flight per warp the residual
-      // stream of the wide-N 1x1 convs (conv3 / downsample of every bottleneck) was latency-bound at ~28 % of DRAM peak
-      auto next_chunk = [&](int c) { c += 16; while (c < p.BN && ((c >> cgran) & 1) != half) c += 16; return c; };
-      const bool has_res = p.res_hi != nullptr && valid;
+      const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+      const int oy = ty * BH + ry, ox = tx * BW + rx;
+      const bool valid = oy < H && ox < W;
+      const long long pix = (long long)n * HW + (long long)oy * W + ox;
+      const bool keep = valid && (mask == nullptr || mask[pix] != 0);
+      const bool has_res = res_hi != nullptr && valid;
+      // per-tile bases: channel n0 of this lane's pixel
+      const long long obase = pix * Cout + n0;
+      float* o32 = out32 != nullptr ? out32 + ((long long)n * Cout + n0) * HW + (long long)oy * W + ox : nullptr;
+      const uint32_t tbase = acc_base + (uint32_t)(mt * KS * BN);
+      const int c_first = half * 16;
+      // the residual and the accumulator columns of chunk i + 1 are requested before chunk i is processed (a lane-per-pixel
+      // 32-byte residual load per plane waits ~1 us on HBM; the TMEM round trip is shorter but was equally exposed)
       uint4 rh_next[2], rl_next[2];
-      auto fetch_res = [&](int c) {
-        if (has_res && c < p.BN && n0 + c + 16 <= p.Cout) {
-          ld_global_nc_v8(p.res_hi + pix * p.Cout + n0 + c, rh_next[0], rh_next[1]);
-          ld_global_nc_v8(p.res_lo + pix * p.Cout + n0 + c, rl_next[0], rl_next[1]);
-        }
-      };
-      const int c_first = next_chunk(-16);
-      fetch_res(c_first);
       uint32_t raw_next[16];
-      if (p.KS == 1 && c_first < p.BN) tmem_ld16_nowait(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.BN + c_first), raw_next);
-      for (int c0 = c_first; c0 < p.BN; c0 = next_chunk(c0)) {
-        uint32_t raw[16];
+      if (has_res && c_first < BN && n0 + c_first + 16 <= Cout) {
+        ld_global_nc_v8(res_hi + obase + c_first, rh_next[0], rh_next[1]);
+        ld_global_nc_v8(res_lo + obase + c_first, rl_next[0], rl_next[1]);
+      }
+      if (KS == 1 && c_first < BN) tmem_ld16_nowait(tbase + (uint32_t)c_first, raw_next);
+      for (int c0 = c_first; c0 < BN; c0 += 32) {
         float v[16];
-        uint4 rhv[2] = {rh_next[0], rh_next[1]}, rlv[2] = {rl_next[0], rl_next[1]};
-        fetch_res(next_chunk(c0));
-        if (p.KS == 1) {
-          // software-pipelined: the load of THIS chunk was issued one iteration ago; the next chunk's load goes out before this one
-          // is processed (the TMEM round trip of every 16-column chunk was exposed otherwise)
+        const uint4 rhv[2] = {rh_next[0], rh_next[1]}, rlv[2] = {rl_next[0], rl_next[1]};
+        const int cn = c0 + 32;
+        if (has_res && cn < BN && n0 + cn + 16 <= Cout) {
+          ld_global_nc_v8(res_hi + obase + cn, rh_next[0], rh_next[1]);
+          ld_global_nc_v8(res_lo + obase + cn, rl_next[0], rl_next[1]);
+        }
+        if (KS == 1) {
           tmem_ld_wait16(raw_next);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw_next[j]);
-          const int cn = next_chunk(c0);
-          if (cn < p.BN) tmem_ld16_nowait(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.BN + cn), raw_next);
+          if (cn < BN) tmem_ld16_nowait(tbase + (uint32_t)cn, raw_next);
         } else {
-          // the KS partial accumulators of a narrow-N tile: all loads are issued before the single wait (one TMEM round trip per
-          // chunk instead of KS serialised ones)
-          uint32_t part[3][16];
-          tmem_ld16_nowait(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.KS * p.BN + c0), raw);
+          // the KS partial accumulators of a narrow-N tile: all loads are issued before the single wait
+          uint32_t part[4][16];
 #pragma unroll
-          for (int ks = 1; ks < 4; ++ks)
-            if (ks < p.KS) tmem_ld16_nowait(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((mt * p.KS + ks) * p.BN + c0), part[ks - 1]);
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < KS) tmem_ld16_nowait(tbase + (uint32_t)(ks * BN + c0), part[ks]);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(part[0][j]);
 #pragma unroll
           for (int ks = 1; ks < 4; ++ks)
-            if (ks < p.KS) {
+            if (ks < KS) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(part[ks - 1][j]);
+              for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(part[ks][j]);
             }
         }
         const int co0 = n0 + c0;
-        if ((!valid && !p.o_tma) || co0 >= p.Cout) continue;
-        if (co0 + 16 <= p.Cout) {
+        if (!valid || co0 >= Cout) continue;
+        if (co0 + 16 <= Cout) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
-            v[j] = fmaf(v[j], p.inv_scale, b.x); v[j + 1] = fmaf(v[j + 1], p.inv_scale, b.y);
-            v[j + 2] = fmaf(v[j + 2], p.inv_scale, b.z); v[j + 3] = fmaf(v[j + 3], p.inv_scale, b.w);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + co0 + j));
+            v[j] = fmaf(v[j], inv_scale, b.x); v[j + 1] = fmaf(v[j + 1], inv_scale, b.y);
+            v[j + 2] = fmaf(v[j + 2], inv_scale, b.z); v[j + 3] = fmaf(v[j + 3], inv_scale, b.w);
           }
           if (has_res) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const uint4 a = rhv[q], b = rlv[q];
-              const __half2* ah = reinterpret_cast<const __half2*>(&a);
-              const __half2* bh = reinterpret_cast<const __half2*>(&b);
+              const __half2* ah = reinterpret_cast<const __half2*>(&rhv[q]);
+              const __half2* bh = reinterpret_cast<const __half2*>(&rlv[q]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
@@ -333,67 +334,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               }
             }
           }
+          if (relu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (p.relu) v[j] = fmaxf(v[j], 0.f);
-            if (p.sigmoid) v[j] = 1.f / (1.f + expf(-v[j]));
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (p.mask != nullptr && !keep) {
+          if (sigm) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+          }
+          if (mask != nullptr && !keep) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
-          if (p.out_hi != nullptr) {
+          if (out_hi != nullptr) {
             uint4 hi4[2], lo4[2];
             uint32_t* hh = reinterpret_cast<uint32_t*>(hi4);
             uint32_t* ll = reinterpret_cast<uint32_t*>(lo4);
+            if (out_lo != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_f16x2(v[2 * e], v[2 * e + 1], hh[e], ll[e]);
-            if (p.o_tma) {
-              // staging rows are 128 B (64 channels) with the 128-byte swizzle of the store's tensor map: 16-byte chunk j of
-              // row r sits at chunk (j ^ (r & 7)); a 64-channel group is complete after four 16-channel pieces
-              const int piece = (c0 >> 4) & 3;
-              if (piece == 0) {                               // the previous group's TMA store must have read the staging
-                if (lane == 0) bulk_wait_read0();
-                __syncwarp();
-              }
-              const uint32_t sw = (uint32_t)(lane & 7);
-              const uint32_t a0 = stg_row + ((((uint32_t)(2 * piece)) ^ sw) << 4), a1 = stg_row + ((((uint32_t)(2 * piece + 1)) ^ sw) << 4);
-              st_shared_v4(a0, hi4[0]); st_shared_v4(a1, hi4[1]);
-              if (p.out_lo != nullptr) { st_shared_v4(a0 + 4096u, lo4[0]); st_shared_v4(a1 + 4096u, lo4[1]); }
-              if (piece == 3 || c0 + 16 >= p.BN) {
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                  const int r0 = quad * 32;
-                  const int ly = r0 / p.BW, lx = r0 - ly * p.BW;
-                  const int gx = tx * p.BW + lx, gy = ty * p.BH + ly;
-                  if (gx < p.W && gy < p.H) {
-                    tma_store_4d(&p.o_map[0], stg, co0 & ~63, gx, gy, n);
-                    if (p.out_lo != nullptr) tma_store_4d(&p.o_map[1], stg + 4096u, co0 & ~63, gx, gy, n);
-                  }
-                  bulk_commit();
-                }
-              }
+              for (int e = 0; e < 8; ++e) split_f16x2(v[2 * e], v[2 * e + 1], hh[e], ll[e]);
+              st_global_v8(out_hi + obase + c0, hi4[0], hi4[1]);
+              st_global_v8(out_lo + obase + c0, lo4[0], lo4[1]);
             } else {
-              st_global_v8(p.out_hi + pix * p.Cout + co0, hi4[0], hi4[1]);
-              if (p.out_lo != nullptr) st_global_v8(p.out_lo + pix * p.Cout + co0, lo4[0], lo4[1]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) hh[e] = f16x2_sat(v[2 * e], v[2 * e + 1]);
+              st_global_v8(out_hi + obase + c0, hi4[0], hi4[1]);
             }
           }
-          if (p.out32 != nullptr && valid) {
+          if (o32 != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) p.out32[((long long)n * p.Cout + co0 + j) * HW + (long long)oy * p.W + ox] = v[j];
+            for (int j = 0; j < 16; ++j) o32[(long long)(c0 + j) * HW] = v[j];
           }
         } else {
           // ragged tail of output channels (head convs: Cout = 5 / 10 / 40): fp32 NCHW output only
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = co0 + j;
-            if (co < p.Cout && valid) {
-              float x = fmaf(v[j], p.inv_scale, __ldg(p.bias + co));
-              if (p.relu) x = fmaxf(x, 0.f);
-              if (p.sigmoid) x = 1.f / (1.f + expf(-x));
+            if (co < Cout) {
+              float x = fmaf(v[j], inv_scale, __ldg(bias + co));
+              if (relu) x = fmaxf(x, 0.f);
+              if (sigm) x = 1.f / (1.f + expf(-x));
               if (!keep) x = 0.f;
-              if (p.out32 != nullptr) p.out32[((long long)n * p.Cout + co) * HW + (long long)oy * p.W + ox] = x;
+              if (o32 != nullptr) o32[(long long)(c0 + j) * HW] = x;
             }
           }
         }
@@ -404,7 +386,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
     }   // work loop
-    if (p.o_tma && lane == 0) bulk_wait_all();              // every TMA store of this warp has landed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -754,11 +735,9 @@ int tc_conv_prepare(TcConvOp* op) {
   const int strip_px = strip ? TC_BM + op->S - 1 : TC_BM;
   p.a_tx_bytes = (unsigned)(strip ? strip_px * 128 : TC_A_TILE);
   p.a_tile_bytes = (unsigned)align_up(p.a_tx_bytes, 1024);
-  // TMA-store epilogue (opt-in, KG_TC_OTMA=1): NHWC outputs go through a 64 KiB smem staging area and leave as full 128-byte rows (a lane-per-pixel
-  // direct store writes 32 B per lane at a Cout * 2 B stride: 32 L2 requests per instruction, which bounds wide-N layers)
-  p.o_tma = (op->out_hi != nullptr && op->Cout % 64 == 0 && p.BN % 64 == 0 && env_int("KG_TC_OTMA", 0) != 0) ? 1 : 0;
-  p.o_bw = p.BW < 32 ? p.BW : 32;
-  const size_t budget = TC_MAX_SMEM - 2048 - (p.o_tma ? 65536 : 0);
+  // (A TMA-store epilogue through a 64 KiB staging area existed in round 1 (KG_TC_OTMA); measured slower -- decoder 12.6 -> 17.7 ms,
+  // the ring loses 64 KiB -- and removed.)
+  const size_t budget = TC_MAX_SMEM - 2048;
   // weight tap group: all S taps of a filter row in one W slot when that slot stays small (narrow-N layers)
   p.wg = 1;
   if (op->S > 1 && (size_t)op->S * npw * p.BN * 128 <= (size_t)env_int("KG_TC_WG_MAXKB", 48) * 1024 && env_int("KG_TC_WG", 1) != 0) p.wg = op->S;
@@ -815,7 +794,7 @@ int tc_conv_prepare(TcConvOp* op) {
                op->res_hi == nullptr && op->mask == nullptr && op->out_hi != nullptr && op->out_lo == nullptr && !op->sigmoid &&
                op->Cout % 16 == 0 && p.m_tiles >= 2 && env_int("KG_TC_2CTA", 1) != 0) ? 1 : 0;
   if (p.two_cta) {
-    p.MT = 1; p.KS = 1; p.acc_stages = 2; p.wg = 1; p.o_tma = 0;
+    p.MT = 1; p.KS = 1; p.acc_stages = 2; p.wg = 1;
     const size_t budget2 = TC_MAX_SMEM - 2048;
     const size_t a_slot = p.a_tile_bytes, w_slot = (size_t)(p.BN / 2) * 128;
     if (strip) { na = 3; nw = (int)((budget2 - 3 * a_slot) / w_slot); if (nw > 8) nw = 8; }
@@ -840,22 +819,18 @@ int tc_conv_prepare(TcConvOp* op) {
   }
   KG_TRY(encode_w_map(&p.w_map[0], op->w->d_hi, op->w->cin, op->w->cout_pad, op->w->taps, p.two_cta ? p.BN / 2 : p.BN, p.wg));
   if (npw == 2) KG_TRY(encode_w_map(&p.w_map[1], op->w->d_lo, op->w->cin, op->w->cout_pad, op->w->taps, p.BN, p.wg));
-  if (p.o_tma) {
-    KG_TRY(encode_act_map(&p.o_map[0], op->out_hi, op->Cout, op->W, op->H, op->N, p.o_bw, 32 / p.o_bw));
-    if (op->out_lo != nullptr) KG_TRY(encode_act_map(&p.o_map[1], op->out_lo, op->Cout, op->W, op->H, op->N, p.o_bw, 32 / p.o_bw));
-  }
   const int persist = env_int("KG_TC_CTAS", g_num_sms);
   op->grid_x = (unsigned)std::min(p.num_work, std::max(1, persist));
   if (p.two_cta) op->grid_x = (unsigned)std::min(2 * p.num_work, std::max(2, persist & ~1));   // whole CTA pairs
   op->grid_y = 1;
-  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.wg * npw * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024 + (p.o_tma ? 65536 : 0));
+  op->smem_bytes = (unsigned)((size_t)p.NA * p.MT * p.NPL * p.a_tile_bytes + (size_t)p.NW * p.wg * npw * p.BN * 128 + 16 * (p.NA + p.NW) + 128 + 1024);
   if (p.two_cta) op->smem_bytes = (unsigned)((size_t)p.NA * p.a_tile_bytes + (size_t)p.NW * (p.BN / 2) * 128 + 16 * (p.NA + p.NW) + 128 + 1024);
   KG_REQUIRE(op->smem_bytes <= (unsigned)TC_MAX_SMEM, "tc_conv_prepare: smem %u > %d", op->smem_bytes, TC_MAX_SMEM);
   op->params = sp;
   if (env_int("KG_TC_DEBUG", 0))
-    fprintf(stderr, "[tc] N%d %dx%d C%d+%d->%d k%dx%d s%d passes%d | BN%d BW%d BH%d MT%d KS%d acc%d strip%d wg%d otma%d 2cta%d NA%d NW%d work%d grid%u smem%u tmem%u\n",
+    fprintf(stderr, "[tc] N%d %dx%d C%d+%d->%d k%dx%d s%d passes%d | BN%d BW%d BH%d MT%d KS%d acc%d strip%d wg%d 2cta%d NA%d NW%d work%d grid%u smem%u tmem%u\n",
             op->N, op->H, op->W, op->C0, op->C1, op->Cout, op->R, op->S, op->stride, op->passes, p.BN, p.BW, p.BH, p.MT, p.KS, p.acc_stages,
-            p.strip, p.wg, p.o_tma, p.two_cta, p.NA, p.NW, p.num_work, op->grid_x, op->smem_bytes, p.tmem_cols);
+            p.strip, p.wg, p.two_cta, p.NA, p.NW, p.num_work, op->grid_x, op->smem_bytes, p.tmem_cols);
   return KG_OK;
 }
 

@@ -167,6 +167,17 @@ def test_box_case_table_and_nms_edge_cases():
     assert np.array_equal(nms.non_maximum_suppression_numpy(big, 0.5), O.nms(big, 0.5))
 
 
+def test_nms_host_lists_beyond_the_shared_memory_kernel():
+    """nms_host rejected more than 8192 boxes; longer lists now run the global-memory variant (same order, same
+    arithmetic).  9 000 boxes on a wide canvas (few overlaps, so the oracle's greedy loop stays fast)."""
+    from kg_instance_segmentation_b200 import nms
+    rs = np.random.RandomState(5)
+    big = rs.uniform(0, 4000, (9000, 5)); big[:, 2:4] = big[:, :2] + rs.uniform(5, 40, (9000, 2)); big[:, 4] = rs.uniform(0, 1, 9000)
+    got = nms.non_maximum_suppression_numpy(big, 0.5)
+    ref = O.nms(big, 0.5)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
 def test_overflow_is_reported_not_hidden():
     """A fixed-capacity Decoder reports the overflow in its status word; decode_batched re-runs with doubled capacity."""
     pp = _pp()
