@@ -527,42 +527,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) tc_co
     }
   } else {
     // ===== epilogue (both CTAs): warps 2..9, TMEM lane quadrant = warp % 4, alternate 16-column chunks per half =====
+    struct { int H, W, BH, BW, tiles_x, m_tiles, n_tiles, BN, Cout, relu, num_work; float inv_scale; const float* bias; __half* out_hi; } const P_ =
+        {p.H, p.W, p.BH, p.BW, p.tiles_x, p.m_tiles, p.n_tiles, p.BN, p.Cout, p.relu, p.num_work, p.inv_scale, p.bias, p.out_hi};   // registers, not parameter-bank reloads
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    const int HW = p.H * p.W;
+    const int HW = P_.H * P_.W;
     int it = 0;
-    for (int work = cluster_id; work < p.num_work; work += n_clusters, ++it) {
-      const int m = (work / p.n_tiles) * 2 + (int)rank;
-      const int n0 = (work % p.n_tiles) * p.BN;
+    for (int work = cluster_id; work < P_.num_work; work += n_clusters, ++it) {
+      const int m = (work / P_.n_tiles) * 2 + (int)rank;
+      const int n0 = (work % P_.n_tiles) * P_.BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tmem_full(acc), acc_phase);
       tc_fence_after();
       const uint32_t acc_base = tmem_base + (uint32_t)acc * acc_cols;
-      if (m < p.m_tiles) {
+      if (m < P_.m_tiles) {
         const int n = m / tiles_per_img, rem = m - n * tiles_per_img;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int oy = ty * p.BH + row / p.BW, ox = tx * p.BW + row % p.BW;
-        const bool valid = oy < p.H && ox < p.W;
-        const long long pix = (long long)n * HW + (long long)oy * p.W + ox;
-        for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
+        const int ty = rem / P_.tiles_x, tx = rem - ty * P_.tiles_x;
+        const int oy = ty * P_.BH + row / P_.BW, ox = tx * P_.BW + row % P_.BW;
+        const bool valid = oy < P_.H && ox < P_.W;
+        const long long pix = (long long)n * HW + (long long)oy * P_.W + ox;
+        for (int c0 = half * 16; c0 < P_.BN; c0 += 32) {
           uint32_t raw[16];
           tmem_ld16(acc_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, raw);
           const int co0 = n0 + c0;
-          if (!valid || co0 >= p.Cout) continue;
+          if (!valid || co0 >= P_.Cout) continue;
           uint4 hi4[2];
           uint32_t* hh = reinterpret_cast<uint32_t*>(hi4);
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
-            const float v0 = fmaf(__uint_as_float(raw[j]), p.inv_scale, b.x), v1 = fmaf(__uint_as_float(raw[j + 1]), p.inv_scale, b.y);
-            const float v2 = fmaf(__uint_as_float(raw[j + 2]), p.inv_scale, b.z), v3 = fmaf(__uint_as_float(raw[j + 3]), p.inv_scale, b.w);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(P_.bias + co0 + j));
+            const float v0 = fmaf(__uint_as_float(raw[j]), P_.inv_scale, b.x), v1 = fmaf(__uint_as_float(raw[j + 1]), P_.inv_scale, b.y);
+            const float v2 = fmaf(__uint_as_float(raw[j + 2]), P_.inv_scale, b.z), v3 = fmaf(__uint_as_float(raw[j + 3]), P_.inv_scale, b.w);
             // ReLU + clamp to the finite fp16 range + convert: one F2FP per pair
-            hh[j / 2] = p.relu ? f16x2_relu_sat(v0, v1) : f16x2_sat(v0, v1);
-            hh[j / 2 + 1] = p.relu ? f16x2_relu_sat(v2, v3) : f16x2_sat(v2, v3);
+            hh[j / 2] = P_.relu ? f16x2_relu_sat(v0, v1) : f16x2_sat(v0, v1);
+            hh[j / 2 + 1] = P_.relu ? f16x2_relu_sat(v2, v3) : f16x2_sat(v2, v3);
           }
-          st_global_v8(p.out_hi + pix * p.Cout + co0, hi4[0], hi4[1]);
+          st_global_v8(P_.out_hi + pix * P_.Cout + co0, hi4[0], hi4[1]);
         }
       }
       tc_fence_before();

@@ -273,11 +273,17 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
   } else {
     // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 * (w % 4) .. + 31 (thread t <-> tile position t); the two warps of
     // a quadrant ("halves") take alternate 16-channel batches of the work list =====
+    // (launch parameters used in the loops below are copied into registers once: the epilogue is instruction-bound, and reloading them
+    // from the parameter bank after every asm barrier cost a third of its instructions in the implicit-GEMM kernel)
+    struct { int H, W, pad, BW, BH, tiles_x, rows_y, num_work, row_mode, RB, relu, noemit; unsigned stage_bytes; const uint8_t* mask;
+             __half* out_hi; __half* out_lo; } const P_ = {p.H, p.W, p.pad, p.BW, p.BH, p.tiles_x, p.rows_y, p.num_work, p.row_mode, p.RB, p.relu,
+                                                       p.noemit, p.stage_bytes, p.mask, p.out_hi, p.out_lo};
+    const ShGroup grp_[SH_MAX_GROUPS] = {p.grp[0], p.grp[1], p.grp[2]};
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int t = quad * 32 + lane;
-    const int tj = p.row_mode ? 0 : t / p.BW, txx = p.row_mode ? t : t - tj * p.BW;
-    const long long cs = (long long)p.H * p.W;
+    const int tj = P_.row_mode ? 0 : t / P_.BW, txx = P_.row_mode ? t : t - tj * P_.BW;
+    const long long cs = (long long)P_.H * P_.W;
     uint32_t tile_it = 0;
     int off = 0;                                           // ring offset of logical buffer row 0
     // register-shuffle epilogue (64-channel 3x3, whole-row tiles): this warp's 32 biases live in registers for the whole kernel
@@ -288,37 +294,37 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
 #pragma unroll
       for (int c = 0; c < 32; ++c) r_bias[c] = s_bias[half * 32 + c];
     }
-    for (int work = blockIdx.x; work < p.num_work; work += gridDim.x) {
-      const int n = work / p.rows_y, y0 = (work - n * p.rows_y) * p.BH;
-      for (int tx = 0; tx < p.tiles_x; ++tx, ++tile_it) {
+    for (int work = blockIdx.x; work < P_.num_work; work += gridDim.x) {
+      const int n = work / P_.rows_y, y0 = (work - n * P_.rows_y) * P_.BH;
+      for (int tx = 0; tx < P_.tiles_x; ++tx, ++tile_it) {
         const uint32_t acc = ACC == 2 ? (tile_it & 1u) : 0u;
         const uint32_t acc_phase = ACC == 2 ? ((tile_it >> 1) & 1u) : (tile_it & 1u);
         mbar_wait(tmem_full(acc), acc_phase);
         tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)COLS;
         if constexpr (OUTMODE == 1 && TAPS == 3 && O0 == 64 && NG == 1) {
-          if (p.row_mode) {
+          if (P_.row_mode) {
             // ---- 3x3, 64 channels, whole-row tiles: shift-add in REGISTERS.  out[x] = Z[x-1][tap 0] + Z[x][tap 1] + Z[x+1][tap 2]:
             // the neighbours' values come by warp shuffle, only warp / tile edges go through shared memory.  (The smem row
             // buffer of the generic path below competes with the tensor core for the shared-memory pipe: measured 48 % LSU +
             // 24 % UMMA wavefronts on c0_conv.2.)  The last pixel of a tile waits for the next tile's first pixel ("pend").
-            const bool first = tx == 0, last = tx == p.tiles_x - 1;
+            const bool first = tx == 0, last = tx == P_.tiles_x - 1;
             const uint32_t par = tile_it & 1u;
             float* e0 = s_edge + par * 256u;                 // tap-0 values of lane 31 of every quadrant, [quad][64], double-buffered
             const float* e0_prev = s_edge + (par ^ 1u) * 256u;
             float* e2 = s_edge + 512;                        // tap-2 values of lane 0 of every quadrant
             float* pend = s_edge + 768;                      // partial sum of the previous tile's last pixel
             const int cb = half * 32;                        // this warp's 32 channels
-            const ShGroup& G = p.grp[0];
+            const ShGroup& G = grp_[0];
             // Finished pixels leave through a staging tile in shared memory and ONE TMA store per plane and tile: a lane-per-pixel
             // direct store writes 16 B per lane at a 128-byte stride, i.e. 32 partial-sector L2 transactions per instruction, and
             // that alone cost half of the kernel time (c0_conv.2: 2.25 ms with, 1.14 ms without the stores).  Staging row j holds
             // pixel x0 + j for j < 127; the tile's last pixel waits in "pend" and is stored directly by the next tile.
-            const bool staged = p.stage_bytes != 0;
+            const bool staged = P_.stage_bytes != 0;
             auto emit32 = [&](const float* v, long long pix, int srow) __attribute__((always_inline)) {
-              if (p.noemit) return;
-              const bool has_mask = p.mask != nullptr;                    // uniform: the forward_seg atlases only
-              const bool keep = !has_mask || p.mask[pix] != 0;
+              if (P_.noemit) return;
+              const bool has_mask = P_.mask != nullptr;                    // uniform: the forward_seg atlases only
+              const bool keep = !has_mask || P_.mask[pix] != 0;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 uint4 h4, l4;
@@ -328,24 +334,24 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                 for (int e = 0; e < 4; ++e) {
                   float a = fmaf(v[8 * k + 2 * e], G.inv_scale, r_bias[8 * k + 2 * e]);
                   float bq = fmaf(v[8 * k + 2 * e + 1], G.inv_scale, r_bias[8 * k + 2 * e + 1]);
-                  if (p.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
+                  if (P_.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
                   if (has_mask) { a = keep ? a : 0.f; bq = keep ? bq : 0.f; }
-                  if (p.out_lo != nullptr) split_f16x2(a, bq, hh[e], ll[e]);
+                  if (P_.out_lo != nullptr) split_f16x2(a, bq, hh[e], ll[e]);
                   else hh[e] = f16x2_sat(a, bq);
                 }
                 if (srow >= 0) {                               // 128-byte swizzle of the store's tensor map: 16-byte piece j of row r at (j ^ (r & 7))
                   const uint32_t a0 = stage + (uint32_t)srow * 128u + ((((uint32_t)(half * 4 + k)) ^ ((uint32_t)srow & 7u)) << 4);
                   st_shared_v4(a0, h4);
-                  if (p.out_lo != nullptr) st_shared_v4(a0 + 16384u, l4);
+                  if (P_.out_lo != nullptr) st_shared_v4(a0 + 16384u, l4);
                 } else {
-                  *reinterpret_cast<uint4*>(p.out_hi + pix * 64 + cb + 8 * k) = h4;
-                  if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * 64 + cb + 8 * k) = l4;
+                  *reinterpret_cast<uint4*>(P_.out_hi + pix * 64 + cb + 8 * k) = h4;
+                  if (P_.out_lo != nullptr) *reinterpret_cast<uint4*>(P_.out_lo + pix * 64 + cb + 8 * k) = l4;
                 }
               }
             };
             if (staged && warp == 2 && lane == 0) bulk_wait_read0();   // the previous tile's TMA stores have read the staging tile
             __syncwarp();                                              // (tcgen05.ld below is warp-collective)
-            const long long pix0 = ((long long)n * p.H + y0) * p.W + (long long)tx * 128;
+            const long long pix0 = ((long long)n * P_.H + y0) * P_.W + (long long)tx * 128;
             float z0[32], z2[32];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -414,9 +420,9 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
             }
             if (staged) fence_proxy_async_smem();
             epi_bar();
-            if (staged && warp == 2 && lane == 0 && !p.noemit) {
+            if (staged && warp == 2 && lane == 0 && !P_.noemit) {
               tma_store_4d(&p.o_map[0], stage, 0, tx * 128, y0, n);                  // pixels x0 .. x0 + 126
-              if (p.out_lo != nullptr) tma_store_4d(&p.o_map[1], stage + 16384u, 0, tx * 128, y0, n);
+              if (P_.out_lo != nullptr) tma_store_4d(&p.o_map[1], stage + 16384u, 0, tx * 128, y0, n);
               bulk_commit();
             }
             __syncwarp();
@@ -427,9 +433,9 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
         static_for<0, TAPS>([&](auto Sx) __attribute__((always_inline)) {
           constexpr int s = decltype(Sx)::value;
           int L; bool valid = true;
-          if (p.row_mode) { L = t - s + 2 * p.pad; }
-          else { const int x2 = txx - s + p.pad; valid = x2 >= 0 && x2 < p.BW; L = tj * p.BW + x2; }
-          int phys = L + off; if (phys >= p.RB) phys -= p.RB;
+          if (P_.row_mode) { L = t - s + 2 * P_.pad; }
+          else { const int x2 = txx - s + P_.pad; valid = x2 >= 0 && x2 < P_.BW; L = tj * P_.BW + x2; }
+          int phys = L + off; if (phys >= P_.RB) phys -= P_.RB;
           float* row = buf + (valid ? phys : 0) * RS;
           // batch by batch (<= 16 channels): TMEM loads -> wait -> smem loads -> adds -> stores
           static_for<0, Cfg::NBT>([&](auto Bx) __attribute__((always_inline)) {
@@ -465,16 +471,16 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
           epi_bar();
         });
         // ---- emit the finished pixels (and clear their buffer rows) ----
-        const bool last = tx == p.tiles_x - 1;
-        const int nL = p.row_mode ? (last ? p.RB : 128) : 128;
+        const bool last = tx == P_.tiles_x - 1;
+        const int nL = P_.row_mode ? (last ? P_.RB : 128) : 128;
         for (int L = t; L < nL; L += 128) {
-          int phys = L + off; if (phys >= p.RB) phys -= p.RB;
+          int phys = L + off; if (phys >= P_.RB) phys -= P_.RB;
           float* row = buf + phys * RS;
           int y, x; bool inside;
-          if (p.row_mode) { y = y0; x = tx * 128 + L - p.pad; inside = x >= 0 && x < p.W; }
-          else { const int jj = L / p.BW; y = y0 + jj; x = L - jj * p.BW; inside = y < p.H; }
-          const long long pix = ((long long)n * p.H + y) * p.W + x;
-          const bool keep = OUTMODE == 1 && inside && (p.mask == nullptr || p.mask[pix] != 0);
+          if (P_.row_mode) { y = y0; x = tx * 128 + L - P_.pad; inside = x >= 0 && x < P_.W; }
+          else { const int jj = L / P_.BW; y = y0 + jj; x = L - jj * P_.BW; inside = y < P_.H; }
+          const long long pix = ((long long)n * P_.H + y) * P_.W + x;
+          const bool keep = OUTMODE == 1 && inside && (P_.mask == nullptr || P_.mask[pix] != 0);
           static_for<0, Cfg::NBT>([&](auto Bx) __attribute__((always_inline)) {
             constexpr int b = decltype(Bx)::value;
             constexpr int g = Cfg::b_group(b), c_lo = Cfg::b_lo(b), c_n = Cfg::b_n(b), b0 = Cfg::bufcol(g), no = Cfg::n_out(g);
@@ -484,10 +490,10 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               for (int e = 0; e < c_n; ++e) v[e] = row[b0 + c_lo + e];
 #pragma unroll
               for (int e = 0; e < c_n; ++e) row[b0 + c_lo + e] = 0.f;
-              const ShGroup& G = p.grp[g];
+              const ShGroup& G = grp_[g];
               if (inside) {
                 if (OUTMODE == 0) {
-                  float* dst = G.out32 + (((long long)n * no + c_lo) * p.H + y) * p.W + x;
+                  float* dst = G.out32 + (((long long)n * no + c_lo) * P_.H + y) * P_.W + x;
 #pragma unroll
                   for (int e = 0; e < c_n; ++e) {
                     float o = fmaf(v[e], G.inv_scale, s_bias[b0 + c_lo + e]);
@@ -506,19 +512,19 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                     for (int e = 0; e < 4; ++e) {
                       float a = fmaf(v[c0 + 2 * e], G.inv_scale, s_bias[b0 + c_lo + c0 + 2 * e]);
                       float bq = fmaf(v[c0 + 2 * e + 1], G.inv_scale, s_bias[b0 + c_lo + c0 + 2 * e + 1]);
-                      if (p.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
+                      if (P_.relu) { a = fmaxf(a, 0.f); bq = fmaxf(bq, 0.f); }
                       if (!keep) { a = 0.f; bq = 0.f; }
                       split_f16x2(a, bq, hh[e], ll[e]);
                     }
-                    *reinterpret_cast<uint4*>(p.out_hi + pix * no + c_lo + c0) = h4;
-                    if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + pix * no + c_lo + c0) = l4;
+                    *reinterpret_cast<uint4*>(P_.out_hi + pix * no + c_lo + c0) = h4;
+                    if (P_.out_lo != nullptr) *reinterpret_cast<uint4*>(P_.out_lo + pix * no + c_lo + c0) = l4;
                   });
                 }
               }
             }
           });
         }
-        if (p.row_mode) { off += 128; if (off >= p.RB) off -= p.RB; }
+        if (P_.row_mode) { off += 128; if (off >= P_.RB) off -= P_.RB; }
         epi_bar();
       }
     }
