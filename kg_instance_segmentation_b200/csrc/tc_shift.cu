@@ -33,6 +33,10 @@
 namespace kg {
 
 constexpr int SH_THREADS = 320;              // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue (two per TMEM lane quadrant)
+// The 7x7 head kernel runs FOUR epilogue warps per TMEM lane quadrant (576 threads): its 464 accumulator columns fit TMEM once, so
+// the tensor core idles while the epilogue holds the accumulators (ncu: 40 % tensor pipe, epilogue warps 23 % of their samples waiting
+// for the MMA and vice versa); the shift-add phase is latency-bound, more warps shorten it.
+__host__ __device__ constexpr int sh_epi_warps(int outmode, int taps) { return (outmode == 0 && taps == 7) ? 16 : 8; }
 constexpr int SH_MAX_UNITS = 6, SH_MAX_TAPS = 8, SH_MAX_CHUNKS = 16;
 constexpr int SH_BK = 64;
 constexpr int SH_A_TILE = 128 * SH_BK * 2;   // 16 KiB
@@ -82,6 +86,7 @@ struct ShCfg {
   static constexpr int b_lo(int b) { int g = 0; while (b >= nbatch(g)) { b -= nbatch(g); ++g; } return b * 16; }
   static constexpr int b_n(int b) { return n_out(b_group(b)) - b_lo(b) < 16 ? n_out(b_group(b)) - b_lo(b) : 16; }
   static constexpr int last_batch_of_half(int h) { int l = -1; for (int b = 0; b < NBT; ++b) if ((b & 1) == h) l = b; return l; }
+  static constexpr int last_batch_of_part(int q, int nparts) { int l = -1; for (int b = 0; b < NBT; ++b) if (b % nparts == q) l = b; return l; }
   static constexpr int NU = (O0 > 0 ? units_of(0) : 0) + (O1 > 0 ? units_of(1) : 0) + (O2 > 0 ? units_of(2) : 0);
   static constexpr int COLS = col0(NG);
   static constexpr int NOUT = bufcol(NG);
@@ -110,14 +115,17 @@ __device__ __forceinline__ void static_for(F&& f) {
   if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NTHREADS = 256>
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 // OUTMODE 0: fp32 NCHW per conv (+sigmoid); OUTMODE 1: conv 0 -> split-fp16 NHWC (+ReLU, +mask)
 // PASSES 1: fp16 x fp16; 2: (hi + lo activations) x hi weights; 3: split-fp16 on both sides (hi*hi + lo*hi + hi*lo).
 // WRES: the whole weight tensor stays resident in shared memory (loaded once per CTA); the ring then carries activations only.
 template <int O0, int O1, int O2, int TAPS, int PASSES, int OUTMODE, bool WRES>
-__global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_constant__ ShParams p) {
+__global__ void __launch_bounds__(64 + 32 * sh_epi_warps(OUTMODE, TAPS), 1) tc_shift_kernel(const __grid_constant__ ShParams p) {
   using Cfg = ShCfg<O0, O1, O2, TAPS>;
+  constexpr int EW = sh_epi_warps(OUTMODE, TAPS);            // epilogue warps
+  constexpr int NPART = EW / 4;                              // epilogue warps per TMEM lane quadrant: batch b belongs to part b % NPART
   static_assert(Cfg::linear(), "tap columns must be linear");
   static_assert(OUTMODE == 0 || (Cfg::NG == 1 && O0 % 8 == 0), "NHWC output: one conv, Cout a multiple of 8");
   constexpr int NU = Cfg::NU, NG = Cfg::NG, RS = Cfg::RS, COLS = Cfg::COLS;
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.NS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), EW); }
     mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -165,10 +173,10 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2) {
-    for (int e = threadIdx.x - 64; e < p.RB * RS; e += 256) buf[e] = 0.f;
+    for (int e = threadIdx.x - 64; e < p.RB * RS; e += 32 * EW) buf[e] = 0.f;
     static_for<0, NG>([&](auto Gx) __attribute__((always_inline)) {
       constexpr int g = decltype(Gx)::value;
-      for (int e = threadIdx.x - 64; e < Cfg::n_out(g); e += 256) s_bias[Cfg::bufcol(g) + e] = p.grp[g].bias[e];
+      for (int e = threadIdx.x - 64; e < Cfg::n_out(g); e += 32 * EW) s_bias[Cfg::bufcol(g) + e] = p.grp[g].bias[e];
     });
   }
   tc_fence_before();
@@ -280,7 +288,8 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                                                        p.noemit, p.stage_bytes, p.mask, p.out_hi, p.out_lo};
     const ShGroup grp_[SH_MAX_GROUPS] = {p.grp[0], p.grp[1], p.grp[2]};
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;                     // which of the NPART warps of this quadrant ("half" in the two-part kernels)
+    const int part = half;
     const int t = quad * 32 + lane;
     const int tj = P_.row_mode ? 0 : t / P_.BW, txx = P_.row_mode ? t : t - tj * P_.BW;
     const long long cs = (long long)P_.H * P_.W;
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
           static_for<0, Cfg::NBT>([&](auto Bx) __attribute__((always_inline)) {
             constexpr int b = decltype(Bx)::value;
             constexpr int g = Cfg::b_group(b), c_lo = Cfg::b_lo(b), c_n = Cfg::b_n(b), b0 = Cfg::bufcol(g), nch = (c_n + 7) / 8;
-            if ((b & 1) == half) {
+            if ((b % NPART) == part) {
               uint32_t raw[nch][8];
               static_for<0, nch>([&](auto Cx) __attribute__((always_inline)) {
                 constexpr int c = decltype(Cx)::value;
@@ -449,7 +458,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
                 tmem_ld8_nowait(lane_addr + col, raw[c]);
               });
               tmem_ld_wait();
-              if (s == TAPS - 1 && b == Cfg::last_batch_of_half(b & 1)) {   // this warp has read all of its columns of Z
+              if (s == TAPS - 1 && b == Cfg::last_batch_of_part(b % NPART, NPART)) {   // this warp has read all of its columns of Z
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
@@ -463,12 +472,17 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
               }
             }
           });
-          if (Cfg::last_batch_of_half(1) < 0 && half == 1 && s == TAPS - 1) {   // a half without work still releases the accumulators
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
+          if (s == TAPS - 1) {                                  // a part without work still releases the accumulators
+            static_for<0, NPART>([&](auto Qx) __attribute__((always_inline)) {
+              constexpr int q = decltype(Qx)::value;
+              if (Cfg::last_batch_of_part(q, NPART) < 0 && part == q) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty(acc)) : "memory");
+              }
+            });
           }
-          epi_bar();
+          epi_bar<32 * EW>();
         });
         // ---- emit the finished pixels (and clear their buffer rows) ----
         const bool last = tx == P_.tiles_x - 1;
@@ -484,7 +498,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
           static_for<0, Cfg::NBT>([&](auto Bx) __attribute__((always_inline)) {
             constexpr int b = decltype(Bx)::value;
             constexpr int g = Cfg::b_group(b), c_lo = Cfg::b_lo(b), c_n = Cfg::b_n(b), b0 = Cfg::bufcol(g), no = Cfg::n_out(g);
-            if ((b & 1) == half) {
+            if ((b % NPART) == part) {
               float v[c_n];
 #pragma unroll
               for (int e = 0; e < c_n; ++e) v[e] = row[b0 + c_lo + e];
@@ -525,7 +539,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) tc_shift_kernel(const __grid_co
           });
         }
         if (P_.row_mode) { off += 128; if (off >= P_.RB) off -= P_.RB; }
-        epi_bar();
+        epi_bar<32 * EW>();
       }
     }
   }
@@ -760,7 +774,7 @@ int tc_shift_launch(const TcShiftOp* op, float* const* out32, cudaStream_t strea
   }
 #define KG_SH_LAUNCH(...) tc_shift_kernel<__VA_ARGS__><<<op->grid, SH_THREADS, op->smem_bytes, stream>>>(p)
   switch (kernel_of(op)) {
-    case SHK_HEADS: KG_SH_LAUNCH(5, 10, 40, 7, 1, 0, false); break;
+    case SHK_HEADS: tc_shift_kernel<5, 10, 40, 7, 1, 0, false><<<op->grid, 64 + 32 * sh_epi_warps(0, 7), op->smem_bytes, stream>>>(p); break;
     case SHK_C64:
       if (op->wres) { if (op->passes == 3) KG_SH_LAUNCH(64, 0, 0, 3, 3, 1, true); else if (op->passes == 2) KG_SH_LAUNCH(64, 0, 0, 3, 2, 1, true); else KG_SH_LAUNCH(64, 0, 0, 3, 1, 1, true); }
       else { if (op->passes == 3) KG_SH_LAUNCH(64, 0, 0, 3, 3, 1, false); else if (op->passes == 2) KG_SH_LAUNCH(64, 0, 0, 3, 2, 1, false); else KG_SH_LAUNCH(64, 0, 0, 3, 1, 1, false); }
