@@ -103,7 +103,7 @@ struct SegPlan {
     size_t mask = 0;                               // byte offset of the uint8 validity mask
     std::vector<ResizeProb> crop, deepest, up;     // feature crop -> P; P -> C for boxes whose deepest level this is; pre -> U
     std::vector<RectProb> rects;
-    int pix_crop = 0, pix_deepest = 0, pix_up = 0;
+    int pix_crop = 0, pix_deepest = 0, pix_up = 0;   // largest problem of each list: rows (crop, deepest) / framed pixels (up)
   } lv[5];
   size_t mask_base = 0;                            // byte offset of the mask region inside the seg workspace
   // problem lists of every launch, packed into ONE blob: built by seg_prepare in pinned host memory, copied by forward_seg
@@ -928,14 +928,14 @@ static int seg_prepare_atlas(Net* net, int N, int H, int W, const int* counts, c
       ResizeProb cp{};      // exact copy (same size) of the feature crop into the atlas
       cp.in_off = (((long long)sb.img * fh[l] + sb.rect[l][0]) * fw[l] + sb.rect[l][1]) * kFeatC[l]; cp.in_pitch = fw[l] * kFeatC[l];
       cp.Hin = h; cp.Win = w; cp.Hout = h; cp.Wout = w; cp.out_off = (long long)L.P + apos * kFeatC[l]; cp.out_pitch = L.WA * kFeatC[l];
-      L.crop.push_back(cp); L.pix_crop = std::max(L.pix_crop, h * w);
+      L.crop.push_back(cp); L.pix_crop = std::max(L.pix_crop, h);
       RectProb rp{}; rp.off = apos; rp.h = h; rp.w = w; rp.pitch = L.WA;
       L.rects.push_back(rp);
       if (l == sb.L - 1 && l < 4) {     // deepest level of this box: its running tensor is the raw crop (mask_forward, KGnet.py:261-262)
         ResizeProb dp = cp;
         dp.in_off = (long long)L.P + apos * kFeatC[l]; dp.in_pitch = L.WA * kFeatC[l];
         dp.out_off = (long long)L.Cc + apos * kSegOut[l]; dp.out_pitch = L.WA * kSegOut[l];
-        L.deepest.push_back(dp); L.pix_deepest = std::max(L.pix_deepest, h * w);
+        L.deepest.push_back(dp); L.pix_deepest = std::max(L.pix_deepest, h);
       }
       if (l + 1 < sb.L) {               // pre(level l+1) -> bilinear -> U_l (KGnet.py:110)
         SegPlan::Level& D = sp.lv[l + 1];
@@ -945,7 +945,8 @@ static int seg_prepare_atlas(Net* net, int N, int H, int W, const int* counts, c
         const int Cs = kSegUpIn[l];
         up.in_off = (long long)(l + 1 == 4 ? D.P : D.Cc) + dpos * Cs; up.in_pitch = D.WA * Cs; up.Hin = dh; up.Win = dw;
         up.Hout = h; up.Wout = w; up.out_off = (long long)L.U + apos * Cs; up.out_pitch = L.WA * Cs;
-        L.up.push_back(up); L.pix_up = std::max(L.pix_up, h * w);
+        up.frame = 1;                   // + the ring of zeros the 3x3 `up` conv reads around the box (the gaps are >= 1 px wide)
+        L.up.push_back(up); L.pix_up = std::max(L.pix_up, (h + 2) * (w + 2));
       }
     }
     if (sb.L > 0) {
@@ -1008,8 +1009,8 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
     auto& L = sp.lv[l];
     if (L.crop.empty()) continue;
     const Tensor& f = p->tensors[p->feat_ids[l]];
-    KG_TRY(launch_bilinear(P.hi(f), lo_of(l) ? P.lo(f) : nullptr, f.C, s_hi, lo_of(l), f.C, f.C, reinterpret_cast<const ResizeProb*>(dp + o_crop[l]),
-                           (int)L.crop.size(), L.pix_crop, stream));
+    KG_TRY(launch_copy_rects(P.hi(f), lo_of(l) ? P.lo(f) : nullptr, f.C, s_hi, lo_of(l), f.C, f.C,
+                             reinterpret_cast<const ResizeProb*>(dp + o_crop[l]), (int)L.crop.size(), L.pix_crop, stream));
     KG_TRY(launch_fill_rects(masks + L.mask, reinterpret_cast<const RectProb*>(dp + o_rect[l]), (int)L.rects.size(), stream));
     launches += 2;
   }
@@ -1048,9 +1049,8 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
     if (L.HA == 0) continue;
     __half* lo = lo_of(l);
     if (!L.up.empty()) {
-      const size_t ubytes = (size_t)L.HA * L.WA * kSegUpIn[l] * sizeof(__half);
-      KG_CUDA_CHECK(cudaMemsetAsync(s_hi + L.U, 0, ubytes, stream));
-      if (lo) KG_CUDA_CHECK(cudaMemsetAsync(lo + L.U, 0, ubytes, stream));
+      // U_l is written inside the boxes that have a deeper level plus a one-pixel frame of zeros around each (ResizeProb::frame); every
+      // other pixel of U_l stays uninitialised: valid conv outputs never read it and the outputs computed there are masked to zero
       KG_TRY(launch_bilinear(s_hi, lo_of(l + 1), kSegUpIn[l], s_hi, lo, kSegUpIn[l], kSegUpIn[l], reinterpret_cast<const ResizeProb*>(dp + o_up[l]),
                              (int)L.up.size(), L.pix_up, stream));
       ++launches;
@@ -1064,8 +1064,8 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
       if (lo) KG_CUDA_CHECK(cudaMemsetAsync(lo + L.Cc, 0, cbytes, stream));
     }
     if (!L.deepest.empty()) {
-      KG_TRY(launch_bilinear(s_hi, lo, kFeatC[l], s_hi, lo, kSegOut[l], kFeatC[l], reinterpret_cast<const ResizeProb*>(dp + o_deep[l]),
-                             (int)L.deepest.size(), L.pix_deepest, stream));
+      KG_TRY(launch_copy_rects(s_hi, lo, kFeatC[l], s_hi, lo, kSegOut[l], kFeatC[l], reinterpret_cast<const ResizeProb*>(dp + o_deep[l]),
+                               (int)L.deepest.size(), L.pix_deepest, stream));
       ++launches;
     }
   }

@@ -35,6 +35,8 @@ struct ConvArgs {
 struct ResizeProb {
   long long in_off, out_off;
   int Hin, Win, in_pitch, Hout, Wout, out_pitch;
+  int frame;       // 1: additionally write a one-pixel frame of zeros around the Hout x Wout output rectangle (forward_seg atlases: the
+  int pad_;        //    zero padding the following 3x3 conv reads), instead of clearing the whole atlas beforehand
 };
 
 struct RectProb { long long off; int h, w, pitch; };
@@ -46,6 +48,9 @@ int launch_stem_conv(const float* x, const float* w, const float* bias, __half* 
                      int stride, cudaStream_t s);
 int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
                     const ResizeProb* probs, int nprob, int max_pix, cudaStream_t s);
+// plain copies of rectangles between NHWC tensors (forward_seg: feature crops into the atlases): Hout x Wout pixels x C channels each
+int launch_copy_rects(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
+                      const ResizeProb* probs, int nprob, int max_h, cudaStream_t s);
 int launch_bilinear2x(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int N, int Hin, int Win, int C, cudaStream_t s);
 int launch_maxpool3x3s2(const __half* in_hi, const __half* in_lo, __half* out_hi, __half* out_lo, int N, int Hin, int Win,
                         int C, cudaStream_t s);

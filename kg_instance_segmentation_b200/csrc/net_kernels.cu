@@ -245,12 +245,20 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict_
                                                        int out_ps, int C, const ResizeProb* __restrict__ probs) {
   const ResizeProb pb = probs[blockIdx.z];
   const int cg = C >> 3;   // channel octets: one 16-byte load per plane per corner
-  const unsigned total = (unsigned)pb.Hout * (unsigned)pb.Wout * (unsigned)cg;   // < 2^31 (checked by the launcher): 32-bit index math
+  const int fr = pb.frame;                                   // 0 / 1: output rectangle grown by a frame of zeros
+  const int Wf = pb.Wout + 2 * fr, Hf = pb.Hout + 2 * fr;
+  const unsigned total = (unsigned)Hf * (unsigned)Wf * (unsigned)cg;   // < 2^31 (checked by the launcher): 32-bit index math
   const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int q = (int)(e / (unsigned)cg);
   const int c = (int)(e - (unsigned)q * (unsigned)cg) * 8;
-  const int oy = q / pb.Wout, ox = q - oy * pb.Wout;
+  const int oy = q / Wf - fr, ox = q - (q / Wf) * Wf - fr;
+  if (oy < 0 || ox < 0 || oy >= pb.Hout || ox >= pb.Wout) {   // frame pixel
+    const long long o = pb.out_off + (long long)oy * pb.out_pitch + (long long)ox * out_ps + c;
+    *reinterpret_cast<uint4*>(out_hi + o) = make_uint4(0u, 0u, 0u, 0u);
+    if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + o) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
   const float rh = (float)pb.Hin / (float)pb.Hout, rw = (float)pb.Win / (float)pb.Wout;
   float sy = rh * ((float)oy + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
   float sx = rw * ((float)ox + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
@@ -355,8 +363,43 @@ int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half*
   if (nprob <= 0 || max_pix <= 0) return KG_OK;
   KG_REQUIRE((C & 7) == 0 && (in_ps & 7) == 0 && (out_ps & 7) == 0, "bilinear: channel counts must be multiples of 8 (C=%d)", C);
   KG_REQUIRE((long long)max_pix * (C >> 3) < (1ll << 31), "bilinear: problem too large (%d pixels x %d channels)", max_pix, C);
+  // (max_pix must count the frame pixels of framed problems)
   dim3 grid((unsigned)(((long long)max_pix * (C >> 3) + 255) / 256), 1, nprob);
   bilinear_kernel<<<grid, 256, 0, s>>>(in_hi, in_lo, in_ps, out_hi, out_lo, out_ps, C, probs);
+  KG_CUDA_CHECK(cudaGetLastError());
+  return KG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rectangle copies between NHWC tensors (forward_seg: the feature crops of every box and level into the atlases).  A rectangle is Hout
+// rows of Wout * C contiguous halfs on both sides: one CTA copies 4 rows with 16-byte vectors.
+constexpr int CR_ROWS = 4;
+__global__ void __launch_bounds__(256) copy_rects_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int in_ps,
+                                                         __half* __restrict__ out_hi, __half* __restrict__ out_lo, int out_ps, int C,
+                                                         const ResizeProb* __restrict__ probs) {
+  const ResizeProb pb = probs[blockIdx.z];
+  const int r0 = blockIdx.x * CR_ROWS;
+  if (r0 >= pb.Hout) return;
+  const int cg = C >> 3;
+  const int vecs = pb.Wout * cg;                              // 16-byte vectors per row and plane
+  const int rows = min(CR_ROWS, pb.Hout - r0);
+  for (int e = threadIdx.x; e < rows * vecs; e += 256) {
+    const int r = e / vecs, v = e - r * vecs;
+    const int x = v / cg, c = (v - x * cg) * 8;
+    const long long i = pb.in_off + (long long)(r0 + r) * pb.in_pitch + (long long)x * in_ps + c;
+    const long long o = pb.out_off + (long long)(r0 + r) * pb.out_pitch + (long long)x * out_ps + c;
+    *reinterpret_cast<uint4*>(out_hi + o) = __ldg(reinterpret_cast<const uint4*>(in_hi + i));
+    if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + o) = __ldg(reinterpret_cast<const uint4*>(in_lo + i));
+  }
+}
+
+int launch_copy_rects(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
+                      const ResizeProb* probs, int nprob, int max_h, cudaStream_t s) {
+  if (nprob <= 0 || max_h <= 0) return KG_OK;
+  KG_REQUIRE((C & 7) == 0 && (in_ps & 7) == 0 && (out_ps & 7) == 0, "copy_rects: channel counts must be multiples of 8 (C=%d)", C);
+  KG_REQUIRE(nprob <= 65535, "copy_rects: too many rectangles (%d)", nprob);
+  dim3 grid((unsigned)ceil_div(max_h, CR_ROWS), 1, (unsigned)nprob);
+  copy_rects_kernel<<<grid, 256, 0, s>>>(in_hi, in_lo, in_ps, out_hi, out_lo, out_ps, C, probs);
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;
 }
