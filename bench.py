@@ -201,6 +201,13 @@ def run_decode(args, rank, world, dist):
         step_device()
     st_ms, st_cnt = _cabi.timing_collect()
     _cabi.timing_enable(False)
+    # device idle time between the last decode kernel and the first forward_seg launch (D2H of the boxes, host unpack, atlas planning)
+    engine.gap_events = []
+    for _ in range(args.steps):
+        step_device()
+    torch.cuda.synchronize()
+    gaps = [a.elapsed_time(b) for a, b in engine.gap_events]
+    engine.gap_events = None
     px = BS * sum(h * w for h, w in shapes)
     names = {0: "vote_kernel", 1: "blur32_candidates_kernel + exact_peaks_kernel", 2: "group_kernel", 3: "nms_kernel"}
     stage = {names[i]: {"ms_per_step": float(st_ms[i]) / args.steps, "launches_per_step": int(st_cnt[i]) // args.steps} for i in names}
@@ -435,6 +442,13 @@ def run_pipeline(args, rank, world, dist):
         step_device()
     st_ms, st_cnt = _cabi.timing_collect()
     _cabi.timing_enable(False)
+    # device idle time between the last decode kernel and the first forward_seg launch (D2H of the boxes, host unpack, atlas planning)
+    engine.gap_events = []
+    for _ in range(args.steps):
+        step_device()
+    torch.cuda.synchronize()
+    gaps = [a.elapsed_time(b) for a, b in engine.gap_events]
+    engine.gap_events = None
     info = np.zeros(8, np.float64)
     _cabi.check(_cabi.lib().kg_net_plan_info(engine.model._handle, info.ctypes.data, 8))
     stages = {STAGE_NAMES[i]: {"ms_per_step": round(float(st_ms[i]) / args.steps, 4), "launches_per_step": int(st_cnt[i]) // args.steps}
@@ -462,7 +476,8 @@ def run_pipeline(args, rank, world, dist):
                 "peak_kind": pk_kind + " (cuBLAS bf16 sustained; kernel timed inside a long step)",
                 "algorithmic_flops_per_step": info[0], "launches_per_step": tc_launches, "avg_launch_ms": round(tc_ms / max(1, tc_launches), 4),
                 "cuda_core_conv_flops_per_step": info[1], "whole_step_tflops": round(whole, 1), "whole_step_frac": round(whole / peak_tf, 4),
-                "per_class": per_class, "stages": stages}
+                "per_class": per_class, "stages": stages,
+                "host_gap_ms_per_step": round(float(np.mean(gaps)), 4) if gaps else None}
     gbs = world * BS
     out = {
         "metric": METRIC, "value": round(gbs * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -512,7 +527,7 @@ def cpu_pipeline(base, n_images, warm=0):
         one(i)
     dt = time.time() - t0
     return {"value": round(n_images / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_images} image(s) 512x512 of the same workload, bs=1 like test.py: torch fp32 forward_dec on {cores} threads + "
+            "sample": f"{n_images} image(s) {HW_IN}x{HW_IN} of the same workload, bs=1 like test.py: torch fp32 forward_dec on {cores} threads + "
                       "NumPy decode (1 thread) + forward_seg (oracle/kg_oracle.py)", "seconds": round(dt, 2)}
 
 

@@ -231,6 +231,19 @@ int kg_detection_loss(const float* d_pr_kp, const float* d_pr_short, const float
 int kg_seg_loss_pairs(const float* d_masks, const void* d_pairs, int n_pairs, const float* d_gt_masks, int H, int W,
                       float* d_pair_loss, void* stream);
 
+/* Gradient of kg_detection_loss's total with respect to the three prediction tensors (what autograd computes for loss.py:12-49:
+ * PyTorch's binary_cross_entropy backward on the keypoint maps, sign(p - t) * mask / radius / (sum(mask) + 1e-10) on the offsets).
+ * d_scratch5: the 5 sums left by kg_detection_loss on the SAME inputs; d_grad_out: upstream gradient (one device float) or NULL = 1;
+ * d_grad_*: fp32 tensors of the predictions' shapes (overwritten). */
+int kg_detection_loss_backward(const float* d_pr_kp, const float* d_pr_short, const float* d_pr_mid, const float* d_gt, int N, int H, int W,
+                               float kp_radius, const double* d_scratch5, const float* d_grad_out, float* d_grad_kp, float* d_grad_short,
+                               float* d_grad_mid, void* stream);
+
+/* Gradient of sum_k d_pair_coeff[k] * pair_loss[k] (kg_seg_loss_pairs) with respect to the mask buffer: ADDED into d_grad_masks
+ * (same indexing as d_masks; the caller clears it), autograd of seg_loss.py:84-90. */
+int kg_seg_loss_pairs_backward(const float* d_masks, const void* d_pairs, int n_pairs, const float* d_gt_masks, int H, int W,
+                               const float* d_pair_coeff, float* d_grad_masks, void* stream);
+
 /* 1 when the tcgen05/TMA path initialised on the current device; kg_tc_status() says why not otherwise. */
 int kg_tc_available(void);
 const char* kg_tc_status(void);

@@ -302,6 +302,8 @@ class ResNet(nn.Module):
                 self._seg_ws = torch.empty(int(seg_bytes.value * 1.25) + 1024, dtype=torch.uint8, device=device)
             masks = torch.empty(max(1, mask_floats.value), dtype=torch.float32, device=device)
             nl = C.c_int(0)
+            if getattr(self, "_seg_launch_event", None) is not None:
+                self._seg_launch_event.record()
             _cabi.check(L.kg_net_forward_seg(self._handle, ws.data_ptr(), self._seg_ws.data_ptr(), self._seg_ws.numel(),
                                              masks.data_ptr(), torch.cuda.current_stream().cuda_stream, C.byref(nl)))
         self.last_launches = nl.value

@@ -103,7 +103,7 @@ struct SegPlan {
     size_t mask = 0;                               // byte offset of the uint8 validity mask
     std::vector<ResizeProb> crop, deepest, up;     // feature crop -> P; P -> C for boxes whose deepest level this is; pre -> U
     std::vector<RectProb> rects;
-    int pix_crop = 0, pix_deepest = 0, pix_up = 0;   // largest problem of each list: rows (crop, deepest) / framed pixels (up)
+    int pix_crop = 0, pix_deepest = 0, pix_up = 0;   // largest problem of each list, in rows (up: framed rows)
   } lv[5];
   size_t mask_base = 0;                            // byte offset of the mask region inside the seg workspace
   // problem lists of every launch, packed into ONE blob: built by seg_prepare in pinned host memory, copied by forward_seg
@@ -946,7 +946,7 @@ static int seg_prepare_atlas(Net* net, int N, int H, int W, const int* counts, c
         up.in_off = (long long)(l + 1 == 4 ? D.P : D.Cc) + dpos * Cs; up.in_pitch = D.WA * Cs; up.Hin = dh; up.Win = dw;
         up.Hout = h; up.Wout = w; up.out_off = (long long)L.U + apos * Cs; up.out_pitch = L.WA * Cs;
         up.frame = 1;                   // + the ring of zeros the 3x3 `up` conv reads around the box (the gaps are >= 1 px wide)
-        L.up.push_back(up); L.pix_up = std::max(L.pix_up, (h + 2) * (w + 2));
+        L.up.push_back(up); L.pix_up = std::max(L.pix_up, h + 2);
       }
     }
     if (sb.L > 0) {
@@ -1051,8 +1051,8 @@ static int seg_run_atlas(Net* net, void* dec_ws, void* seg_ws, size_t seg_bytes,
     if (!L.up.empty()) {
       // U_l is written inside the boxes that have a deeper level plus a one-pixel frame of zeros around each (ResizeProb::frame); every
       // other pixel of U_l stays uninitialised: valid conv outputs never read it and the outputs computed there are masked to zero
-      KG_TRY(launch_bilinear(s_hi, lo_of(l + 1), kSegUpIn[l], s_hi, lo, kSegUpIn[l], kSegUpIn[l], reinterpret_cast<const ResizeProb*>(dp + o_up[l]),
-                             (int)L.up.size(), L.pix_up, stream));
+      KG_TRY(launch_bilinear_rows(s_hi, lo_of(l + 1), kSegUpIn[l], s_hi, lo, kSegUpIn[l], kSegUpIn[l],
+                                  reinterpret_cast<const ResizeProb*>(dp + o_up[l]), (int)L.up.size(), L.pix_up, stream));
       ++launches;
       const std::string pre = "skip_combine." + std::to_string(l);
       KG_TRY(conv(pre + ".up.0", L, L.U, kSegUpIn[l], 0, 0, L.V, kSegOut[l], nullptr, true, false));

@@ -48,6 +48,9 @@ int launch_stem_conv(const float* x, const float* w, const float* bias, __half* 
                      int stride, cudaStream_t s);
 int launch_bilinear(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
                     const ResizeProb* probs, int nprob, int max_pix, cudaStream_t s);
+// same resize, row-tiled (one CTA per two output rows of a problem): max_rows = the largest Hout (+ 2 for framed problems)
+int launch_bilinear_rows(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
+                         const ResizeProb* probs, int nprob, int max_rows, cudaStream_t s);
 // plain copies of rectangles between NHWC tensors (forward_seg: feature crops into the atlases): Hout x Wout pixels x C channels each
 int launch_copy_rects(const __half* in_hi, const __half* in_lo, int in_ps, __half* out_hi, __half* out_lo, int out_ps, int C,
                       const ResizeProb* probs, int nprob, int max_h, cudaStream_t s);

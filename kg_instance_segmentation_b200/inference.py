@@ -65,6 +65,7 @@ class InstanceHeat:
         self._decoders = {}
         self.last_launches = 0
         self.packed_k = 0        # > 0: the decode also writes the fixed-size per-image detection records (data-parallel all-gather)
+        self.gap_events = None   # a list: detect_batch appends (decode finished, forward_seg starts) CUDA event pairs (diagnostics)
 
     def load_weights(self, resume, dataset):
         """test.py:60-61."""
@@ -109,11 +110,19 @@ class InstanceHeat:
         launches += res.n_launches
         if on_decoded is not None:
             on_decoded(res)
+        gap = None
+        if self.gap_events is not None and with_masks:
+            gap = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            gap[0].record()
         dets = res.detections()                     # the one host sync of the pipeline: boxes are needed on the host
         self.last_result = res
         seg = None
         if with_masks:
+            model._seg_launch_event = gap[1] if gap is not None else None
             seg = model.forward_seg_packed(out[4], [d if d is not None else [] for d in dets])
+            model._seg_launch_event = None
+            if gap is not None and model.last_launches > 0:
+                self.gap_events.append(gap)
             if not packed:
                 seg = seg.as_lists()
             launches += model.last_launches

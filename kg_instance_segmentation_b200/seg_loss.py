@@ -2,7 +2,8 @@
 predicted and ground-truth boxes is list logic and stays on the host (seg_loss.py:48-61, float32 like the reference's torch
 scalars); every matched pair's mask BCE -- crop of the ground-truth mask, nearest-neighbour resize to the patch, mean binary
 cross entropy -- runs in ONE launch of `seg_loss_kernel` (csrc/loss.cu) instead of a cv2.resize + H2D + BCE kernel per pair.
-Forward only (the reference's validation loop, train.py:165-177)."""
+With reference-style lists of patch tensors that require grad, the result is differentiable with respect to the patches
+(`seg_loss_backward_kernel`, one launch); patches of this library's own forward_seg carry no graph (no network backward here)."""
 from __future__ import annotations
 
 import numpy as np
@@ -25,6 +26,34 @@ def _jaccard(a, b):
     inter = ih * iw
     union = area_a + area_b - inter
     return f(0.) if union <= 2 else np.divide(inter, union)
+
+
+class _PairLoss(torch.autograd.Function):
+    """per-pair mean BCE of windows of `buf` (fp32, flat) against the nearest-resized ground-truth crops"""
+
+    @staticmethod
+    def forward(ctx, buf, d_rec, n_pairs, d_gt, height, width):
+        dev = buf.device
+        per_pair = torch.empty(n_pairs, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().kg_seg_loss_pairs(buf.data_ptr(), d_rec.data_ptr(), n_pairs, d_gt.data_ptr(), height, width,
+                                                      per_pair.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(buf, d_rec, d_gt)
+        ctx.geom = (n_pairs, height, width)
+        return per_pair
+
+    @staticmethod
+    def backward(ctx, grad_pairs):
+        buf, d_rec, d_gt = ctx.saved_tensors
+        n_pairs, height, width = ctx.geom
+        dev = buf.device
+        coeff = grad_pairs.detach().to(device=dev, dtype=torch.float32).contiguous()
+        grad = torch.zeros_like(buf)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().kg_seg_loss_pairs_backward(buf.data_ptr(), d_rec.data_ptr(), n_pairs, d_gt.data_ptr(), height, width,
+                                                               coeff.data_ptr(), grad.data_ptr(),
+                                                               torch.cuda.current_stream(dev).cuda_stream))
+        return grad, None, None, None, None, None
 
 
 class SEG_loss(torch.nn.Module):
@@ -65,7 +94,7 @@ class SEG_loss(torch.nn.Module):
                 r["gt_index"], r["y1"], r["x1"], r["y2"], r["x2"] = g, y1, x1, y2, x2
         else:
             uniq = sorted({pi for pi, *_ in pairs})
-            flat = [patches[pi].detach().to(torch.float32).contiguous().view(-1) for pi in uniq]
+            flat = [patches[pi].to(torch.float32).contiguous().view(-1) for pi in uniq]      # differentiable: grads flow back through cat
             starts = dict(zip(uniq, np.concatenate([[0], np.cumsum([f.numel() for f in flat])[:-1]]).tolist()))
             buf = torch.cat(flat)
             for r, (pi, patch, g, y1, x1, y2, x2) in zip(rec, pairs):
@@ -76,10 +105,7 @@ class SEG_loss(torch.nn.Module):
                 raise ValueError(f"ground-truth mask of shape {g.shape}, expected {(self.height, self.width)}")
         d_gt = torch.from_numpy(np.ascontiguousarray(np.stack(gt_list))).to(dev)
         d_rec = torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(dev)
-        per_pair = torch.empty(len(pairs), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _cabi.check(_cabi.lib().kg_seg_loss_pairs(buf.data_ptr(), d_rec.data_ptr(), len(pairs), d_gt.data_ptr(), self.height, self.width,
-                                                      per_pair.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        per_pair = _PairLoss.apply(buf, d_rec, len(pairs), d_gt, self.height, self.width)
         # loss_batch / num_obj per image, then / len(mask_patches) (:88-94): a weighted sum of the per-pair terms
         owners = np.asarray(owners)
         counts = np.bincount(owners, minlength=len(mask_patches)).astype(np.float32)

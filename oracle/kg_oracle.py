@@ -536,7 +536,7 @@ def seg_loss(predictions, gt_masks, gt_boxes, height, width):
     for i in range(len(mask_patches)):
         loss_batch, num_obj = 0., 0
         for j in range(len(mask_patches[i])):
-            patch = mask_patches[i][j].detach().cpu().to(torch.float32)
+            patch = mask_patches[i][j].cpu().to(torch.float32)          # (keeps the autograd graph of a patch that requires grad)
             pbox = np.asarray(mask_dets[i][j], np.float32)[:4]
             for k in range(len(gt_boxes[i])):
                 if jaccard(pbox, np.asarray(gt_boxes[i][k], np.float32)) >= 0.5:

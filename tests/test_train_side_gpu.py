@@ -95,6 +95,65 @@ def test_seg_loss_matches_oracle_on_forward_seg_output():
     assert seg_loss.SEG_loss(H, W)(preds, [gt_masks[0][:1], gt_masks[1]], far) is None and O.seg_loss(preds, [gt_masks[0][:1], gt_masks[1]], far, H, W) is None
 
 
+def test_detection_loss_gradient_matches_autograd_of_the_oracle():
+    """`loss.backward()` (train.py:150): gradients with respect to the three prediction tensors against torch autograd of the
+    oracle's restatement on the CPU.  fp32 elementwise formulas; the denominators are fp64 sums here: rtol 1e-5."""
+    from kg_instance_segmentation_b200 import loss
+    torch.manual_seed(1)
+    for N, H, W in ((2, 32, 48), (1, 64, 64)):
+        pr = [torch.rand(N, 5, H, W) * 0.98 + 0.01, torch.randn(N, 10, H, W) * 3, torch.randn(N, 40, H, W) * 20]
+        gt = torch.zeros(N, 55, H, W)
+        gt[:, :5] = (torch.rand(N, 5, H, W) > 0.9).float(); gt[:, 5:] = torch.randn(N, 50, H, W) * 5
+        gt[:, 5:7][:, :, :4] = pr[1][:, :2, :4]                     # exact ties: sign(0) = 0 like torch.abs' backward
+        ref_in = [t.clone().requires_grad_(True) for t in pr]
+        (O.detection_loss(ref_in, gt)[0] * 3.0).backward()
+        dev_in = [t.clone().cuda().requires_grad_(True) for t in pr]
+        got = loss.DetectionLossAll(5)(dev_in, gt.cuda())
+        assert got.requires_grad
+        (got * 3.0).backward()
+        for a, b in zip(dev_in, ref_in):
+            scale = float(b.grad.abs().max())
+            np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-5, atol=1e-6 * scale)
+    # saturated keypoint predictions: PyTorch clamps the BCE-backward denominator at 1e-12
+    pr = [torch.tensor([0.0, 1.0, 1e-8, 0.5, 1 - 1e-7]).reshape(1, 5, 1, 1).repeat(1, 1, 2, 2), torch.ones(1, 10, 2, 2), torch.ones(1, 40, 2, 2)]
+    gt = torch.zeros(1, 55, 2, 2); gt[0, 1] = 1.0; gt[0, 2, 0, 0] = 1.0
+    ref_in = [t.clone().requires_grad_(True) for t in pr]
+    O.detection_loss(ref_in, gt)[0].backward()
+    dev_in = [t.clone().cuda().requires_grad_(True) for t in pr]
+    loss.DetectionLossAll(5)(dev_in, gt.cuda()).backward()
+    for a, b in zip(dev_in, ref_in):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-5, atol=1e-30)
+    # predictions that do not require grad: a plain tensor comes back (validation loop)
+    assert not loss.DetectionLossAll(5)([t.cuda() for t in pr], gt.cuda()).requires_grad
+
+
+def test_seg_loss_gradient_matches_autograd_of_the_oracle():
+    """SEG_loss on reference-style lists of patch tensors that require grad: d loss / d patch against torch autograd of the oracle
+    (a patch matched with two ground-truth objects accumulates both terms)."""
+    from kg_instance_segmentation_b200 import seg_loss
+    H = W = 80
+    rs = np.random.RandomState(5)
+    torch.manual_seed(5)
+    gt_boxes = [np.array([[4., 6., 50., 60., 1.], [6., 8., 52., 58., 1.]], np.float32), np.array([[10., 12., 70., 64., 1.]], np.float32)]
+    gt_masks = [rs.rand(2, H, W).round().astype(np.float32), rs.rand(1, H, W).round().astype(np.float32)]
+    dets = [[np.array([5., 7., 49., 61., 0.9], np.float32), np.array([0., 0., 10., 10., 0.3], np.float32)], [np.array([11., 12., 69., 66., 0.7], np.float32)]]
+    shapes = [[(44, 54), (10, 10)], [(58, 54)]]
+    base = [[torch.rand(s) * 0.96 + 0.02 for s in per] for per in shapes]
+    ref_p = [[t.clone().requires_grad_(True) for t in per] for per in base]
+    ref = O.seg_loss([ref_p, dets], gt_masks, gt_boxes, H, W)
+    ref.backward()
+    dev_p = [[t.clone().cuda().requires_grad_(True) for t in per] for per in base]
+    got = seg_loss.SEG_loss(H, W)([dev_p, dets], gt_masks, gt_boxes)
+    np.testing.assert_allclose(float(got), float(ref), rtol=5e-6)
+    got.backward()
+    for per_d, per_r in zip(dev_p, ref_p):
+        for a, b in zip(per_d, per_r):
+            if b.grad is None:                      # the unmatched patch
+                assert a.grad is None or float(a.grad.abs().max()) == 0.0
+            else:
+                np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=2e-5, atol=1e-9)
+
+
 def test_validation_step_flow():
     """train.py:165-177 `validating` with the three imports swapped: forward(x, boxes) -> 4 x DetectionLossAll + SEG_loss."""
     from kg_instance_segmentation_b200 import KGnet, loss, preprocessing, seg_loss

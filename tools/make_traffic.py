@@ -1,11 +1,14 @@
 """profiles/<tag>_traffic.json from `ncu --page raw --csv` dumps of one bench step: DRAM bytes per launch of the dominant kernels
 (tensor-core convs of forward_dec + forward_seg; decode head-maps -> peaks path).  bench.py copies these into `roofline.traffic`.
 
-    python tools/make_traffic.py <tag> <tc_raw.csv> [<decode_raw.csv>]"""
+    python tools/make_traffic.py <tag> <tc_raw.csv> [<decode_raw.csv> [<n forward_dec launches>]]
+The tensor-core launches of a step are forward_dec's (first, `roofline.launches_per_step` of the bench line) followed by
+forward_seg's; with the count given, the headline figures cover forward_dec only and forward_seg is listed separately."""
 import csv, json, subprocess, sys
 
 tag, tc_csv = sys.argv[1], sys.argv[2]
 dec_csv = sys.argv[3] if len(sys.argv) > 3 else None
+n_dec = int(sys.argv[4]) if len(sys.argv) > 4 else None
 
 
 def load(path, names):
@@ -30,11 +33,17 @@ def load(path, names):
     return out
 
 commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-tc = load(tc_csv, ("tc_conv", "tc_shift"))
-d = {"source": f"{tc_csv} (ncu --set full --clock-control none, one bench step: every tc_conv_kernel / tc_conv2_kernel / tc_shift_kernel launch of forward_dec + forward_seg)",
+tc_all = load(tc_csv, ("tc_conv", "tc_shift"))
+tc = tc_all[:n_dec] if n_dec else tc_all
+d = {"source": f"{tc_csv} (ncu --set full --clock-control none, one bench step: every tc_conv_kernel / tc_conv2_kernel / tc_shift_kernel launch of "
+               + ("forward_dec)" if n_dec else "forward_dec + forward_seg)"),
      "code_state": commit, "kernel": "tc_conv_kernel + tc_conv2_kernel + tc_shift_kernel", "launches": len(tc),
      "dram_bytes_per_step": sum(b for _, b, _ in tc), "dram_bytes_per_launch": sum(b for _, b, _ in tc) / max(1, len(tc)),
      "ncu_duration_ms_sum": sum(t for _, _, t in tc)}
+if n_dec and len(tc_all) > n_dec:
+    sg = tc_all[n_dec:]
+    d["forward_seg"] = {"launches": len(sg), "dram_bytes_per_step": sum(b for _, b, _ in sg),
+                        "dram_bytes_per_launch": sum(b for _, b, _ in sg) / len(sg), "ncu_duration_ms_sum": sum(t for _, _, t in sg)}
 if dec_csv:
     dec = load(dec_csv, ("vote_kernel", "blur32_candidates", "exact_peaks"))
     d["decode"] = {"source": dec_csv, "kernel": "vote_kernel + blur32_candidates_kernel + exact_peaks_kernel", "launches": len(dec),
