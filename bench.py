@@ -199,12 +199,13 @@ def run_decode(args, rank, world, dist):
     _cabi.timing_enable(True)
     for _ in range(args.steps):
         step_device()
+    drain()
     st_ms, st_cnt = _cabi.timing_collect()
     _cabi.timing_enable(False)
     # device idle time between the last decode kernel and the first forward_seg launch (D2H of the boxes, host unpack, atlas planning)
     engine.gap_events = []
     for _ in range(args.steps):
-        step_device()
+        state["dets"] = engine.detect_batch(x_dev, head_override=forced, packed=True)[0]     # serial path: what submit / collect hide
     torch.cuda.synchronize()
     gaps = [a.elapsed_time(b) for a, b in engine.gap_events]
     engine.gap_events = None
@@ -355,12 +356,25 @@ def run_pipeline(args, rank, world, dist):
                 dist.all_gather_into_tensor(gathered, res.packed)
                 comm_done.record(comm_stream)
 
+    # Two batches in flight (InstanceHeat.submit / collect): forward_dec + decode of batch i+1 are enqueued BEFORE the host waits for
+    # the boxes of batch i and plans its forward_seg, so the device never idles on the host round trip.  Every step submits one batch
+    # and collects one: K timed steps contain K forward_dec + decode and K forward_seg.  --serial times detect_batch instead.
     def step_device():
         if world > 1:
             torch.cuda.current_stream().wait_event(comm_done)      # the previous gather has read the record buffer (long done)
-        dets, seg = engine.detect_batch(x_dev, head_override=forced, packed=True, on_decoded=on_decoded)
+        if args.serial:
+            dets, seg = engine.detect_batch(x_dev, head_override=forced, packed=True, on_decoded=on_decoded)
+        else:
+            engine.submit(x_dev, head_override=forced, on_decoded=on_decoded)
+            if engine._n_submitted - engine._n_collected < 2:
+                return None
+            dets, seg = engine.collect(packed=True)
         state["dets"] = dets
         return dets
+
+    def drain():
+        while engine._n_submitted > engine._n_collected:
+            state["dets"] = engine.collect(packed=True)[0]
 
     # e2e: every step's input crosses PCIe inside the timed region.  The copy of step i+1 runs on a side stream while step i
     # computes (two staging buffers); detections + mask patches of every step are copied back before the step ends.
@@ -376,26 +390,48 @@ def run_pipeline(args, rank, world, dist):
             x_stages[b].copy_(x_host, non_blocking=True)                      # H2D of step i's input from pinned memory
             copied[b].record(copy_stream)
 
+    landed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def read_back(i):
+        det_host.copy_(engine.last_result.packed, non_blocking=True)
+        m = engine.last_seg_model.last_masks
+        nf = min(m.numel(), mask_host.numel())
+        mask_host[:nf].copy_(m[:nf], non_blocking=True)                       # D2H of the batch's result: detections + mask patches
+        state["mask_floats"] = nf
+        landed[i & 1].record(torch.cuda.current_stream())
+
     def run_e2e(steps):
+        cur = torch.cuda.current_stream()
         for b in range(2):
-            consumed[b].record(torch.cuda.current_stream())
+            consumed[b].record(cur)
         issue_h2d(0)
+        done = 0
         for i in range(steps):
             b = i & 1
-            cur = torch.cuda.current_stream()
             cur.wait_event(copied[b])
             if i + 1 < steps:
                 issue_h2d(i + 1)
             if world > 1:
                 cur.wait_event(comm_done)
-            dets, seg = engine.detect_batch(x_stages[b], head_override=forced, packed=True, on_decoded=on_decoded)
+            if args.serial:
+                engine.detect_batch(x_stages[b], head_override=forced, packed=True, on_decoded=on_decoded)
+                consumed[b].record(cur)
+                read_back(i)
+                cur.synchronize()
+                continue
+            engine.submit(x_stages[b], head_override=forced, on_decoded=on_decoded)
             consumed[b].record(cur)
-            det_host.copy_(engine.last_result.packed, non_blocking=True)
-            m = engine.model.last_masks
-            nf = min(m.numel(), mask_host.numel())
-            mask_host[:nf].copy_(m[:nf], non_blocking=True)                   # D2H of the step's result: detections + mask patches
-            state["mask_floats"] = nf
-            cur.synchronize()
+            if engine._n_submitted - engine._n_collected == 2:
+                engine.collect(packed=True)
+                read_back(done)
+                if done > 0:
+                    landed[(done - 1) & 1].synchronize()                      # the previous batch's results are on the host (bounded lag)
+                done += 1
+        while engine._n_submitted > engine._n_collected:                      # the last batch in flight belongs to the timed region
+            engine.collect(packed=True)
+            read_back(done)
+            done += 1
+        cur.synchronize()
 
     def sync_all():
         if world > 1:
@@ -420,7 +456,7 @@ def run_pipeline(args, rank, world, dist):
         return ms
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):
+    for _ in range(warm + (0 if args.serial else 1)):
         step_device()
     n_det = sum(0 if d is None else len(d) for d in state["dets"])
     truncated = bool(int(engine.last_result.status.item()) & 4)
@@ -428,6 +464,7 @@ def run_pipeline(args, rank, world, dist):
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     ms = timed(step_device, args.steps)
     clocks = sampler.stop() if sampler else None
+    drain()
     run_e2e(2)
     ms_e2e = timed(lambda: run_e2e(args.steps), 1)
     if world > 1:     # the gathered records must equal every rank's own detections, ordered by global image index
@@ -440,12 +477,13 @@ def run_pipeline(args, rank, world, dist):
     _cabi.timing_enable(True)
     for _ in range(args.steps):
         step_device()
+    drain()
     st_ms, st_cnt = _cabi.timing_collect()
     _cabi.timing_enable(False)
     # device idle time between the last decode kernel and the first forward_seg launch (D2H of the boxes, host unpack, atlas planning)
     engine.gap_events = []
     for _ in range(args.steps):
-        step_device()
+        state["dets"] = engine.detect_batch(x_dev, head_override=forced, packed=True)[0]     # serial path: what submit / collect hide
     torch.cuda.synchronize()
     gaps = [a.elapsed_time(b) for a, b in engine.gap_events]
     engine.gap_events = None
@@ -477,7 +515,7 @@ def run_pipeline(args, rank, world, dist):
                 "algorithmic_flops_per_step": info[0], "launches_per_step": tc_launches, "avg_launch_ms": round(tc_ms / max(1, tc_launches), 4),
                 "cuda_core_conv_flops_per_step": info[1], "whole_step_tflops": round(whole, 1), "whole_step_frac": round(whole / peak_tf, 4),
                 "per_class": per_class, "stages": stages,
-                "host_gap_ms_per_step": round(float(np.mean(gaps)), 4) if gaps else None}
+                "serial_host_gap_ms_per_step": round(float(np.mean(gaps)), 4) if gaps else None}
     gbs = world * BS
     out = {
         "metric": METRIC, "value": round(gbs * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -489,6 +527,7 @@ def run_pipeline(args, rank, world, dist):
                                + (f"; decode teacher-forced with planted {CELLS}-cell head maps (SURVEY.md 8d-ii)" if forced is not None else "; free-running decode (the network's own head maps)"),
                    "config": args.config, "global_batch": gbs, "precision": args.precision, "detections_per_step": n_det,
                    "detection_record_truncated": truncated,
+                   "batches_in_flight": 1 if args.serial else 2,
                    "l2_note": "activations of one step (>20 GB) exceed L2; no flush needed"},
         "e2e": {"value": round(gbs * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel(),
                 "d2h_bytes_per_step": det_host.numel() * 8 + int(state.get("mask_floats", 0)) * 4},
@@ -578,6 +617,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configuration (cfg2 = the headline)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: bs per GPU fixed; strong: the global batch of the config divided over the ranks")
+    ap.add_argument("--serial", action="store_true", help="one batch in flight (detect_batch) instead of submit / collect with two")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch/cuDNN forward_dec line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -62,23 +62,125 @@ class InstanceHeat:
         self.device = torch.device(device)
         self.model = model if model is not None else KGnet.resnet50(pretrained=True, precision=precision)   # test.py:53
         self.model.to(self.device).eval()
-        self._decoders = {}
+        self._decoders = {}      # slot -> {configuration: Decoder}
         self.last_launches = 0
         self.packed_k = 0        # > 0: the decode also writes the fixed-size per-image detection records (data-parallel all-gather)
+        self._slots = None       # submit() / collect(): two engines (shared parameters) with their own workspaces
+        self._n_submitted = self._n_collected = 0
+        self.last_seg_model = self.model
         self.gap_events = None   # a list: detect_batch appends (decode finished, forward_seg starts) CUDA event pairs (diagnostics)
 
     def load_weights(self, resume, dataset):
         """test.py:60-61."""
         self.model.load_state_dict(torch.load(os.path.join("weights_" + dataset, resume), map_location="cpu"))
 
-    def _decoder(self, N, shapes, nms_thresh, max_peaks, max_boxes):
+    def _decoder(self, N, shapes, nms_thresh, max_peaks, max_boxes, slot=0):
         key = (N, tuple(shapes), float(nms_thresh), max_peaks, max_boxes, self.packed_k)
-        d = self._decoders.get(key)
+        cache = self._decoders.setdefault(slot, {})
+        d = cache.get(key)
         if d is None:
-            self._decoders.clear()
-            d = self._decoders[key] = postprocessing.Decoder(N, shapes, nms_thresh=nms_thresh, max_peaks=max_peaks,
-                                                             max_boxes=max_boxes, device=self.device, packed_k=self.packed_k)
+            cache.clear()
+            d = cache[key] = postprocessing.Decoder(N, shapes, nms_thresh=nms_thresh, max_peaks=max_peaks,
+                                                    max_boxes=max_boxes, device=self.device, packed_k=self.packed_k)
         return d
+
+    # ---- two batches in flight ------------------------------------------------------------------------
+    # detect_batch has one host round trip in the middle of the device work: the boxes must reach the host (the atlas of forward_seg
+    # is planned there), so the GPU idles from the end of the decode until the first forward_seg launch (measured 1.2 ms per bs32
+    # step).  submit() / collect() hide it: submit(i+1) enqueues forward_dec + decode of the NEXT batch before collect(i) waits for
+    # the boxes of batch i, which by then landed in pinned memory long ago; forward_seg(i) queues up behind decode(i+1).  Two slots
+    # (engine + workspaces + decode buffers each) alternate; the second engine shares the first one's parameter tensors.
+    def _slot(self, k):
+        if self._slots is None:
+            self._slots = [{"model": self.model, "pending": None}, None]
+        if self._slots[k] is None:
+            twin = KGnet.resnet50(pretrained=False, precision=self.model.precision)
+            src = dict(self.model.named_modules())
+            for name, mod in twin.named_modules():           # the SAME Parameter / buffer objects: weight updates reach both engines
+                for key in list(mod._parameters):
+                    mod._parameters[key] = src[name]._parameters[key]
+                for key in list(mod._buffers):
+                    mod._buffers[key] = src[name]._buffers[key]
+            twin.eval()
+            self._slots[k] = {"model": twin, "pending": None}
+        slot = self._slots[k]
+        slot["model"].precision = self.model.precision
+        return slot
+
+    def submit(self, x, nms_thresh=0.5, head_override=None, max_peaks=4096, max_boxes=4096, on_decoded=None):
+        """Enqueue preprocess + forward_dec + decode of one batch (arguments as detect_batch) and return without waiting.  At most two
+        batches may be in flight: collect() the older one before the third submit."""
+        k = self._n_submitted & 1
+        slot = self._slot(k)
+        if slot["pending"] is not None:
+            raise RuntimeError("two batches are already in flight: call collect() first")
+        model = slot["model"]
+        launches = 0
+        if x.dtype == torch.uint8:
+            x = preprocess_u8(x)
+            launches += 1
+        keep = model.export_feats
+        model.export_feats = False
+        try:
+            out = model.forward_dec(x)
+        finally:
+            model.export_feats = keep
+        launches += model.last_launches
+        heads = head_override if head_override is not None else [tuple(o) for o in out[:4]]
+        N = x.shape[0]
+        shapes = [tuple(h[0].shape[2:]) for h in heads]
+        res = self._decoder(N, shapes, nms_thresh, max_peaks, max_boxes, slot=k)(heads)
+        res.prefetch()                       # status / counts / boxes -> pinned memory, right behind the decode
+        launches += res.n_launches
+        if on_decoded is not None:
+            on_decoded(res)
+        slot["pending"] = dict(out=out, heads=heads, res=res, launches=launches, N=N, shapes=shapes, nms=nms_thresh,
+                               caps=(max_peaks, max_boxes), on_decoded=on_decoded)
+        self._n_submitted += 1
+
+    def collect(self, with_masks=True, packed=False):
+        """(detections, seg) of the OLDEST batch in flight, like detect_batch's return value."""
+        k = self._n_collected & 1
+        slot = self._slots[k] if self._slots is not None else None
+        if slot is None or slot["pending"] is None:
+            raise RuntimeError("collect() without a batch in flight")
+        pend, model = slot["pending"], slot["model"]
+        slot["pending"] = None
+        self._n_collected += 1
+        res, launches = pend["res"], pend["launches"]
+        st = res.overflow() & 3
+        if st:                               # a bounded device list overflowed: decode this batch again with doubled capacities
+            mp, mb = pend["caps"]
+            mp2 = min(2 * mp, postprocessing.MAX_CAPACITY) if st & 1 else mp
+            mb2 = min(2 * mb, postprocessing.MAX_CAPACITY) if st & 2 else mb
+            if (mp2, mb2) == (mp, mb):
+                res.check()                  # raises: already at the largest capacity
+            res = postprocessing.run_with_growth(lambda a, b: self._decoder(pend["N"], pend["shapes"], pend["nms"], a, b, slot=k),
+                                                 pend["heads"], mp2, mb2)
+            launches += res.n_launches
+            if pend["on_decoded"] is not None:
+                pend["on_decoded"](res)
+        dets = res.detections()
+        self.last_result = res
+        seg = None
+        if with_masks:
+            seg = model.forward_seg_packed(pend["out"][4], [d if d is not None else [] for d in dets])
+            if not packed:
+                seg = seg.as_lists()
+            launches += model.last_launches
+        self.last_seg_model = model
+        self.last_launches = launches
+        return dets, seg
+
+    def detect_pipelined(self, batches, **kw):
+        """Generator over (detections, seg) of every batch of `batches`, two batches in flight."""
+        collect_kw = {k: kw.pop(k) for k in ("with_masks", "packed") if k in kw}
+        for x in batches:
+            self.submit(x, **kw)
+            if self._n_submitted - self._n_collected == 2:
+                yield self.collect(**collect_kw)
+        while self._n_submitted > self._n_collected:
+            yield self.collect(**collect_kw)
 
     def detect_batch(self, x, nms_thresh=0.5, with_masks=True, head_override=None, max_peaks=4096, max_boxes=4096, packed=False,
                      on_decoded=None):
@@ -116,6 +218,7 @@ class InstanceHeat:
             gap[0].record()
         dets = res.detections()                     # the one host sync of the pipeline: boxes are needed on the host
         self.last_result = res
+        self.last_seg_model = model
         seg = None
         if with_masks:
             model._seg_launch_event = gap[1] if gap is not None else None

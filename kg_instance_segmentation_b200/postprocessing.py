@@ -49,10 +49,61 @@ class DecodeResult:
     status: Optional[torch.Tensor] = None
     packed: Optional[torch.Tensor] = None        # [N, packed_k + 1, 5] f64: all-gather record (row 0 = count, rows stored)
     n_launches: int = 0
+    meta: Optional[torch.Tensor] = None          # [N + 1] i32 = det_count | status (one buffer: one D2H fetches both)
+    h_meta: Optional[torch.Tensor] = None        # pinned host copies
+    h_dets: Optional[torch.Tensor] = None
+    _guess: int = 64                             # detection rows per image fetched speculatively together with the counts
+    _fetch: Optional[tuple] = None               # (event, rows) of the copies enqueued by prefetch()
+    _host: Optional[tuple] = None                # (status, counts, rows) once the copies have landed
+
+    def invalidate(self):
+        """A new decode has been enqueued into these buffers."""
+        self._fetch = self._host = None
+
+    def prefetch(self):
+        """Enqueue, on the current stream (i.e. right behind the decode), the D2H copies the host will need: status + counts and
+        the first rows of every image's detection list, into pinned memory; record an event.  No synchronisation: a pipelined
+        caller enqueues the next batch before it waits."""
+        if self._fetch is not None or self._host is not None:
+            return
+        dev = self.dets.device
+        N, cap = self.dets.shape[0], self.dets.shape[1]
+        if self.h_meta is None:
+            self.h_meta = torch.empty(N + 1, dtype=torch.int32).pin_memory()
+            self.h_dets = torch.empty(N * cap * 5, dtype=torch.float64).pin_memory()
+        g = max(1, min(self._guess, cap))
+        with torch.cuda.device(dev):
+            self.h_meta.copy_(self.meta, non_blocking=True)
+            self.h_dets[:N * g * 5].view(N, g, 5).copy_(self.dets[:, :g], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+        self._fetch = (ev, g)
+
+    def _landed(self):
+        """(status, counts [N] i32, rows [N, m, 5] f64) on the host: ONE blocking wait per decode (a second copy only when an image
+        holds more detections than the speculative fetch covered)."""
+        if self._host is None:
+            self.prefetch()
+            ev, g = self._fetch
+            ev.synchronize()
+            N, cap = self.dets.shape[0], self.dets.shape[1]
+            cnt = self.h_meta[:N].numpy().copy()
+            st = int(self.h_meta[N])
+            m = int(cnt.max()) if N else 0
+            rows = self.h_dets[:N * g * 5].view(N, g, 5)
+            if m > g:
+                rows = self.h_dets[:N * m * 5].view(N, m, 5)
+                rows.copy_(self.dets[:, :m])             # blocking copy on the current stream
+            self._guess = int(min(cap, max(64, 1 << int(np.ceil(np.log2(max(1, m) * 1.25))))))
+            self._host = (st, cnt, rows.numpy())
+            self._fetch = None
+        return self._host
 
     def overflow(self) -> int:
         """0, or the status bits of a list overflow (bit0: a peak list, bit1: a box list).  Synchronises."""
-        return int(self.status.item())
+        if self.meta is None:
+            return int(self.status.item())
+        return self._landed()[0]
 
     def check(self):
         st = self.overflow()
@@ -62,9 +113,12 @@ class DecodeResult:
     def detections(self) -> List[Optional[np.ndarray]]:
         """Per image: (M,5) float64 array in NMS keep order, or None (nms.py:8-9) when there are no boxes."""
         self.check()
-        cnt = self.det_count.cpu().numpy()
-        m = int(cnt.max()) if len(cnt) else 0
-        d = self.dets[:, :max(m, 1)].cpu().numpy()
+        if self.meta is None:
+            cnt = self.det_count.cpu().numpy()
+            m = int(cnt.max()) if len(cnt) else 0
+            d = self.dets[:, :max(m, 1)].cpu().numpy()
+        else:
+            _, cnt, d = self._landed()
         return [d[i, :c].copy() if c > 0 else None for i, c in enumerate(cnt)]
 
 
@@ -93,9 +147,9 @@ class Decoder:
         self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev)
         self.debug = debug
         f64, i32 = torch.float64, torch.int32
-        r = DecodeResult(dets=torch.zeros(self.N, max_boxes, 5, dtype=f64, device=dev),
-                         det_count=torch.zeros(self.N, dtype=i32, device=dev),
-                         status=torch.zeros(1, dtype=i32, device=dev))
+        meta = torch.zeros(self.N + 1, dtype=i32, device=dev)
+        r = DecodeResult(dets=torch.zeros(self.N, max_boxes, 5, dtype=f64, device=dev), det_count=meta[:self.N], status=meta[self.N:],
+                         meta=meta)
         if debug:
             r.boxes = torch.zeros(self.N, max_boxes, 5, dtype=f64, device=dev)
             r.box_count = torch.zeros(self.N, dtype=i32, device=dev)
@@ -141,6 +195,7 @@ class Decoder:
             _cabi.check(self.L.kg_decode(C.byref(self.cfg), self.sc, C.byref(self.out), self.workspace.data_ptr(),
                                          self.workspace.numel(), st.cuda_stream, C.byref(nl)))
         self.result.n_launches = nl.value
+        self.result.invalidate()
         self._keepalive = keep
         return self.result
 
