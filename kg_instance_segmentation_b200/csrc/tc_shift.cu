@@ -59,7 +59,6 @@ struct ShParams {
   int NS;
   unsigned slot_bytes, w_slab, tmem_cols;     // w_slab: bytes reserved per weight plane inside a slot
   unsigned wres_bytes;                        // resident-weights mode: bytes of the weight region in front of the ring
-  int noemit;                                 // diagnostics (KG_SH_NOEMIT=1): the register-shuffle epilogue skips conversion + stores
 };
 
 // Compile-time geometry of one fused launch: up to three convs with O0 / O1 / O2 output channels, TAPS x TAPS filters.
@@ -283,9 +282,9 @@ __global__ void __launch_bounds__(64 + 32 * sh_epi_warps(OUTMODE, TAPS), 1) tc_s
     // a quadrant ("halves") take alternate 16-channel batches of the work list =====
     // (launch parameters used in the loops below are copied into registers once: the epilogue is instruction-bound, and reloading them
     // from the parameter bank after every asm barrier cost a third of its instructions in the implicit-GEMM kernel)
-    struct { int H, W, pad, BW, BH, tiles_x, rows_y, num_work, row_mode, RB, relu, noemit; unsigned stage_bytes; const uint8_t* mask;
+    struct { int H, W, pad, BW, BH, tiles_x, rows_y, num_work, row_mode, RB, relu; unsigned stage_bytes; const uint8_t* mask;
              __half* out_hi; __half* out_lo; } const P_ = {p.H, p.W, p.pad, p.BW, p.BH, p.tiles_x, p.rows_y, p.num_work, p.row_mode, p.RB, p.relu,
-                                                       p.noemit, p.stage_bytes, p.mask, p.out_hi, p.out_lo};
+                                                       p.stage_bytes, p.mask, p.out_hi, p.out_lo};
     const ShGroup grp_[SH_MAX_GROUPS] = {p.grp[0], p.grp[1], p.grp[2]};
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;                     // which of the NPART warps of this quadrant ("half" in the two-part kernels)
@@ -331,7 +330,6 @@ __global__ void __launch_bounds__(64 + 32 * sh_epi_warps(OUTMODE, TAPS), 1) tc_s
             // pixel x0 + j for j < 127; the tile's last pixel waits in "pend" and is stored directly by the next tile.
             const bool staged = P_.stage_bytes != 0;
             auto emit32 = [&](const float* v, long long pix, int srow) __attribute__((always_inline)) {
-              if (P_.noemit) return;
               const bool has_mask = P_.mask != nullptr;                    // uniform: the forward_seg atlases only
               const bool keep = !has_mask || P_.mask[pix] != 0;
 #pragma unroll
@@ -429,7 +427,7 @@ __global__ void __launch_bounds__(64 + 32 * sh_epi_warps(OUTMODE, TAPS), 1) tc_s
             }
             if (staged) fence_proxy_async_smem();
             epi_bar();
-            if (staged && warp == 2 && lane == 0 && !P_.noemit) {
+            if (staged && warp == 2 && lane == 0) {
               tma_store_4d(&p.o_map[0], stage, 0, tx * 128, y0, n);                  // pixels x0 .. x0 + 126
               if (P_.out_lo != nullptr) tma_store_4d(&p.o_map[1], stage + 16384u, 0, tx * 128, y0, n);
               bulk_commit();
@@ -707,7 +705,6 @@ static int shift_prepare_t(TcShiftOp* op, EncodeTiledFn encode) {
   if (ns > 8) ns = 8;
   KG_REQUIRE(ns >= 2, "tc_shift_prepare: tile does not fit in shared memory");
   p.NS = ns;
-  p.noemit = getenv("KG_SH_NOEMIT") != nullptr ? 1 : 0;
   op->smem_bytes = (unsigned)(1024 + p.stage_bytes + p.wres_bytes + (size_t)ns * p.slot_bytes + 16 * ns + 64 + buf_bytes + 64);
   op->grid = (unsigned)std::min(p.num_work, tc_num_sms());
   op->params = sp;
