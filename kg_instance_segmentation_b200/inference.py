@@ -101,6 +101,7 @@ class InstanceHeat:
                     mod._parameters[key] = src[name]._parameters[key]
                 for key in list(mod._buffers):
                     mod._buffers[key] = src[name]._buffers[key]
+            twin._flat_tensors = None
             twin.eval()
             self._slots[k] = {"model": twin, "pending": None}
         slot = self._slots[k]

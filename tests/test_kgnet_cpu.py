@@ -81,3 +81,29 @@ def test_patch_rect_matches_oracle_rounding():
     for v in (0.5, 1.5, 2.5, 3.5):      # exact .5 products: half-to-even
         b = np.asarray([0.0, 0.0, v / 8, v / 8], np.float32)
         assert KGnet.patch_rect(b, 8, 8) == O.get_patch_rect(list(b), 8, 8)
+
+
+def test_weight_signature_sees_every_kind_of_update():
+    """The cached slot list behind _sync_weights must notice in-place edits, load_state_dict, .to()-style re-materialisation and a
+    Parameter object swapped by hand (a stale signature would silently keep the old weights on the device)."""
+    from kg_instance_segmentation_b200 import KGnet
+    m = KGnet.resnet50(pretrained=False)
+    sigs = [m._signature()]
+
+    def changed():
+        sigs.append(m._signature())
+        return sigs[-1] != sigs[-2]
+
+    assert not changed()
+    with torch.no_grad():
+        m.kp_head_c0[2].weight.mul_(0.5)
+    assert changed()
+    m.bn1.running_var.add_(1.0)
+    assert changed()
+    m.load_state_dict(O.make_state_dict(seed=3), strict=True)
+    assert changed()
+    m.conv1.weight = torch.nn.Parameter(torch.zeros_like(m.conv1.weight))
+    assert changed()
+    m.double()
+    assert changed()
+    assert len(sigs[-1]) == len(list(m.parameters())) + len(list(m.buffers()))
