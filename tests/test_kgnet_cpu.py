@@ -96,7 +96,7 @@ def test_weight_signature_sees_every_kind_of_update():
 
     assert not changed()
     with torch.no_grad():
-        m.kp_head_c0[2].weight.mul_(0.5)
+        dict(m.named_parameters())["kp_head_c0.2.weight"].mul_(0.5)
     assert changed()
     m.bn1.running_var.add_(1.0)
     assert changed()
