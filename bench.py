@@ -199,16 +199,8 @@ def run_decode(args, rank, world, dist):
     _cabi.timing_enable(True)
     for _ in range(args.steps):
         step_device()
-    drain()
     st_ms, st_cnt = _cabi.timing_collect()
     _cabi.timing_enable(False)
-    # device idle time between the last decode kernel and the first forward_seg launch (D2H of the boxes, host unpack, atlas planning)
-    engine.gap_events = []
-    for _ in range(args.steps):
-        state["dets"] = engine.detect_batch(x_dev, head_override=forced, packed=True)[0]     # serial path: what submit / collect hide
-    torch.cuda.synchronize()
-    gaps = [a.elapsed_time(b) for a, b in engine.gap_events]
-    engine.gap_events = None
     px = BS * sum(h * w for h, w in shapes)
     names = {0: "vote_kernel", 1: "blur32_candidates_kernel + exact_peaks_kernel", 2: "group_kernel", 3: "nms_kernel"}
     stage = {names[i]: {"ms_per_step": float(st_ms[i]) / args.steps, "launches_per_step": int(st_cnt[i]) // args.steps} for i in names}

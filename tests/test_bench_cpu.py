@@ -30,3 +30,28 @@ def test_roofline_traffic_comes_from_the_committed_capture():
     assert src is not None and "_traffic.json" in src and per_launch > 1e8
     blur, _ = bench.profiled_traffic("decode")
     assert 5e7 < blur < 5e8        # ~446 MB of accumulators per step over four launches
+
+
+def test_bench_has_no_undefined_names():
+    """The GPU legs of bench.py cannot run here: at least every name their (nested) functions read must resolve to a module-level
+    definition, an import or a builtin (a stray line once left `drain()` in the decode leg)."""
+    import builtins
+    import symtable
+    path = os.path.join(ROOT, "bench.py")
+    src = open(path).read()
+    top = symtable.symtable(src, path, "exec")
+    module_names = {s.get_name() for s in top.get_symbols() if s.is_assigned() or s.is_imported() or s.is_namespace()}
+    missing = []
+
+    def walk(tab):
+        for s in tab.get_symbols():
+            if s.is_global() and s.is_referenced() and not s.is_assigned():
+                n = s.get_name()
+                if n not in module_names and not hasattr(builtins, n):
+                    missing.append((tab.get_name(), n))
+        for ch in tab.get_children():
+            walk(ch)
+
+    for ch in top.get_children():
+        walk(ch)
+    assert not missing, missing
