@@ -381,8 +381,7 @@ __device__ __forceinline__ int reflect_near(int i, int n) {
   return i >= n ? 2 * n - 1 - i : i;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) blur32_candidates_kernel(const BlurParams p) {
+__global__ void __launch_bounds__(128, 4) blur32_candidates_kernel(const BlurParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int plane_id = blockIdx.y;
   const int H = p.H, W = p.W;
@@ -1089,16 +1088,12 @@ static int launch_blur_peak(BlurParams bp, int N, cudaStream_t stream) {
 
 // fp32 prefilter (blur32_candidates_kernel): warp-private strips of 110 output columns, 4 warps per CTA, 16 warps per SM at 128 registers
 static int launch_blur32(BlurParams bp, int N, cudaStream_t stream) {
-  const char* occ_env = getenv("KG_B32_OCC");
-  const int occ = occ_env ? atoi(occ_env) : 4;
   bp.n_strips = ceil_div(bp.W, B32_CW);
-  bp.RH = pick_rows(bp.H, (long long)N * 5 * bp.n_strips, (long long)num_sms() * 4 * occ);
+  bp.RH = pick_rows(bp.H, (long long)N * 5 * bp.n_strips, (long long)num_sms() * 16);
   const int items = bp.n_strips * ceil_div(bp.H, bp.RH);
   dim3 grid(ceil_div(items, 4), N * 5, 1);
   KG_REQUIRE(grid.y <= 65535, "blur32: grid too large");
-  { if (occ == 5) blur32_candidates_kernel<5><<<grid, 128, 0, stream>>>(bp);
-    else if (occ == 6) blur32_candidates_kernel<6><<<grid, 128, 0, stream>>>(bp);
-    else blur32_candidates_kernel<4><<<grid, 128, 0, stream>>>(bp); }
+  blur32_candidates_kernel<<<grid, 128, 0, stream>>>(bp);
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;
 }
