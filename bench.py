@@ -27,6 +27,8 @@ UNIT = "images/s"
 CONFIGS = {
     "cfg2": dict(bs=32, hw=512, cells=40, side=(24, 110), gap=12,
                  metric="images/sec at 512x512 bs32 (KGnet inference hot path)"),
+    "cfg1": dict(bs=1, hw=512, cells=40, side=(24, 110), gap=12,
+                 metric="images/sec at 512x512 bs1 (KGnet inference hot path, BASELINE config 1: the reference's own test.py case)"),
     "cfg4": dict(bs=8, hw=1024, cells=500, side=(16, 40), gap=6,
                  metric="images/sec at 1024x1024 bs8, ~500 cells/img (KGnet inference hot path, BASELINE config 4)"),
 }

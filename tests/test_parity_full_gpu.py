@@ -326,3 +326,32 @@ def test_stale_feature_list_is_not_mistaken_for_the_current_pass():
     m.forward_dec(xb)
     with pytest.raises(RuntimeError):
         m.forward_seg(fa, [np.array([[4., 6., 40., 50., 0.9]])])
+
+
+@pytest.mark.parametrize("precision,kp_tol", [("fast", 1e-3), ("exact", 1e-4)])
+def test_forward_dec_and_seg_ragged_size(precision, kp_tol):
+    """320 x 448: widths that are neither a multiple of the 128-pixel strip nor below it (scale 0: three full strips + a 64-pixel
+    tail; scale 1: 224 = 128 + 96; scale 2: 112 < 128), 20 x 28 at the deepest level -- the ragged-tile paths of every kernel family."""
+    sd = O.make_state_dict(seed=0)
+    torch.manual_seed(11)
+    x = torch.rand(1, 3, 320, 448) - 0.5
+    ref = O.forward_dec(sd, x)
+    m = _model(precision, sd)
+    out = m.forward_dec(x.cuda())
+    for s in range(4):
+        assert float((out[s][0].cpu() - ref[s][0]).abs().max()) <= kp_tol, s
+        for k in (1, 2):
+            scale = max(1.0, float(ref[s][k].abs().max()))
+            assert float((out[s][k].cpu() - ref[s][k]).abs().max()) <= (2e-2 if precision == "fast" else 2e-3) * scale, (s, k)
+    boxes = [np.array([[3., 5., 150., 200., 0.9], [100., 300., 318., 446., 0.8], [10., 10., 14., 13., 0.4], [0., 0., 319., 447., 0.3]])]
+    rseg = O.forward_seg(sd, ref[4], boxes)
+    seg = m.forward_seg(out[4], boxes)
+    assert len(seg[0][0]) == len(rseg[0][0]) == 4
+    tol = 2e-2 if precision == "fast" else 2e-3
+    for a, b in zip(seg[0][0], rseg[0][0]):
+        a = a.cpu()
+        assert a.shape == b.shape
+        sure = (b - 0.5).abs() > tol
+        assert bool(((a >= 0.5) == (b >= 0.5))[sure].all())
+        if precision == "exact":
+            assert float((a - b).abs().max()) <= tol
