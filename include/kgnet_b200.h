@@ -156,6 +156,12 @@ size_t kg_net_workspace_bytes(kg_net* net, int N, int H, int W, int precision);
 int kg_net_forward_dec(kg_net* net, const float* d_x, int N, int H, int W, float* const* d_heads, float* const* d_feats,
                        int precision, void* d_workspace, size_t workspace_bytes, void* stream, int* n_launches);
 
+/* The same pass fed by the camera image: d_img = uint8 NHWC [N,H,W,3] (cv2 BGR order), i.e. BEFORE the `x / 255 - 0.5` of test.py:92.
+ * The normalisation is folded into the two stem convs (exactly: k - 128 is an fp16 integer, w / 255 and the constant go into weights
+ * and bias), so neither kg_preprocess_u8 nor an fp32 copy of the input is needed.  Tensor-core precisions (1, 2) only. */
+int kg_net_forward_dec_u8(kg_net* net, const unsigned char* d_img, int N, int H, int W, float* const* d_heads, float* const* d_feats,
+                          int precision, void* d_workspace, size_t workspace_bytes, void* stream, int* n_launches);
+
 /* Loads caller-provided fp32 NCHW features c0..c4 into the workspace (forward_seg on features that did not come
  * from kg_net_forward_dec, KGnet.py:321). */
 int kg_net_import_feats(kg_net* net, const float* const* d_feats, int N, int H, int W, int precision, void* d_workspace,

@@ -206,12 +206,28 @@ class ResNet(nn.Module):
 
     # ---- KGnet.py:275-318 -----------------------------------------------------------------------
     def forward_dec(self, x):
+        return self._forward_dec(x, False)
+
+    def forward_dec_u8(self, images):
+        """forward_dec of a uint8 [N,H,W,3] CUDA batch (cv2 BGR order) as it comes from the camera: the `x / 255 - 0.5` of test.py:92
+        is folded into the two stem convs (exactly), no fp32 copy of the input is made.  Tensor-core precisions only."""
+        if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3:
+            raise ValueError(f"expected a uint8 [N,H,W,3] batch, got {tuple(images.shape)} {images.dtype}")
+        if self._precision_code() == 0:
+            raise RuntimeError("precision 'reference' runs on CUDA cores from the fp32 input: normalise with inference.preprocess_u8")
+        return self._forward_dec(images, True)
+
+    def _forward_dec(self, x, u8):
         if self.training:
             raise RuntimeError("kgnet_b200 implements the inference path: call .eval() first (train-mode BatchNorm is out of scope)")
         if not x.is_cuda:
             raise RuntimeError("kgnet_b200 needs CUDA tensors (no CPU fallback): move the model and input to cuda")
-        x = x.detach().to(torch.float32).contiguous()
-        N, c, H, W = x.shape
+        if u8:
+            x = x.detach().contiguous()
+            N, H, W, c = x.shape
+        else:
+            x = x.detach().to(torch.float32).contiguous()
+            N, c, H, W = x.shape
         assert c == 3, "input must be [N,3,H,W]"
         with torch.cuda.device(x.device):
             self._sync_weights()
@@ -227,8 +243,9 @@ class ResNet(nn.Module):
             heads_p = (C.c_void_p * 12)(*[t.data_ptr() for o in outs for t in o])
             feats_p = (C.c_void_p * 5)(*[t.data_ptr() for t in feats]) if feats is not None else None
             nl = C.c_int(0)
-            _cabi.check(_cabi.lib().kg_net_forward_dec(self._handle, x.data_ptr(), N, H, W, heads_p, feats_p, prec, ws.data_ptr(),
-                                                       ws.numel(), torch.cuda.current_stream().cuda_stream, C.byref(nl)))
+            entry = _cabi.lib().kg_net_forward_dec_u8 if u8 else _cabi.lib().kg_net_forward_dec
+            _cabi.check(entry(self._handle, x.data_ptr(), N, H, W, heads_p, feats_p, prec, ws.data_ptr(), ws.numel(),
+                              torch.cuda.current_stream().cuda_stream, C.byref(nl)))
         self.last_launches = nl.value
         # every forward_dec gets a serial number: a _FeatList from an EARLIER pass must not match the workspace contents
         # of a later one (with export_feats=False the list holds no tensors that could tell the two apart)

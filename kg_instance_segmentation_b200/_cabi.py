@@ -88,6 +88,8 @@ def _bind_net(L):
     L.kg_net_workspace_bytes.argtypes = [vp, ci, ci, ci, ci]
     L.kg_net_forward_dec.restype = ci
     L.kg_net_forward_dec.argtypes = [vp, vp, ci, ci, ci, vp, vp, ci, vp, cs, vp, C.POINTER(ci)]
+    L.kg_net_forward_dec_u8.restype = ci
+    L.kg_net_forward_dec_u8.argtypes = [vp, vp, ci, ci, ci, vp, vp, ci, vp, cs, vp, C.POINTER(ci)]
     L.kg_net_import_feats.restype = ci
     L.kg_net_import_feats.argtypes = [vp, vp, ci, ci, ci, ci, vp, cs, vp]
     L.kg_net_seg_prepare.restype = ci
@@ -125,7 +127,7 @@ def check(code):
 
 EXPORTS = ["kg_last_error", "kg_abi_version", "kg_device_arch", "kg_decode_workspace_bytes", "kg_decode",
            "kg_decode_host", "kg_skeletons_to_boxes_host", "kg_nms_host", "kg_timing_enable", "kg_timing_collect",
-           "kg_net_create", "kg_net_destroy", "kg_net_set_conv", "kg_net_finalize", "kg_net_workspace_bytes", "kg_net_forward_dec",
+           "kg_net_create", "kg_net_destroy", "kg_net_set_conv", "kg_net_finalize", "kg_net_workspace_bytes", "kg_net_forward_dec", "kg_net_forward_dec_u8",
            "kg_net_import_feats", "kg_net_seg_prepare", "kg_net_forward_seg", "kg_conv2d_nchw", "kg_heads_l2_nchw", "kg_net_plan_info", "kg_tc_available", "kg_tc_status",
            "kg_preprocess_u8", "kg_paste_masks", "kg_encode_ground_truth", "kg_detection_loss", "kg_seg_loss_pairs",
            "kg_detection_loss_backward", "kg_seg_loss_pairs_backward"]

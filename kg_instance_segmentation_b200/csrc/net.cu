@@ -30,6 +30,7 @@ struct ConvW {
   float* d_b = nullptr;
   TcWeights tc;             // fp16 hi/lo [tap][cout_pad][cin] (tensor-core path)
   mutable TcStemWeights stemw;            // swizzled weight image of the tensor-core stem kernel, built on first use
+  mutable TcStemWeights stemw_u8;         // same for the uint8-input variant (w / 255, folded bias)
   mutable TcShiftPacked shift1, shift3;   // weights packed for the row-GEMM + shift-add kernel (1 / 3 passes), built on first use
 };
 
@@ -204,7 +205,7 @@ static int set_conv(Net* net, const char* name, const float* w, int Cout, int Ci
   ConvW& c = net->convs[name];
   c.name = name; c.Cout = Cout; c.Cin = Cin; c.R = R; c.S = S;
   // lazily built packings of the PREVIOUS weights (stem image, shift-add slabs) must not survive a weight update
-  c.stemw = TcStemWeights(); c.shift1 = TcShiftPacked(); c.shift3 = TcShiftPacked();
+  c.stemw = TcStemWeights(); c.stemw_u8 = TcStemWeights(); c.shift1 = TcShiftPacked(); c.shift3 = TcShiftPacked();
   c.h_w.assign((size_t)R * S * Cin * Cout, 0.f);
   c.h_b.assign(Cout, 0.f);
   for (int co = 0; co < Cout; ++co) {
@@ -481,7 +482,9 @@ struct Ptrs {
   __half* lo(const Tensor& t) const { return t.off_lo == (size_t)-1 ? nullptr : reinterpret_cast<__half*>(ws + t.off_lo); }
 };
 
-static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_feats, void* ws, cudaStream_t stream, int* n_launches) {
+// d_x: fp32 NCHW input, or nullptr with d_img = the uint8 NHWC image (tensor-core precisions only: the stems normalise on the fly)
+static int run_plan(Net* net, const float* d_x, const uint8_t* d_img, float* const* ext, bool want_feats, void* ws, cudaStream_t stream,
+                    int* n_launches) {
   Plan* p = net->plan.get();
   Ptrs P{(char*)ws};
   int launches = 0;
@@ -563,6 +566,14 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
         if (op.x_input && w->Cin == 3 && w->Cout == 64 && op.relu && op.out >= 0 && !op.out_single && out32 == nullptr &&
             ((w->R == 3 && op.stride == 1) || (w->R == 7 && op.stride == 2)) && w->R == w->S && op.pad == w->R / 2) {
           const Tensor& to = p->tensors[op.out];
+          if (d_img != nullptr) {
+            KG_REQUIRE(p->precision != 0 && tc_stem_supported(w->R, op.stride),
+                       "kg_net_forward_dec_u8: uint8 input needs a tensor-core precision (normalise with kg_preprocess_u8 for precision 0)");
+            if (!w->stemw_u8.d_img) KG_TRY(tc_stem_pack_u8(w->h_w.data(), w->h_b.data(), w->R, &w->stemw_u8));
+            KG_TRY(tc_stem_launch_u8(d_img, &w->stemw_u8, P.hi(to), P.lo(to), p->N, p->H, p->W, w->R, op.stride, stream));
+            ++launches;
+            break;
+          }
           if (p->precision != 0 && tc_stem_supported(w->R, op.stride)) {
             if (!w->stemw.d_img) KG_TRY(tc_stem_pack(w->h_w.data(), w->R, &w->stemw));
             KG_TRY(tc_stem_launch(d_x, &w->stemw, w->d_b, P.hi(to), P.lo(to), p->N, p->H, p->W, w->R, op.stride, stream));
@@ -574,7 +585,7 @@ static int run_plan(Net* net, const float* d_x, float* const* ext, bool want_fea
           break;
         }
         ConvArgs a{};
-        if (op.x_input) { a.x32 = d_x; }
+        if (op.x_input) { KG_REQUIRE(d_x != nullptr, "forward_dec: this layer needs the fp32 input (uint8 input covers the tensor-core stems only)"); a.x32 = d_x; }
         else {
           const Tensor& t0 = p->tensors[op.in0];
           a.in0_hi = P.hi(t0); a.in0_lo = op.in_single ? nullptr : P.lo(t0); a.in0_ps = t0.C;
@@ -1227,7 +1238,23 @@ int kg_net_forward_dec(kg_net* h, const float* d_x, int N, int H, int W, float* 
   float* ext[17];
   for (int i = 0; i < 12; ++i) { KG_REQUIRE(d_heads[i] != nullptr, "kg_net_forward_dec: d_heads[%d] is null", i); ext[i] = d_heads[i]; }
   for (int i = 0; i < 5; ++i) ext[12 + i] = d_feats ? d_feats[i] : nullptr;
-  return run_plan(net, d_x, ext, d_feats != nullptr, d_workspace, (cudaStream_t)stream, n_launches);
+  return run_plan(net, d_x, nullptr, ext, d_feats != nullptr, d_workspace, (cudaStream_t)stream, n_launches);
+}
+
+int kg_net_forward_dec_u8(kg_net* h, const uint8_t* d_img, int N, int H, int W, float* const* d_heads, float* const* d_feats, int precision,
+                          void* d_workspace, size_t workspace_bytes, void* stream, int* n_launches) {
+  Net* net = reinterpret_cast<Net*>(h);
+  KG_REQUIRE(d_img && d_heads && d_workspace, "kg_net_forward_dec_u8: null argument");
+  KG_REQUIRE(precision != 0, "kg_net_forward_dec_u8: uint8 input needs a tensor-core precision (1 fast / 2 exact)");
+  KG_TRY(ensure_plan(net, N, H, W, precision));
+  if (workspace_bytes < net->plan->bytes) {
+    set_error("kg_net_forward_dec_u8: workspace too small (%zu < %zu bytes)", workspace_bytes, net->plan->bytes);
+    return KG_ERR_WORKSPACE;
+  }
+  float* ext[17];
+  for (int i = 0; i < 12; ++i) { KG_REQUIRE(d_heads[i] != nullptr, "kg_net_forward_dec_u8: d_heads[%d] is null", i); ext[i] = d_heads[i]; }
+  for (int i = 0; i < 5; ++i) ext[12 + i] = d_feats ? d_feats[i] : nullptr;
+  return run_plan(net, nullptr, d_img, ext, d_feats != nullptr, d_workspace, (cudaStream_t)stream, n_launches);
 }
 
 int kg_net_import_feats(kg_net* h, const float* const* d_feats, int N, int H, int W, int precision, void* d_workspace, size_t workspace_bytes,

@@ -116,17 +116,7 @@ class InstanceHeat:
         if slot["pending"] is not None:
             raise RuntimeError("two batches are already in flight: call collect() first")
         model = slot["model"]
-        launches = 0
-        if x.dtype == torch.uint8:
-            x = preprocess_u8(x)
-            launches += 1
-        keep = model.export_feats
-        model.export_feats = False
-        try:
-            out = model.forward_dec(x)
-        finally:
-            model.export_feats = keep
-        launches += model.last_launches
+        out, launches = self._forward_dec_any(model, x)
         heads = head_override if head_override is not None else [tuple(o) for o in out[:4]]
         N = x.shape[0]
         shapes = [tuple(h[0].shape[2:]) for h in heads]
@@ -183,6 +173,25 @@ class InstanceHeat:
         while self._n_submitted > self._n_collected:
             yield self.collect(**collect_kw)
 
+    @staticmethod
+    def _forward_dec_any(model, x):
+        """forward_dec of an fp32 NCHW batch or of a uint8 NHWC batch (normalisation folded into the stem convs; through the separate
+        normalisation kernel for precision 'reference').  Returns (outputs, launches); the feature maps stay inside the engine."""
+        launches = 0
+        keep = model.export_feats
+        model.export_feats = False
+        try:
+            if x.dtype == torch.uint8 and model._precision_code() != 0:
+                out = model.forward_dec_u8(x)
+            else:
+                if x.dtype == torch.uint8:
+                    x = preprocess_u8(x)
+                    launches += 1
+                out = model.forward_dec(x)
+        finally:
+            model.export_feats = keep
+        return out, launches + model.last_launches
+
     def detect_batch(self, x, nms_thresh=0.5, with_masks=True, head_override=None, max_peaks=4096, max_boxes=4096, packed=False,
                      on_decoded=None):
         """x: [N,3,H,W] fp32 CUDA tensor in the reference's input convention (BGR/255 - 0.5, test.py:92), or a uint8
@@ -195,17 +204,7 @@ class InstanceHeat:
         on_decoded(result): called right after the decode has been ENQUEUED (before any host sync), e.g. to issue the
         data-parallel all-gather of result.packed on a side stream."""
         model = self.model
-        launches = 0
-        if x.dtype == torch.uint8:
-            x = preprocess_u8(x)
-            launches += 1
-        keep = model.export_feats
-        model.export_feats = False
-        try:
-            out = model.forward_dec(x)
-        finally:
-            model.export_feats = keep
-        launches += model.last_launches
+        out, launches = self._forward_dec_any(model, x)
         heads = head_override if head_override is not None else [tuple(o) for o in out[:4]]
         N = x.shape[0]
         shapes = [tuple(h[0].shape[2:]) for h in heads]

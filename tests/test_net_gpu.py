@@ -301,3 +301,33 @@ def test_forward_dec_batch_consistency_and_sizes():
     ref = O.forward_dec(sd, x)
     for s in range(4):
         assert float((out[s][0].cpu() - ref[s][0]).abs().max()) <= 1e-3
+
+
+@pytest.mark.parametrize("precision,kp_tol,feat_tol", [("exact", 1e-4, 2e-5), ("fast", 1e-3, 2e-5)])
+def test_forward_dec_u8_matches_oracle_and_float_path(precision, kp_tol, feat_tol):
+    """uint8 NHWC input with the normalisation folded into the stem convs (kg_net_forward_dec_u8) against the oracle fed with the
+    reference's `x / 255 - 0.5` (test.py:92) and against this library's own fp32-input path.  The c0 / c1 feature maps come straight
+    out of the two stem kernels' consumers: their borders check the out-of-image tap value (-0.5 in the shifted integer domain)."""
+    from kg_instance_segmentation_b200 import inference
+    m, sd = _model(precision)
+    rs = np.random.RandomState(7)
+    img = rs.randint(0, 256, (2, 96, 80, 3)).astype(np.uint8)
+    img[0, :3] = 255; img[0, -2:] = 0; img[1, :, :2] = 255; img[1, :, -3:] = 0       # extreme values on every border
+    x_ref = torch.from_numpy(np.transpose(img, (0, 3, 1, 2)).copy()).float() / 255 - 0.5
+    ref = O.forward_dec(sd, x_ref)
+    d_img = torch.from_numpy(img).cuda()
+    out = m.forward_dec_u8(d_img)
+    flt = m.forward_dec(inference.preprocess_u8(d_img))
+    for s in range(4):
+        assert float((out[s][0].cpu() - ref[s][0]).abs().max()) <= kp_tol, s
+        # the two input paths differ by the stems' rounding only (1e-6 on the heat maps); the single-pass fp16 heads of `fast`
+        # amplify that to the size of their own rounding steps
+        assert float((out[s][0] - flt[s][0]).abs().max()) <= (1e-4 if precision == "exact" else 5e-4), s
+    for l in (0, 1):       # c0 (3x3 stem -> c0_conv.2 -> ...) and c1 features: relative to the map's magnitude
+        scale = max(1.0, float(ref[4][l].abs().max()))
+        assert float((out[4][l].cpu() - ref[4][l]).abs().max()) <= (feat_tol if precision == "exact" else 5e-3) * scale, l
+    with pytest.raises(ValueError):
+        m.forward_dec_u8(d_img.float())
+    m.precision = "reference"
+    with pytest.raises(RuntimeError):
+        m.forward_dec_u8(d_img)

@@ -12,8 +12,8 @@ tail -c 300 gpurun_out/${tag}_bench.json; echo
 python bench.py --workload decode --steps 20 --warmup 3 > gpurun_out/${tag}_bench_decode.json 2>> gpurun_out/${tag}_bench.err
 python bench.py --config cfg4 --steps 8 --warmup 3 --no-gpu-baseline > gpurun_out/${tag}_bench_cfg4.json 2>> gpurun_out/${tag}_bench.err
 python bench.py --free-running --steps 8 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_bench_free_running.json 2>> gpurun_out/${tag}_bench.err
-# launch list: every launch of the library's kernels in a 3 + 1 step run; tools/last_step.py keeps the final step (a step starts with
-# kg::preprocess_u8_kernel) -> gpurun_out/<tag>_launches.csv
+# launch list: every launch of the library's kernels in a 3 + 1 step run; tools/last_step.py keeps the timed step (a step starts with
+# the 3x3 stem kernel) -> gpurun_out/<tag>_launches.csv
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'kg::|tc_|vote|blur|exact_peaks|group_kernel|nms_kernel|bilinear|maxpool|preprocess|copy_rects|fill_rects' --csv \
     --log-file gpurun_out/${tag}_launches_all.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1
 python tools/last_step.py gpurun_out/${tag}_launches_all.csv gpurun_out/${tag}_launches.csv

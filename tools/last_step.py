@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Trim an `ncu --csv --metrics gpu__time_duration.sum` launch list to ONE step of bench.py (the first complete step after the
-warm-up: from one preprocess_u8 launch up to the next) and print the per-kernel-family shares.
+warm-up: from one launch of the first kernel of a step up to the next) and print the per-kernel-family shares.
 usage: tools/last_step.py <all_launches.csv> <out.csv>"""
 import csv
 import sys
@@ -13,7 +13,9 @@ def main(src, dst):
     head, body = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
     k, v, m = head.index("Kernel Name"), head.index("Metric Value"), head.index("Metric Name")
     body = [r for r in body if r[m] == "gpu__time_duration.sum"]
-    starts = [i for i, r in enumerate(body) if "preprocess_u8" in r[k]]
+    # a step starts with the 3x3 stem conv on the uint8 image (with the separate normalisation kernel in older captures)
+    first = "tc_stem_u8_kernel<3" if any("tc_stem_u8_kernel<3" in r[k] for r in body) else "preprocess_u8"
+    starts = [i for i, r in enumerate(body) if first in r[k]]
     if len(starts) < 5:
         raise SystemExit(f"expected >= 5 steps (3 warm-up + 1 timed + e2e) in {src}, found {len(starts)}")
     step = body[starts[3]:starts[4]]           # the timed step
