@@ -204,14 +204,15 @@ def run_decode(args, rank, world, dist):
     st_ms, st_cnt = _cabi.timing_collect()
     _cabi.timing_enable(False)
     px = BS * sum(h * w for h, w in shapes)
-    names = {0: "vote_kernel", 1: "blur32_candidates_kernel + exact_peaks_kernel", 2: "group_kernel", 3: "nms_kernel"}
+    # stage 0 is ONE timed region: the vote -> prefilter chains of the four scales run on concurrent streams (fork .. join)
+    names = {0: "vote_kernel + blur32_candidates_kernel (4 scales, concurrent streams)", 1: "exact_peaks_kernel", 2: "group_kernel", 3: "nms_kernel"}
     stage = {names[i]: {"ms_per_step": float(st_ms[i]) / args.steps, "launches_per_step": int(st_cnt[i]) // args.steps} for i in names}
     # the HBM-bound part of the decode is heat-map -> peak list (140 B per pixel and scale: vote reads 15 f32 and
     # writes 5 x 8 B accumulators, blur+peak reads them back once); grouping / NMS are latency-bound list kernels (~0 bytes)
     alg_bytes = px * (VOTE_BYTES_PX + BLUR_BYTES_PX)
     pk, pk_kind = peaks()
     dom_ms = float(st_ms[0] + st_ms[1]) / args.steps
-    dom_launches = int(st_cnt[0] + st_cnt[1]) // args.steps
+    dom_launches = 2 * len(shapes) + 1          # a vote and a prefilter launch per scale + the candidate re-evaluation
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic, traffic_src = profiled_traffic("decode")
     roofline = {"kernel": "vote_kernel + blur32_candidates_kernel + exact_peaks_kernel (head maps -> peak lists)", "bound": "hbm",
@@ -237,7 +238,7 @@ def run_decode(args, rank, world, dist):
 
 # ---------------------------------------------------------------------------------------------------------
 # FLOPs of forward_dec per image at 512x512 come from the plan census (kg_net_plan_info); SURVEY.md §8d: 1357.31 GF.
-STAGE_NAMES = {0: "vote", 1: "blur_peak", 2: "group", 3: "nms", 8: "conv_cuda_core", 9: "tc_backbone", 10: "tc_decoder",
+STAGE_NAMES = {0: "vote_blur_prefilter", 1: "exact_peaks", 2: "group", 3: "nms", 8: "conv_cuda_core", 9: "tc_backbone", 10: "tc_decoder",
                11: "tc_heads_l1", 12: "tc_heads_l2", 13: "bilinear", 14: "maxpool", 15: "export_feats", 16: "forward_seg"}
 
 

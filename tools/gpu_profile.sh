@@ -1,7 +1,8 @@
 #!/bin/bash
 # usage (on the GPU box, via gpurun): tools/gpu_profile.sh <tag>   -> gpurun_out/<tag>_*
 # pytest -m gpu, the default bench line (with CPU and cuDNN baselines), the decode / cfg4 / free-running lines, the ncu launch list of
-# one step and `--set full` captures of (a) the tensor-core launches and (b) the decode kernels of that step.
+# one step and `--set full` captures of (a) the tensor-core launches and (b) the decode kernels of that step (captured with --serial,
+# one batch in flight, so that the launches of a step are contiguous: forward_dec, decode, forward_seg).
 tag=${1:-r2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv,noheader > gpurun_out/${tag}_gpu.txt
@@ -28,10 +29,10 @@ PY
 )
   echo "tensor-core launches/step=$TC"
   timeout 900 ncu --set full --clock-control none -k regex:'tc_conv|tc_shift' -s $((3*TC)) -c $TC -f -o gpurun_out/${tag}_tc \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
+      python bench.py --serial --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1
   ncu -i gpurun_out/${tag}_tc.ncu-rep --page raw --csv > gpurun_out/${tag}_tc_raw.csv 2>/dev/null
   timeout 600 ncu --set full --clock-control none -k regex:'vote_kernel|blur32|exact_peaks' -s 27 -c 9 -f -o gpurun_out/${tag}_decode \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_ncu_decode.log 2>&1
+      python bench.py --serial --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/${tag}_ncu_decode.log 2>&1
   ncu -i gpurun_out/${tag}_decode.ncu-rep --page raw --csv > gpurun_out/${tag}_decode_raw.csv 2>/dev/null
   for f in gpurun_out/${tag}_tc.ncu-rep gpurun_out/${tag}_decode.ncu-rep; do
     sz=$(stat -c %s $f 2>/dev/null || echo 0); if [ "$sz" -gt 30000000 ]; then rm -f $f; fi
