@@ -204,8 +204,8 @@ def run_decode(args, rank, world, dist):
     st_ms, st_cnt = _cabi.timing_collect()
     _cabi.timing_enable(False)
     px = BS * sum(h * w for h, w in shapes)
-    # stage 0 is ONE timed region: the vote -> prefilter chains of the four scales run on concurrent streams (fork .. join)
-    names = {0: "vote_kernel + blur32_candidates_kernel (4 scales, concurrent streams)", 1: "exact_peaks_kernel", 2: "group_kernel", 3: "nms_kernel"}
+    # stage 0 is ONE timed region (vote + prefilter of the four scales: 8 launches back to back)
+    names = {0: "vote_kernel + blur32_candidates_kernel (4 scales)", 1: "exact_peaks_kernel", 2: "group_kernel", 3: "nms_kernel"}
     stage = {names[i]: {"ms_per_step": float(st_ms[i]) / args.steps, "launches_per_step": int(st_cnt[i]) // args.steps} for i in names}
     # the HBM-bound part of the decode is heat-map -> peak list (140 B per pixel and scale: vote reads 15 f32 and
     # writes 5 x 8 B accumulators, blur+peak reads them back once); grouping / NMS are latency-bound list kernels (~0 bytes)

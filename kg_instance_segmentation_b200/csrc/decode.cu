@@ -1167,29 +1167,6 @@ size_t decode_workspace_bytes(const kg_decode_config* cfg, const kg_decode_scale
 static size_t group_smem(int P) { return (size_t)P * 24 + 16; }
 static size_t nms_smem(int B) { return (((size_t)B * 13 + 15) & ~(size_t)15) + (size_t)std::min(B, NMS_MASK_CAP) * 32; }   // + staged boxes of the bit-matrix path
 
-// The vote -> prefilter chains of the scales are independent until the candidate re-evaluation, and the coarse scales' launches are
-// too small to fill the chip (scale 3 at bs32: 160 vote CTAs): they run on three side streams (fork / join with events, the pattern
-// stream capture understands) next to scale 0 on the caller's stream.
-struct SideStreams {
-  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
-  bool ready = false;
-};
-static SideStreams* side_streams() {
-  static SideStreams per_device[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideStreams& ss = per_device[dev];
-  if (!ss.ready) {
-    if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    for (int i = 0; i < 3; ++i)
-      if (cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    ss.ready = true;
-  }
-  return &ss;
-}
-
 int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const kg_decode_outputs* out, void* workspace,
                   size_t workspace_bytes, cudaStream_t stream, int* n_launches) {
   KG_TRY(check_config(cfg, sc));
@@ -1212,32 +1189,23 @@ int decode_launch(const kg_decode_config* cfg, const kg_decode_scale* sc, const 
   double* peak_conf = out->d_peak_conf ? out->d_peak_conf : w.peak_conf;
   int* peak_key = out->d_peak_key ? out->d_peak_key : w.peak_key;
   int* peak_count = w.peak_count;
-  // KG_DECODE_SERIAL=1: every scale on the caller's stream (A/B of the side streams)
-  static const bool serial_scales = getenv("KG_DECODE_SERIAL") != nullptr;
-  SideStreams* side = (S > 1 && S <= 4 && !serial_scales) ? side_streams() : nullptr;
   {
-    // stage 0 = vote + prefilter of all scales (the scales overlap, so they are timed as one region: fork .. join)
+    // stage 0 = vote + prefilter of all scales, timed as one region.  (Running the scales' chains on concurrent side streams was
+    // measured: 0.855 vs 0.853 ms -- the coarse scales' small grids are not what the time goes to.)
     StageScope t(0, stream);
-    if (side) KG_CUDA_CHECK(cudaEventRecord(side->fork, stream));
     for (int s = 0; s < S; ++s) {
-      cudaStream_t st = (side && s > 0) ? side->s[s - 1] : stream;
-      if (side && s > 0) KG_CUDA_CHECK(cudaStreamWaitEvent(st, side->fork, 0));
       const int H = sc[s].H, W = sc[s].W;
       dim3 g1(ceil_div(W, VT_W), ceil_div(H, VT_H), N * 5);
-      vote_kernel<<<g1, 256, 0, st>>>(sc[s].d_kp, sc[s].d_short, w.acc[s], H, W);
+      vote_kernel<<<g1, 256, 0, stream>>>(sc[s].d_kp, sc[s].d_short, w.acc[s], H, W);
       BlurParams bp{};
       bp.acc = w.acc[s]; bp.H = H; bp.W = W; bp.peak_thresh = cfg->peak_thresh; bp.list_index_base = s; bp.n_scales = S; bp.max_peaks = P;
       bp.peak_conf = peak_conf; bp.peak_key = peak_key; bp.peak_count = peak_count;
       bp.out_vote = out->d_vote[s]; bp.out_heat = out->d_heat[s]; bp.status = out->d_status;
       bp.cand = w.cand; bp.cand_count = w.cand_count; bp.cand_cap = w.cand_cap; bp.scale = s;
       bp.emit_peaks = all_fp64 ? 1 : 0;
-      if (all_fp64 || bp.out_vote != nullptr || bp.out_heat != nullptr) { KG_TRY(launch_blur_peak(bp, N, st)); ++launches; }
-      if (!all_fp64) { KG_TRY(launch_blur32(bp, N, st)); ++launches; }
+      if (all_fp64 || bp.out_vote != nullptr || bp.out_heat != nullptr) { KG_TRY(launch_blur_peak(bp, N, stream)); ++launches; }
+      if (!all_fp64) { KG_TRY(launch_blur32(bp, N, stream)); ++launches; }
       launches += 1;
-      if (side && s > 0) {
-        KG_CUDA_CHECK(cudaEventRecord(side->join[s - 1], st));
-        KG_CUDA_CHECK(cudaStreamWaitEvent(stream, side->join[s - 1], 0));
-      }
     }
   }
   if (!all_fp64) {
