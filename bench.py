@@ -523,6 +523,7 @@ def run_pipeline(args, rank, world, dist):
                    "config": args.config, "global_batch": gbs, "precision": args.precision, "detections_per_step": n_det,
                    "detection_record_truncated": truncated,
                    "batches_in_flight": 1 if args.serial else 2,
+                   "env_switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("KG_")},
                    "l2_note": "activations of one step (>20 GB) exceed L2; no flush needed"},
         "e2e": {"value": round(gbs * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": x_host.numel(),
                 "d2h_bytes_per_step": det_host.numel() * 8 + int(state.get("mask_floats", 0)) * 4},

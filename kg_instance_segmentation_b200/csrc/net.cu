@@ -334,6 +334,64 @@ struct PlanBuilder {
   }
 };
 
+// Workspace placement by liveness.  The builder above hands out consecutive offsets (21 GB for a bs32 / 512^2 step); every kernel of
+// a pass runs on one stream in op order, so a tensor's planes can be reused once its last reader has been enqueued.  First-fit over a
+// free list of byte ranges, in op order: a tensor is placed when its producer is reached and released AFTER its last consumer (an op
+// never writes into the memory of its own inputs).  The five feature maps forward_seg reads later (and kg_net_import_feats writes)
+// are never released.  KG_NO_WS_REUSE=1 keeps the consecutive layout (A/B, debugging).
+static void place_by_liveness(Plan* p) {
+  if (getenv("KG_NO_WS_REUSE") != nullptr) return;
+  const int nt = (int)p->tensors.size(), nop = (int)p->ops.size();
+  std::vector<int> def(nt, -1), last(nt, -1);
+  for (int i = 0; i < nop; ++i) {
+    const Op& op = p->ops[i];
+    if (op.out >= 0 && def[op.out] < 0) def[op.out] = i;
+    for (int t : {op.in0, op.in1, op.res})
+      if (t >= 0) last[t] = std::max(last[t], i);
+  }
+  for (int l = 0; l < 5; ++l) last[p->feat_ids[l]] = nop + 1;                       // persistent
+  for (int t = 0; t < nt; ++t) { if (def[t] < 0) def[t] = 0; last[t] = std::max(last[t], def[t]); }
+  struct Range { size_t off, len; };
+  std::vector<Range> freel;                                                          // sorted by offset, coalesced
+  size_t top = 0;
+  auto take = [&](size_t len) -> size_t {
+    for (size_t i = 0; i < freel.size(); ++i)
+      if (freel[i].len >= len) {
+        const size_t o = freel[i].off;
+        freel[i].off += len; freel[i].len -= len;
+        if (freel[i].len == 0) freel.erase(freel.begin() + (long)i);
+        return o;
+      }
+    const size_t o = top; top += len; return o;
+  };
+  auto give = [&](size_t off, size_t len) {
+    size_t i = 0;
+    while (i < freel.size() && freel[i].off < off) ++i;
+    freel.insert(freel.begin() + (long)i, Range{off, len});
+    if (i + 1 < freel.size() && freel[i].off + freel[i].len == freel[i + 1].off) { freel[i].len += freel[i + 1].len; freel.erase(freel.begin() + (long)i + 1); }
+    if (i > 0 && freel[i - 1].off + freel[i - 1].len == freel[i].off) { freel[i - 1].len += freel[i].len; freel.erase(freel.begin() + (long)i); }
+  };
+  std::vector<std::vector<int>> born(nop), dies(nop + 1);
+  for (int t = 0; t < nt; ++t) {
+    born[def[t]].push_back(t);
+    if (last[t] < nop) dies[last[t] + 1].push_back(t);                               // released once its last reader (op last[t]) is enqueued
+  }
+  auto plane_bytes = [&](const Tensor& T) { return align_up((size_t)p->N * T.H * T.W * T.C * sizeof(__half), 1024); };
+  for (int i = 0; i < nop; ++i) {
+    for (int t : dies[i]) {
+      const Tensor& T = p->tensors[t];
+      give(T.off_hi, plane_bytes(T));
+      if (T.off_lo != (size_t)-1) give(T.off_lo, plane_bytes(T));
+    }
+    for (int t : born[i]) {
+      Tensor& T = p->tensors[t];
+      T.off_hi = take(plane_bytes(T));
+      if (T.off_lo != (size_t)-1) T.off_lo = take(plane_bytes(T));
+    }
+  }
+  p->bytes = top;
+}
+
 // precision: 0 = CUDA-core fp32 everywhere (on-device reference), 1 = "fast": tensor cores, split-fp16 3-pass in the
 // backbone/decoder and single-pass fp16 in the heads, 2 = "exact": tensor cores, 3-pass everywhere.
 static void assign_tc(Plan* p, int precision) {
@@ -437,6 +495,7 @@ static int build_plan(Net* net, int N, int H, int W, int precision) {
   const int fe[5] = {c0, c1, c2, c3, c4};
   for (int l = 0; l < 5; ++l) { p->feat_ids[l] = fe[l]; b.exportf(fe[l], 12 + l); }
   p->bytes = b.off;
+  place_by_liveness(p.get());
   assign_tc(p.get(), precision);
   KG_CUDA_CHECK(cudaMalloc(&p->d_conv_probs, p->h_conv_probs.size() * sizeof(ConvProb)));
   KG_CUDA_CHECK(cudaMemcpy(p->d_conv_probs, p->h_conv_probs.data(), p->h_conv_probs.size() * sizeof(ConvProb), cudaMemcpyHostToDevice));

@@ -331,3 +331,13 @@ def test_forward_dec_u8_matches_oracle_and_float_path(precision, kp_tol, feat_to
     m.precision = "reference"
     with pytest.raises(RuntimeError):
         m.forward_dec_u8(d_img)
+
+
+def test_workspace_is_placed_by_liveness():
+    """The activation workspace reuses the planes of dead tensors: a bs32 / 512 x 512 `fast` pass needs well under half of the
+    21 GB a consecutive layout takes (the parity tests of this file and of test_parity_full_gpu.py run on the reused layout)."""
+    from kg_instance_segmentation_b200 import _cabi
+    m, _ = _model("fast")
+    m._sync_weights()
+    nbytes = _cabi.lib().kg_net_workspace_bytes(m._handle, 32, 512, 512, 1)
+    assert 4e9 < nbytes < 11e9, nbytes
