@@ -11,6 +11,8 @@ def q16(t):
 def run(sd, x, groups, blocks=(3, 4, 6)):
     def conv(xx, name, group, bias=True, stride=1, pad=0):
         w = sd[name + ".weight"]; b = sd.get(name + ".bias") if bias else None
+        if (group + ":a") in groups:                          # "<group>:a" rounds only the activations (weights stay split-fp16)
+            xx = q16(xx)
         if group in groups or (group + ":w") in groups:       # "<group>:w" rounds only the weights (activations stay split-fp16)
             mx = w.abs().max(); sc = 2.0 ** (10 - torch.frexp(mx)[1].item())
             if group in groups:
@@ -57,7 +59,8 @@ for seed in (0, 1):
     torch.manual_seed(seed)
     x = torch.rand(1, 3, size, size) - 0.5
     ref = run(sd, x, set())
-    for groups in (["head1", "head2"], ["head1", "head2", "c0b:w", "c1up:w"], ["head1", "head2", "c0b:w", "c1up:w", "c2up:w"],
+    cases = os.environ.get("KG_EMU_CASES")
+    for groups in ([c.split("+") for c in cases.split(",")] if cases else []) or (["head1", "head2"], ["head1", "head2", "c0b:w", "c1up:w"], ["head1", "head2", "c0b:w", "c1up:w", "c2up:w"],
                    ["head1", "head2", "c0b:w", "c1up:w", "dec_cat:w"], ["head1", "head2", "dec_up"], ["head1", "head2", "dec_cat"], ["head1", "head2", "dec_up", "dec_cat"],
                    ["head1", "head2", "dec_up", "dec_cat", "c0b"], ["head1", "head2", "backbone"],
                    ["head1", "head2", "dec_up", "dec_cat", "c0b", "backbone"]):
