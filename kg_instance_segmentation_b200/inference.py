@@ -94,7 +94,8 @@ class InstanceHeat:
         if self._slots is None:
             self._slots = [{"model": self.model, "pending": None}, None]
         if self._slots[k] is None:
-            twin = KGnet.resnet50(pretrained=False, precision=self.model.precision)
+            with torch.device("meta"):                      # no storage, no random initialisation: every tensor is replaced below
+                twin = KGnet.resnet50(pretrained=False, precision=self.model.precision)
             src = dict(self.model.named_modules())
             for name, mod in twin.named_modules():           # the SAME Parameter / buffer objects: weight updates reach both engines
                 for key in list(mod._parameters):
