@@ -240,6 +240,16 @@ __device__ __forceinline__ void ld8_split(const __half* hi, const __half* lo, lo
   }
 }
 
+// hi = fp16(v) with saturation to +-65504 (one packed convert, F2FP.SATFINITE: replaces an explicit clamp), lo = fp16(v - hi)
+__device__ __forceinline__ void split2_sat(float a, float b, __half2& hi, __half2& lo) {
+  uint32_t h, l;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(b - hf.y), "f"(a - hf.x));
+  hi = *reinterpret_cast<const __half2*>(&h);
+  lo = *reinterpret_cast<const __half2*>(&l);
+}
+
 __global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
                                                        int in_ps, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                                                        int out_ps, int C, const ResizeProb* __restrict__ probs) {
@@ -280,13 +290,9 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const __half* __restrict_
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int k = 2 * j + t;
-      const float v = ly0 * (lx0 * v00[k] + lx1 * v01[k]) + ly1 * (lx0 * v10[k] + lx1 * v11[k]);
-      r[t] = fminf(fmaxf(v, -65504.f), 65504.f);
+      r[t] = ly0 * (lx0 * v00[k] + lx1 * v01[k]) + ly1 * (lx0 * v10[k] + lx1 * v11[k]);
     }
-    const __half2 h = __floats2half2_rn(r[0], r[1]);
-    const float2 hf = __half22float2(h);
-    hh[j] = h;
-    ll[j] = __floats2half2_rn(r[0] - hf.x, r[1] - hf.y);
+    split2_sat(r[0], r[1], hh[j], ll[j]);
   }
   *reinterpret_cast<uint4*>(out_hi + o) = h4;
   if (out_lo != nullptr) *reinterpret_cast<uint4*>(out_lo + o) = l4;
@@ -358,13 +364,9 @@ __global__ void __launch_bounds__(256) bilinear_rows_kernel(const __half* __rest
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int k = 2 * j + t;
-            const float val = ly0 * (lx0 * v00[r][k] + lx1 * v01[r][k]) + ly1[r] * (lx0 * v10[r][k] + lx1 * v11[r][k]);
-            q[t] = fminf(fmaxf(val, -65504.f), 65504.f);
+            q[t] = ly0 * (lx0 * v00[r][k] + lx1 * v01[r][k]) + ly1[r] * (lx0 * v10[r][k] + lx1 * v11[r][k]);
           }
-          const __half2 h = __floats2half2_rn(q[0], q[1]);
-          const float2 hf = __half22float2(h);
-          hh[j] = h;
-          ll[j] = __floats2half2_rn(q[0] - hf.x, q[1] - hf.y);
+          split2_sat(q[0], q[1], hh[j], ll[j]);
         }
       }
       *reinterpret_cast<uint4*>(out_hi + o) = h4;
@@ -415,14 +417,10 @@ __global__ void __launch_bounds__(256) bilinear2x_kernel(const __half* __restric
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int ch = 2 * k + t;
-          const float val = wy[py][0] * (wx[px][0] * v[py][px][ch] + wx[px][1] * v[py][px + 1][ch]) +
-                            wy[py][1] * (wx[px][0] * v[py + 1][px][ch] + wx[px][1] * v[py + 1][px + 1][ch]);
-          o[t] = fminf(fmaxf(val, -65504.f), 65504.f);
+          o[t] = wy[py][0] * (wx[px][0] * v[py][px][ch] + wx[px][1] * v[py][px + 1][ch]) +
+                 wy[py][1] * (wx[px][0] * v[py + 1][px][ch] + wx[px][1] * v[py + 1][px + 1][ch]);
         }
-        const __half2 h = __floats2half2_rn(o[0], o[1]);
-        const float2 hf = __half22float2(h);
-        hh[k] = h;
-        ll[k] = __floats2half2_rn(o[0] - hf.x, o[1] - hf.y);
+        split2_sat(o[0], o[1], hh[k], ll[k]);
       }
       const long long op = (oimg + (long long)(2 * i + py) * Wout + (2 * j + px)) * C + c;
       *reinterpret_cast<uint4*>(out_hi + op) = h4;
