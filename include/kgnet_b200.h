@@ -250,6 +250,12 @@ int kg_detection_loss_backward(const float* d_pr_kp, const float* d_pr_short, co
 int kg_seg_loss_pairs_backward(const float* d_masks, const void* d_pairs, int n_pairs, const float* d_gt_masks, int H, int W,
                                const float* d_pair_coeff, float* d_grad_masks, void* stream);
 
+/* Test hook (host only, no GPU needed): the first-fit placement by liveness that lays out the activation workspace of forward_dec.
+ * Buffer b (bytes[b]) is first written by op def[b] and last read by op last[b] (last[b] >= n_ops: never released); a buffer may reuse
+ * memory released by ops < def[b] only.  Writes the byte offsets and the arena size. */
+int kg_debug_place_by_liveness(int n_ops, int n_buffers, const int* def, const int* last, const unsigned long long* bytes,
+                               unsigned long long* offsets, unsigned long long* total);
+
 /* 1 when the tcgen05/TMA path initialised on the current device; kg_tc_status() says why not otherwise. */
 int kg_tc_available(void);
 const char* kg_tc_status(void);

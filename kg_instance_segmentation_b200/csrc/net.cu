@@ -339,18 +339,11 @@ struct PlanBuilder {
 // free list of byte ranges, in op order: a tensor is placed when its producer is reached and released AFTER its last consumer (an op
 // never writes into the memory of its own inputs).  The five feature maps forward_seg reads later (and kg_net_import_feats writes)
 // are never released.  KG_NO_WS_REUSE=1 keeps the consecutive layout (A/B, debugging).
-static void place_by_liveness(Plan* p) {
-  if (getenv("KG_NO_WS_REUSE") != nullptr) return;
-  const int nt = (int)p->tensors.size(), nop = (int)p->ops.size();
-  std::vector<int> def(nt, -1), last(nt, -1);
-  for (int i = 0; i < nop; ++i) {
-    const Op& op = p->ops[i];
-    if (op.out >= 0 && def[op.out] < 0) def[op.out] = i;
-    for (int t : {op.in0, op.in1, op.res})
-      if (t >= 0) last[t] = std::max(last[t], i);
-  }
-  for (int l = 0; l < 5; ++l) last[p->feat_ids[l]] = nop + 1;                       // persistent
-  for (int t = 0; t < nt; ++t) { if (def[t] < 0) def[t] = 0; last[t] = std::max(last[t], def[t]); }
+// Core of the placement, free of plan types (kg_debug_place_by_liveness exposes it to the CPU tests): buffer b of `bytes[b]` bytes is
+// written first by op def[b] and read last by op last[b] (last[b] >= n_ops: never released).  Returns the arena size.
+static size_t first_fit_by_liveness(int n_ops, const std::vector<int>& def, const std::vector<int>& last, const std::vector<size_t>& bytes,
+                                    std::vector<size_t>& off) {
+  const int nb = (int)bytes.size();
   struct Range { size_t off, len; };
   std::vector<Range> freel;                                                          // sorted by offset, coalesced
   size_t top = 0;
@@ -364,32 +357,54 @@ static void place_by_liveness(Plan* p) {
       }
     const size_t o = top; top += len; return o;
   };
-  auto give = [&](size_t off, size_t len) {
+  auto give = [&](size_t o, size_t len) {
+    if (len == 0) return;
     size_t i = 0;
-    while (i < freel.size() && freel[i].off < off) ++i;
-    freel.insert(freel.begin() + (long)i, Range{off, len});
+    while (i < freel.size() && freel[i].off < o) ++i;
+    freel.insert(freel.begin() + (long)i, Range{o, len});
     if (i + 1 < freel.size() && freel[i].off + freel[i].len == freel[i + 1].off) { freel[i].len += freel[i + 1].len; freel.erase(freel.begin() + (long)i + 1); }
     if (i > 0 && freel[i - 1].off + freel[i - 1].len == freel[i].off) { freel[i - 1].len += freel[i].len; freel.erase(freel.begin() + (long)i); }
   };
-  std::vector<std::vector<int>> born(nop), dies(nop + 1);
-  for (int t = 0; t < nt; ++t) {
-    born[def[t]].push_back(t);
-    if (last[t] < nop) dies[last[t] + 1].push_back(t);                               // released once its last reader (op last[t]) is enqueued
+  std::vector<std::vector<int>> born(n_ops), dies(n_ops + 1);
+  for (int b = 0; b < nb; ++b) {
+    born[def[b]].push_back(b);
+    if (last[b] < n_ops) dies[last[b] + 1].push_back(b);                             // released once its last reader (op last[b]) is enqueued
   }
-  auto plane_bytes = [&](const Tensor& T) { return align_up((size_t)p->N * T.H * T.W * T.C * sizeof(__half), 1024); };
+  off.assign(nb, 0);
+  for (int i = 0; i < n_ops; ++i) {
+    for (int b : dies[i]) give(off[b], bytes[b]);
+    for (int b : born[i]) off[b] = take(bytes[b]);
+  }
+  return top;
+}
+
+static void place_by_liveness(Plan* p) {
+  if (getenv("KG_NO_WS_REUSE") != nullptr) return;
+  const int nt = (int)p->tensors.size(), nop = (int)p->ops.size();
+  std::vector<int> def(nt, -1), last(nt, -1);
   for (int i = 0; i < nop; ++i) {
-    for (int t : dies[i]) {
-      const Tensor& T = p->tensors[t];
-      give(T.off_hi, plane_bytes(T));
-      if (T.off_lo != (size_t)-1) give(T.off_lo, plane_bytes(T));
-    }
-    for (int t : born[i]) {
-      Tensor& T = p->tensors[t];
-      T.off_hi = take(plane_bytes(T));
-      if (T.off_lo != (size_t)-1) T.off_lo = take(plane_bytes(T));
-    }
+    const Op& op = p->ops[i];
+    if (op.out >= 0 && def[op.out] < 0) def[op.out] = i;
+    for (int t : {op.in0, op.in1, op.res})
+      if (t >= 0) last[t] = std::max(last[t], i);
   }
-  p->bytes = top;
+  for (int l = 0; l < 5; ++l) last[p->feat_ids[l]] = nop + 1;                       // persistent
+  for (int t = 0; t < nt; ++t) { if (def[t] < 0) def[t] = 0; last[t] = std::max(last[t], def[t]); }
+  // one buffer per plane: hi of tensor t = 2 t, lo = 2 t + 1 (size 0 when the tensor has no lo plane)
+  std::vector<int> bdef(2 * nt), blast(2 * nt);
+  std::vector<size_t> bytes(2 * nt), off;
+  for (int t = 0; t < nt; ++t) {
+    const Tensor& T = p->tensors[t];
+    const size_t len = align_up((size_t)p->N * T.H * T.W * T.C * sizeof(__half), 1024);
+    bdef[2 * t] = bdef[2 * t + 1] = def[t]; blast[2 * t] = blast[2 * t + 1] = last[t];
+    bytes[2 * t] = len; bytes[2 * t + 1] = T.off_lo != (size_t)-1 ? len : 0;
+  }
+  p->bytes = first_fit_by_liveness(nop, bdef, blast, bytes, off);
+  for (int t = 0; t < nt; ++t) {
+    Tensor& T = p->tensors[t];
+    T.off_hi = off[2 * t];
+    if (T.off_lo != (size_t)-1) T.off_lo = off[2 * t + 1];
+  }
 }
 
 // precision: 0 = CUDA-core fp32 everywhere (on-device reference), 1 = "fast": tensor cores, split-fp16 3-pass in the
@@ -1277,6 +1292,20 @@ int kg_net_set_conv(kg_net* h, const char* name, const float* h_w, int Cout, int
 int kg_net_finalize(kg_net* h) {
   KG_REQUIRE(h != nullptr, "kg_net_finalize: null handle");
   return finalize(reinterpret_cast<Net*>(h));
+}
+
+int kg_debug_place_by_liveness(int n_ops, int n_buffers, const int* def, const int* last, const unsigned long long* bytes,
+                               unsigned long long* offsets, unsigned long long* total) {
+  KG_REQUIRE(n_ops > 0 && n_buffers >= 0 && def && last && bytes && offsets && total, "kg_debug_place_by_liveness: bad arguments");
+  std::vector<int> d(def, def + n_buffers), l(last, last + n_buffers);
+  std::vector<size_t> by(n_buffers), off;
+  for (int b = 0; b < n_buffers; ++b) {
+    KG_REQUIRE(d[b] >= 0 && d[b] < n_ops && l[b] >= d[b], "kg_debug_place_by_liveness: buffer %d has def=%d last=%d", b, d[b], l[b]);
+    by[b] = (size_t)bytes[b];
+  }
+  *total = first_fit_by_liveness(n_ops, d, l, by, off);
+  for (int b = 0; b < n_buffers; ++b) offsets[b] = off[b];
+  return KG_OK;
 }
 
 size_t kg_net_workspace_bytes(kg_net* h, int N, int H, int W, int precision) {

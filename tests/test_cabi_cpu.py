@@ -61,3 +61,43 @@ def test_no_cpu_fallback_in_product_package():
         src = open(f).read()
         assert "oracle" not in src.replace("no CPU or PyTorch-op fallback", ""), f
         assert "F.conv2d" not in src and "scipy" not in src, f
+
+
+def test_workspace_placement_never_overlaps_live_buffers():
+    """kg_debug_place_by_liveness = the first-fit placement that lays out forward_dec's activation workspace.  Property: two buffers
+    whose lifetimes [def, last] intersect -- or touch: an op must not write into the memory of its own inputs -- never share a byte;
+    persistent buffers (last >= n_ops) are never reused; the arena is no larger than the consecutive layout."""
+    import ctypes as C
+    import numpy as np
+    from kg_instance_segmentation_b200 import _cabi
+    L = _cabi.lib()
+    rs = np.random.RandomState(0)
+    for trial in range(200):
+        n_ops = int(rs.randint(1, 60))
+        nb = int(rs.randint(0, 80))
+        d = rs.randint(0, n_ops, nb).astype(np.int32)
+        span = rs.randint(0, 12, nb)
+        last = np.minimum(d + span, n_ops - 1).astype(np.int32)
+        keep = rs.rand(nb) < 0.1
+        last[keep] = n_ops + 1
+        size = (rs.randint(0, 50, nb) * 1024).astype(np.uint64)        # zero-sized buffers occur (tensors without a lo plane)
+        off = np.zeros(nb, np.uint64)
+        total = C.c_ulonglong(0)
+        _cabi.check(L.kg_debug_place_by_liveness(n_ops, nb, d.ctypes.data, last.ctypes.data, size.ctypes.data, off.ctypes.data,
+                                                 C.byref(total)))
+        assert total.value <= int(size.sum())
+        for a in range(nb):
+            assert int(off[a]) + int(size[a]) <= total.value
+            for b in range(a + 1, nb):
+                if size[a] == 0 or size[b] == 0:
+                    continue
+                live_together = not (last[a] < d[b] or last[b] < d[a])
+                if live_together:
+                    assert int(off[a]) + int(size[a]) <= int(off[b]) or int(off[b]) + int(size[b]) <= int(off[a]), (trial, a, b)
+    # a chain a -> b -> c of equal sizes needs two slots, not three
+    d = np.array([0, 1, 2], np.int32); last = np.array([1, 2, 2], np.int32); size = np.array([4096] * 3, np.uint64)
+    off = np.zeros(3, np.uint64); total = C.c_ulonglong(0)
+    _cabi.check(L.kg_debug_place_by_liveness(3, 3, d.ctypes.data, last.ctypes.data, size.ctypes.data, off.ctypes.data, C.byref(total)))
+    assert total.value == 8192 and off[2] == off[0]
+    assert L.kg_debug_place_by_liveness(3, 1, np.array([5], np.int32).ctypes.data, last.ctypes.data, size.ctypes.data, off.ctypes.data,
+                                        C.byref(total)) != 0
