@@ -193,3 +193,39 @@ def test_loss_restatements_match_reference_modules(reference):
         ref = RS.SEG_loss(H, W)([patches, dets], gt_masks, gt_boxes)
     assert torch.equal(ref, O.seg_loss([patches, dets], gt_masks, gt_boxes, H, W))
     assert O.seg_loss([[[]], [[]]], [gt_masks[0]], [gt_boxes[0]], H, W) is None
+
+
+def test_loss_gradients_of_the_restatements_match_the_reference_modules(reference):
+    """The device gradients (tests/test_train_side_gpu.py) are checked against torch autograd of the ORACLE losses: pin that
+    autograd of the oracle equals autograd of the reference's own modules (`loss.backward()`, train.py:150)."""
+    import warnings
+    import loss as RL
+    import seg_loss as RS
+    torch.manual_seed(1)
+    N, H, W = 2, 24, 32
+    base = [torch.rand(N, 5, H, W) * 0.98 + 0.01, torch.randn(N, 10, H, W), torch.randn(N, 40, H, W)]
+    gt = torch.zeros(N, 55, H, W)
+    gt[:, :5] = (torch.rand(N, 5, H, W) > 0.8).float(); gt[:, 5:] = torch.randn(N, 50, H, W)
+    a = [t.clone().requires_grad_(True) for t in base]
+    b = [t.clone().requires_grad_(True) for t in base]
+    RL.DetectionLossAll(5)(a, gt).backward()
+    O.detection_loss(b, gt)[0].backward()
+    for x, y in zip(a, b):
+        assert torch.equal(x.grad, y.grad)
+    rs = np.random.RandomState(0)
+    gt_masks = [rs.rand(3, H, W).round().astype(np.float32), rs.rand(2, H, W).round().astype(np.float32)]
+    gt_boxes = [np.array([[2, 3, 14, 20, 1], [10, 10, 22, 30, 1], [0, 0, 5, 5, 1]], np.float32), np.array([[4, 4, 20, 28, 1], [1, 1, 3, 3, 1]], np.float32)]
+    shapes = [[(12, 17), (11, 19)], [(16, 24)]]
+    dets = [[torch.Tensor([2.2, 3.1, 14.4, 20.3, 0.9]), torch.Tensor([10.6, 10.2, 21.7, 29.9, 0.8])], [torch.Tensor([4, 4, 20, 28, 0.7])]]
+    pbase = [[torch.rand(s) * 0.98 + 0.01 for s in per] for per in shapes]
+    pa = [[t.clone().requires_grad_(True) for t in per] for per in pbase]
+    pb = [[t.clone().requires_grad_(True) for t in per] for per in pbase]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        RS.SEG_loss(H, W)([pa, dets], gt_masks, gt_boxes).backward()
+    O.seg_loss([pb, dets], gt_masks, gt_boxes, H, W).backward()
+    for per_a, per_b in zip(pa, pb):
+        for x, y in zip(per_a, per_b):
+            assert (x.grad is None) == (y.grad is None)
+            if x.grad is not None:
+                assert torch.equal(x.grad, y.grad)

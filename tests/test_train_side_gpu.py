@@ -180,3 +180,51 @@ def test_validation_step_flow():
                for s, sc in enumerate((1, 2, 4, 8)))
     ref2 = O.seg_loss(O.forward_seg(sd, ref_out[4], bboxes_c0), masks, bboxes_c0, H, W)
     np.testing.assert_allclose(total, float(ref1 + ref2), rtol=2e-3)
+
+
+def test_training_step_through_an_autograd_network():
+    """train.py:145-154 with the loss modules swapped: an autograd network (here a small torch conv net standing in for the
+    reference's nn.Module) -> DetectionLossAll -> loss.backward() -> optimizer step.  The parameter gradients through this library's
+    fused loss kernels must equal those through the oracle's torch loss, and an SGD step must lower the loss."""
+    from kg_instance_segmentation_b200 import loss
+    torch.manual_seed(0)
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = torch.nn.Conv2d(3, 16, 3, padding=1)
+            self.kp = torch.nn.Conv2d(16, 5, 3, padding=1)
+            self.sh = torch.nn.Conv2d(16, 10, 3, padding=1)
+            self.mid = torch.nn.Conv2d(16, 40, 3, padding=1)
+
+        def forward(self, x):
+            f = torch.relu(self.body(x))
+            return [torch.sigmoid(self.kp(f)), self.sh(f), self.mid(f)]
+
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net_a, net_b = Tiny().cuda(), Tiny().cuda()
+        net_b.load_state_dict(net_a.state_dict())
+        x = torch.rand(2, 3, 48, 64, device="cuda") - 0.5
+        gt = torch.zeros(2, 55, 48, 64, device="cuda")
+        gt[:, :5] = (torch.rand(2, 5, 48, 64, device="cuda") > 0.9).float(); gt[:, 5:] = torch.randn(2, 50, 48, 64, device="cuda") * 3
+        crit = loss.DetectionLossAll(5)
+        la = crit(net_a(x), gt)
+        la.backward()
+        lb = O.detection_loss(net_b(x), gt)[0]
+        lb.backward()
+        np.testing.assert_allclose(float(la), float(lb), rtol=2e-6)
+        for (name, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+            scale = float(pb.grad.abs().max())
+            np.testing.assert_allclose(pa.grad.cpu().numpy(), pb.grad.cpu().numpy(), rtol=2e-4, atol=2e-6 * scale, err_msg=name)
+        opt = torch.optim.SGD(net_a.parameters(), lr=0.05)
+        first = float(la)
+        for _ in range(5):
+            opt.zero_grad()
+            l = crit(net_a(x), gt)
+            l.backward()
+            opt.step()
+        assert float(crit(net_a(x), gt)) < first
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
