@@ -91,6 +91,10 @@ class InstanceHeat:
     # the boxes of batch i, which by then landed in pinned memory long ago; forward_seg(i) queues up behind decode(i+1).  Two slots
     # (engine + workspaces + decode buffers each) alternate; the second engine shares the first one's parameter tensors.
     def _slot(self, k):
+        if self._slots is not None and self._slots[0]["model"] is not self.model:      # the caller swapped engine.model
+            if any(sl is not None and sl["pending"] is not None for sl in self._slots):
+                raise RuntimeError("engine.model was replaced while a batch is in flight: collect() first")
+            self._slots = None
         if self._slots is None:
             self._slots = [{"model": self.model, "pending": None}, None]
         if self._slots[k] is None:

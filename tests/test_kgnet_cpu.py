@@ -107,3 +107,28 @@ def test_weight_signature_sees_every_kind_of_update():
     m.double()
     assert changed()
     assert len(sigs[-1]) == len(list(m.parameters())) + len(list(m.buffers()))
+
+
+def test_twin_engine_shares_the_parameters():
+    """InstanceHeat.submit / collect alternate between the model and a twin built on the meta device whose parameters and buffers are
+    the SAME tensor objects (weight updates reach both); swapping engine.model rebuilds the twin."""
+    from kg_instance_segmentation_b200 import KGnet
+    from kg_instance_segmentation_b200.inference import InstanceHeat
+    m = KGnet.resnet50(pretrained=False)
+    eng = InstanceHeat(model=m, device="cpu")
+    twin = eng._slot(1)["model"]
+    assert twin is not m and eng._slot(0)["model"] is m
+    pm, pt = dict(m.named_parameters()), dict(twin.named_parameters())
+    assert set(pm) == set(pt) and all(pm[k] is pt[k] for k in pm)
+    bm, bt = dict(m.named_buffers()), dict(twin.named_buffers())
+    assert set(bm) == set(bt) and all(bm[k] is bt[k] for k in bm)
+    assert not any(p.is_meta for p in twin.parameters()) and not any(b.is_meta for b in twin.buffers())
+    before = twin._signature()
+    m.load_state_dict(O.make_state_dict(seed=5), strict=True)
+    assert twin._signature() != before and twin._signature() == m._signature()
+    eng.model = KGnet.resnet50(pretrained=False).eval()
+    assert eng._slot(0)["model"] is eng.model and eng._slot(1)["model"] is not twin
+    eng._slots[1]["pending"] = {"fake": True}
+    eng.model = m
+    with pytest.raises(RuntimeError):
+        eng._slot(0)
