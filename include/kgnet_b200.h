@@ -250,6 +250,13 @@ int kg_detection_loss_backward(const float* d_pr_kp, const float* d_pr_short, co
 int kg_seg_loss_pairs_backward(const float* d_masks, const void* d_pairs, int n_pairs, const float* d_gt_masks, int H, int W,
                                const float* d_pair_coeff, float* d_grad_masks, void* stream);
 
+/* torch.optim.Adam.step() of the reference's training loop (train.py:71,154; PyTorch defaults: no weight decay, no amsgrad) for ALL
+ * parameter tensors in one launch.  d_tensors: records { float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+ * int64 numel; } (40 bytes); d_chunks: n_chunks records { int32 tensor; int32 pad; int64 start; } covering every tensor in pieces of
+ * at most 65536 elements; step = the 1-based step count of these tensors (bias correction). */
+int kg_adam_step(const void* d_tensors, const void* d_chunks, int n_chunks, float lr, float beta1, float beta2, float eps, int step,
+                 void* stream);
+
 /* Test hook (host only, no GPU needed): the first-fit placement by liveness that lays out the activation workspace of forward_dec.
  * Buffer b (bytes[b]) is first written by op def[b] and last read by op last[b] (last[b] >= n_ops: never released); a buffer may reuse
  * memory released by ops < def[b] only.  Writes the byte offsets and the arena size. */

@@ -116,6 +116,8 @@ def _bind_net(L):
     L.kg_detection_loss_backward.argtypes = [vp, vp, vp, vp, ci, ci, ci, C.c_float, vp, vp, vp, vp, vp, vp]
     L.kg_seg_loss_pairs_backward.restype = ci
     L.kg_seg_loss_pairs_backward.argtypes = [vp, vp, ci, vp, ci, ci, vp, vp, vp]
+    L.kg_adam_step.restype = ci
+    L.kg_adam_step.argtypes = [vp, vp, ci, C.c_float, C.c_float, C.c_float, C.c_float, ci, vp]
     L.kg_debug_place_by_liveness.restype = ci
     L.kg_debug_place_by_liveness.argtypes = [ci, ci, vp, vp, vp, vp, vp]
     L.kg_tc_available.restype = ci
@@ -132,7 +134,7 @@ EXPORTS = ["kg_last_error", "kg_abi_version", "kg_device_arch", "kg_decode_works
            "kg_net_create", "kg_net_destroy", "kg_net_set_conv", "kg_net_finalize", "kg_net_workspace_bytes", "kg_net_forward_dec", "kg_net_forward_dec_u8",
            "kg_net_import_feats", "kg_net_seg_prepare", "kg_net_forward_seg", "kg_conv2d_nchw", "kg_heads_l2_nchw", "kg_net_plan_info", "kg_tc_available", "kg_tc_status",
            "kg_preprocess_u8", "kg_paste_masks", "kg_encode_ground_truth", "kg_detection_loss", "kg_seg_loss_pairs",
-           "kg_detection_loss_backward", "kg_seg_loss_pairs_backward", "kg_debug_place_by_liveness"]
+           "kg_detection_loss_backward", "kg_seg_loss_pairs_backward", "kg_debug_place_by_liveness", "kg_adam_step"]
 
 
 def timing_enable(on=True):

@@ -228,3 +228,36 @@ def test_training_step_through_an_autograd_network():
         assert float(crit(net_a(x), gt)) < first
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_fused_adam_matches_torch_adam():
+    """optim.Adam (ONE launch for all tensors) against torch.optim.Adam on the CPU (train.py:71,154): parameters and both moment
+    buffers after several steps, an lr scheduler in between, one parameter that skips a step (its own step count must not advance),
+    tensors larger than one 65 536-element chunk."""
+    from kg_instance_segmentation_b200 import optim
+    torch.manual_seed(0)
+    shapes = [(64, 3, 7, 7), (64,), (300, 257), (1,), (70000,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    dev_p = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref_p]
+    ref_o = torch.optim.Adam(ref_p, lr=1e-2)
+    dev_o = optim.Adam(dev_p, lr=1e-2)
+    ref_s = torch.optim.lr_scheduler.ExponentialLR(ref_o, gamma=0.96)
+    dev_s = torch.optim.lr_scheduler.ExponentialLR(dev_o, gamma=0.96)
+    for it in range(6):
+        for i, (a, b) in enumerate(zip(ref_p, dev_p)):
+            if i == 3 and it == 2:
+                a.grad = None; b.grad = None                       # this parameter sits out one step
+                continue
+            g = torch.randn(shapes[i]) * (10.0 ** (it - 3))        # gradients over six orders of magnitude
+            a.grad = g.clone(); b.grad = g.clone().cuda()
+        ref_o.step(); dev_o.step()
+        ref_s.step(); dev_s.step()
+        for i, (a, b) in enumerate(zip(ref_p, dev_p)):
+            np.testing.assert_allclose(b.detach().cpu().numpy(), a.detach().numpy(), rtol=2e-6, atol=1e-7, err_msg=f"param {i} step {it}")
+            np.testing.assert_allclose(dev_o.state[b]["exp_avg"].cpu().numpy(), ref_o.state[a]["exp_avg"].numpy(), rtol=2e-6, atol=1e-12)
+            np.testing.assert_allclose(dev_o.state[b]["exp_avg_sq"].cpu().numpy(), ref_o.state[a]["exp_avg_sq"].numpy(), rtol=2e-6, atol=1e-20)
+    assert dev_o.state[dev_p[3]]["step"] == 5 and dev_o.state[dev_p[0]]["step"] == 6
+    cpu_p = torch.nn.Parameter(torch.zeros(3))
+    cpu_p.grad = torch.zeros(3)
+    with pytest.raises(RuntimeError):
+        optim.Adam([cpu_p], lr=1e-3).step()                    # no CPU fallback
