@@ -254,7 +254,7 @@ int kg_seg_loss_pairs_backward(const float* d_masks, const void* d_pairs, int n_
  * parameter tensors in one launch.  d_tensors: records { float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
  * int64 numel; } (40 bytes); d_chunks: n_chunks records { int32 tensor; int32 pad; int64 start; } covering every tensor in pieces of
  * at most 65536 elements; step = the 1-based step count of these tensors (bias correction). */
-int kg_adam_step(const void* d_tensors, const void* d_chunks, int n_chunks, float lr, float beta1, float beta2, float eps, int step,
+int kg_adam_step(const void* d_tensors, const void* d_chunks, int n_chunks, double lr, double beta1, double beta2, double eps, int step,
                  void* stream);
 
 /* Test hook (host only, no GPU needed): the first-fit placement by liveness that lays out the activation workspace of forward_dec.

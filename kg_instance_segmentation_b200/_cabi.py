@@ -117,7 +117,7 @@ def _bind_net(L):
     L.kg_seg_loss_pairs_backward.restype = ci
     L.kg_seg_loss_pairs_backward.argtypes = [vp, vp, ci, vp, ci, ci, vp, vp, vp]
     L.kg_adam_step.restype = ci
-    L.kg_adam_step.argtypes = [vp, vp, ci, C.c_float, C.c_float, C.c_float, C.c_float, ci, vp]
+    L.kg_adam_step.argtypes = [vp, vp, ci, C.c_double, C.c_double, C.c_double, C.c_double, ci, vp]
     L.kg_debug_place_by_liveness.restype = ci
     L.kg_debug_place_by_liveness.argtypes = [ci, ci, vp, vp, vp, vp, vp]
     L.kg_tc_available.restype = ci

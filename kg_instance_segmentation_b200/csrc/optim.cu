@@ -38,19 +38,20 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const AdamTensor* __rest
 
 using namespace kg;
 
-extern "C" int kg_adam_step(const void* d_tensors, const void* d_chunks, int n_chunks, float lr, float beta1, float beta2, float eps,
+extern "C" int kg_adam_step(const void* d_tensors, const void* d_chunks, int n_chunks, double lr, double beta1, double beta2, double eps,
                             int step, void* stream) {
-  KG_REQUIRE(n_chunks >= 0 && step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
+  KG_REQUIRE(n_chunks >= 0 && step >= 1 && lr >= 0. && beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0.,
              "kg_adam_step: bad arguments (step=%d lr=%g betas=(%g, %g) eps=%g)", step, lr, beta1, beta2, eps);
   if (n_chunks == 0) return KG_OK;
   KG_REQUIRE(d_tensors && d_chunks, "kg_adam_step: null table");
-  // bias corrections in double like the Python scalars of torch/optim/adam.py, rounded to fp32 where they meet the tensors
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
+  // the hyper-parameters are Python floats (doubles) in torch/optim/adam.py: 1 - beta and the bias corrections are formed in double
+  // and rounded to fp32 only where they meet the tensors (1 - 0.999f differs from float(1 - 0.999) by 1.3e-5)
+  const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
   const float inv_bc2_sqrt = 1.f / (float)std::sqrt(bc2);
   adam_step_kernel<<<(unsigned)n_chunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const AdamTensor*>(d_tensors),
-                                                                         reinterpret_cast<const AdamChunk*>(d_chunks), 1.f - beta1, beta2,
-                                                                         1.f - beta2, step_size, inv_bc2_sqrt, eps);
+                                                                         reinterpret_cast<const AdamChunk*>(d_chunks), (float)(1.0 - beta1),
+                                                                         (float)beta2, (float)(1.0 - beta2), step_size, inv_bc2_sqrt, (float)eps);
   KG_CUDA_CHECK(cudaGetLastError());
   return KG_OK;
 }
