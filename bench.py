@@ -591,22 +591,85 @@ def cpu_baseline_decode(base, budget_s=12.0):
             "sample": f"{n} image(s) of the same planted 512x512 workload, NumPy oracle decode (oracle/kg_oracle.py), single thread"}
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  /root/reference is pure Python and cannot
-    travel to the GPU box, so this times the oracle port (bit-exact restatement, tests/test_oracle_vs_reference.py)."""
+def reference_modules():
+    """The UNMODIFIED reference modules (KGnet, postprocessing, nms) when they can be imported: from baseline/_ref/ (git-ignored copy
+    made by baseline/fetch_ref.py; it travels to the GPU box) or /root/reference (this container); None otherwise."""
+    import importlib
+    for d in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if all(os.path.exists(os.path.join(d, f)) for f in ("KGnet.py", "postprocessing.py", "nms.py", "config.py")):
+            sys.dont_write_bytecode = True
+            sys.path.insert(0, d)
+            try:
+                for name in ("config", "nms", "postprocessing", "KGnet"):
+                    sys.modules.pop(name, None)
+                mods = tuple(importlib.import_module(n) for n in ("KGnet", "postprocessing", "nms"))
+                if os.path.dirname(os.path.abspath(mods[0].__file__)) == os.path.abspath(d):
+                    return mods + (d,)
+            except Exception:
+                pass
+            finally:
+                sys.path.remove(d)
+    return None
+
+
+def reference_pipeline(mods, base, n_images, warm=0):
+    """test.py:88-125 with the reference's own functions on host cores, one image at a time: forward_dec (torch fp32 CPU) -> 4 x
+    get_skeletons_and_masks -> refine_skeleton -> gather_skeleton -> NMS -> forward_seg.  Like the own arm, the decode is fed the
+    planted head maps (teacher-forced decode load); weights = the same seeded state dict."""
     import torch
-    from oracle import kg_oracle as O
+    from kg_instance_segmentation_b200 import synthetic
+    KG, PP, NMS, where = mods
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = KG.resnet50(pretrained=False)
+    model.load_state_dict(synthetic.make_state_dict(seed=0), strict=True)
+    model.eval()
+    torch.manual_seed(0)
+    xs = torch.rand(max(1, n_images), 3, HW_IN, HW_IN) - 0.5
+
+    def one(i):
+        with torch.no_grad():
+            out = model.forward_dec(xs[i % len(xs)][None])
+        heads = base[i % len(base)]
+        sk = [PP.refine_skeleton(PP.get_skeletons_and_masks(*[torch.from_numpy(a[None]) for a in heads[s]])) for s in range(4)]
+        boxes = NMS.non_maximum_suppression_numpy(PP.gather_skeleton(*sk), nms_thresh=0.5)
+        if boxes is not None:
+            with torch.no_grad():
+                model.forward_seg(out[4], [boxes])
+
+    for i in range(warm):
+        one(i)
+    t0 = time.time()
+    for i in range(n_images):
+        one(i)
+    dt = time.time() - t0
+    return {"value": round(n_images / dt, 4), "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{n_images} image(s) {HW_IN}x{HW_IN} of the same workload, bs=1 like test.py, through the UNMODIFIED reference modules "
+                      f"({where}): forward_dec on {cores} threads + get_skeletons_and_masks x4 + refine + gather + NMS + forward_seg",
+            "seconds": round(dt, 2)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores -- the unmodified reference modules when
+    they are importable (baseline/_ref/ or /root/reference), else the oracle port (bit-exact restatement,
+    tests/test_oracle_vs_reference.py)."""
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     base, _ = planted_batch(n_distinct=2)
     steps = min(args.steps, 6)           # bounded: ~5 s of CPU work per step
-    r = cpu_pipeline(base, n_images=steps, warm=min(args.warmup, 1))
+    mods = reference_modules()
+    if mods is not None:
+        r = reference_pipeline(mods, base, n_images=steps, warm=min(args.warmup, 1))
+    else:
+        r = cpu_pipeline(base, n_images=steps, warm=min(args.warmup, 1))
     v = r["value"]
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32 (torch CPU) + fp64 decode", "data": "synthetic",
             "config": {"workload": "same path as the own arm, one 512x512 image per step (the reference is batch-size-1 by construction, "
-                                   "postprocessing.py:138-140); oracle port of the reference (pure-Python reference cannot travel to the GPU box)",
+                                   "postprocessing.py:138-140); " + ("unmodified reference modules" if r["kind"] == "reference"
+                                                                     else "oracle port of the reference (reference modules not importable)"),
                        "global_batch": 1},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
