@@ -595,6 +595,8 @@ def reference_modules():
     """The UNMODIFIED reference modules (KGnet, postprocessing, nms) when they can be imported: from baseline/_ref/ (git-ignored copy
     made by baseline/fetch_ref.py; it travels to the GPU box) or /root/reference (this container); None otherwise."""
     import importlib
+    if os.environ.get("KG_REFERENCE_PORT"):          # force the oracle port (what a GPU box without the reference runs)
+        return None
     for d in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
         if all(os.path.exists(os.path.join(d, f)) for f in ("KGnet.py", "postprocessing.py", "nms.py", "config.py")):
             sys.dont_write_bytecode = True

@@ -8,9 +8,17 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_prints_one_json_line():
+import pytest
+
+
+@pytest.mark.parametrize("force_port", [False, True])
+def test_reference_arm_prints_one_json_line(force_port):
+    """Unmodified reference modules where /root/reference (or baseline/_ref) exists, the oracle port otherwise / when forced."""
+    env = dict(os.environ)
+    if force_port:
+        env["KG_REFERENCE_PORT"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -19,7 +27,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    have_ref = os.path.exists("/root/reference/KGnet.py") or os.path.exists(os.path.join(ROOT, "baseline", "_ref", "KGnet.py"))
+    assert cb["kind"] == ("reference" if have_ref and not force_port else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert "workload" in d["config"]
 
 
